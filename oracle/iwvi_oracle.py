@@ -248,11 +248,20 @@ def sample_conditional_2d(Xnew, Z, kern, f, *, full_cov=False, q_sqrt=None, whit
                           jitter=JITTER):
     """gpflow.conditionals.sample_conditional on 2-D inputs (temp_workaround.py:134,157): the same
     algebra as above without the leading S axis (GPflow base_conditional).
-    Xnew [N,D] -> sample/mean [N,R], var [N,R] or [R,N,N]."""
-    s, m, v = independent_multisample_sample_conditional(
-        Xnew[None], Z, kern, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white,
-        eps=None if eps is None else eps[None], jitter=jitter)
-    return (None if s is None else s[0]), m[0], v[0]
+    Xnew [N,D] -> sample/mean [N,R], var [N,R] or [R,N,N].  With full_cov GPflow's _sample_mvn draws
+    jointly over N: mean + chol(cov + jitter*I) eps  (GPflow adds jitter there)."""
+    _, m, v = independent_multisample_sample_conditional(
+        Xnew[None], Z, kern, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white, eps=None, jitter=jitter)
+    m, v = m[0], v[0]
+    if eps is None:
+        return None, m, v
+    if full_cov:
+        N = Xnew.shape[0]
+        chol = torch.linalg.cholesky(v + jitter * torch.eye(N, dtype=v.dtype))   # [R,N,N]
+        s = m + (chol @ eps.t()[:, :, None])[:, :, 0].t()
+    else:
+        s = m + eps * v ** 0.5
+    return s, m, v
 
 
 class Mok:
