@@ -1,0 +1,279 @@
+// common.cuh -- device building blocks shared by the sm_100a IW-ELBO kernels.
+//
+// * DMMA: on sm_100a every f64 mma.sync shape lowers to DMMA.8x8x4 (checked with cuobjdump), so m8n8k4 is used
+//   directly; tcgen05/TMEM has no f64 kind.  Measured pipe peak on B200: 37.05 TFLOP/s (profiles/FP64_PEAK_r01.md).
+// * staging: 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) global->shared with mbarrier transaction counting.
+// * shared-memory operand layouts use leading dimensions == 4 (mod 16) doubles, which makes every DMMA fragment
+//   load (8 rows x 4 k, one double per lane) conflict-free per half-warp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/iwvi_b200.h"
+
+#define IWVI_BLK 64            // block size of the blocked triangular algorithms
+#define IWVI_LDS 68            // leading dimension of a staged 64x64 block in shared memory (== 4 mod 16)
+#define IWVI_STAGE_DOUBLES (IWVI_BLK * IWVI_LDS)
+
+__host__ __device__ inline int iwvi_round_up(int x, int m) { return (x + m - 1) / m * m; }
+// leading dimension of length-scaled inputs (Zt rows in aux, x tile in smem): == 4 (mod 16), >= round_up(D,4)
+__host__ __device__ inline int iwvi_ldz(int D) { return D <= 20 ? 20 : 36; }
+
+// ---------------------------------------------------------------------------------------------
+// aux layout (doubles), written by the prologue, read by the row kernels
+// ---------------------------------------------------------------------------------------------
+struct AuxLayout {
+  int Mp, NB, ldz, R;
+  int64_t off_dinv, off_lqp, off_zt, off_zn, off_qmu, off_consts, total;
+};
+__host__ __device__ inline AuxLayout iwvi_aux_layout(int M, int D, int R) {
+  AuxLayout a;
+  a.Mp = iwvi_round_up(M, IWVI_BLK);
+  a.NB = a.Mp / IWVI_BLK;
+  a.ldz = iwvi_ldz(D);
+  a.R = R;
+  int64_t o = 0;
+  a.off_dinv = o;   o += (int64_t)a.NB * IWVI_BLK * IWVI_BLK;   // inverted diagonal blocks of Lm
+  a.off_lqp = o;    o += (int64_t)R * a.Mp * a.Mp;              // tril(q_sqrt), zero padded
+  a.off_zt = o;     o += (int64_t)a.Mp * a.ldz;                 // Z / ls, zero padded
+  a.off_zn = o;     o += a.Mp;                                  // |Z/ls|^2
+  a.off_qmu = o;    o += (int64_t)a.Mp * IWVI_MAX_R;            // q_mu padded to [Mp, 8]
+  a.off_consts = o; o += 64;                                    // [0]=variance, [1..32]=1/ls[d] at [8+d], see below
+  a.total = o;
+  return a;
+}
+#define IWVI_C_VARIANCE 0
+#define IWVI_C_INVLS 8   // consts[8 + d] = 1 / ls[d], d < 32
+
+// save layout (doubles): A_T [Tp, ldA], U_T [R, Tp, ldA], gvar [T, R], gmean [T, R]; Tp = T rounded up to 128,
+// rows T..Tp-1 are written as zeros by the forward kernel so that whole 64-row blocks can be bulk-copied.
+struct SaveLayout { int64_t off_a, off_u, off_gvar, off_gmean, total; int ldA; int Tp; };
+__host__ __device__ inline SaveLayout iwvi_save_layout(int T, int M, int R) {
+  SaveLayout s;
+  s.ldA = iwvi_round_up(M, IWVI_BLK) + 4;
+  s.Tp = iwvi_round_up(T, 128);
+  int64_t o = 0;
+  s.off_a = o;     o += (int64_t)s.Tp * s.ldA;
+  s.off_u = o;     o += (int64_t)R * s.Tp * s.ldA;
+  s.off_gvar = o;  o += (int64_t)T * R;
+  s.off_gmean = o; o += (int64_t)T * R;
+  s.total = o;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DMMA m8n8k4 and the warp-level tile product
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// acc[TM][TN][2] += A(m,k) * B(k,n),  m in [0, 8*TM), n in [0, 8*TN), k in [0, KC), KC % 4 == 0.
+//   ALAY == 0: A(m,k) = As[m*lda + k]      ALAY == 1: A(m,k) = As[k*lda + m]
+//   BLAY == 0: B(k,n) = Bs[n*ldb + k]      BLAY == 1: B(k,n) = Bs[k*ldb + n]
+// accumulator element acc[i][j][c] is C(8*i + lane/4, 8*j + 2*(lane%4) + c).
+template <int TM, int TN, int ALAY, int BLAY>
+__device__ __forceinline__ void warp_gemm(double (&acc)[TM][TN][2], const double* __restrict__ As, int lda,
+                                          const double* __restrict__ Bs, int ldb, int KC, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const double* ap = ALAY == 0 ? As + g * lda + t : As + t * lda + g;
+  const double* bp = BLAY == 0 ? Bs + g * ldb + t : Bs + t * ldb + g;
+#pragma unroll 2
+  for (int k0 = 0; k0 < KC; k0 += 4) {
+    double a[TM], b[TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++) a[i] = ALAY == 0 ? ap[i * 8 * lda + k0] : ap[k0 * lda + i * 8];
+#pragma unroll
+    for (int j = 0; j < TN; j++) b[j] = BLAY == 0 ? bp[j * 8 * ldb + k0] : bp[k0 * ldb + j * 8];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++) dmma884(acc[i][j], a[i], b[j]);
+  }
+}
+
+template <int TM, int TN>
+__device__ __forceinline__ void acc_zero(double (&acc)[TM][TN][2]) {
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk TMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+// 1-D bulk copy global -> shared, completion signalled on `bar` (bytes % 16 == 0, both addresses 16B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// A 2-deep (NST) ring of 64-row blocks filled by warp 0 with bulk TMA; arrival through mbarriers,
+// release through the block-wide barrier that the algorithms need anyway between dependent steps.
+#define IWVI_NST 2
+struct BlockSrc { const double* src; int row_bytes; int src_stride; int dst_stride; };
+
+template <int NST>
+struct StagePipeT {
+  uint64_t* bars;   // [NST]
+  double* stages;   // [NST][IWVI_STAGE_DOUBLES]
+  uint32_t it_c;    // blocks consumed so far (uniform across the CTA)
+  uint32_t it_p;    // blocks produced so far (meaningful in warp 0)
+
+  __device__ __forceinline__ void setup(uint64_t* b, double* s) {
+    bars = b; stages = s; it_c = 0; it_p = 0;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  // warp 0 only (all 32 lanes): issue one block into the next stage
+  __device__ __forceinline__ void produce(const BlockSrc& b, int lane) {
+    const uint32_t s = it_p % NST;
+    uint64_t* bar = &bars[s];
+    double* dst = stages + (size_t)s * IWVI_STAGE_DOUBLES;
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(IWVI_BLK * b.row_bytes));
+    __syncwarp();
+#pragma unroll
+    for (int r = lane; r < IWVI_BLK; r += 32)
+      bulk_g2s(dst + (size_t)r * b.dst_stride, b.src + (size_t)r * b.src_stride, (uint32_t)b.row_bytes, bar);
+    it_p++;
+  }
+  // all threads: wait for the oldest outstanding block, return its stage
+  __device__ __forceinline__ const double* wait() {
+    const uint32_t s = it_c % NST;
+    mbar_wait(&bars[s], (it_c / NST) & 1u);
+    return stages + (size_t)s * IWVI_STAGE_DOUBLES;
+  }
+  // all threads: the block returned by the last wait() is no longer needed.  Contains a __syncthreads().
+  // `seq` is the producer's block sequence (only warp 0's copy is used/advanced).
+  template <class Seq>
+  __device__ __forceinline__ void release(Seq& seq, int warp, int lane) {
+    __syncthreads();
+    it_c++;
+    if (warp == 0 && !seq.done()) {
+      produce(seq.get(), lane);
+      seq.advance();
+    }
+  }
+  // all threads: wait for the block `k` positions after the oldest outstanding one (k < NST)
+  __device__ __forceinline__ const double* wait_ahead(uint32_t k) {
+    const uint32_t it = it_c + k;
+    const uint32_t s = it % NST;
+    mbar_wait(&bars[s], (it / NST) & 1u);
+    return stages + (size_t)s * IWVI_STAGE_DOUBLES;
+  }
+  // all threads: the n oldest blocks are no longer needed (one __syncthreads())
+  template <class Seq>
+  __device__ __forceinline__ void release_n(Seq& seq, int n, int warp, int lane) {
+    __syncthreads();
+    it_c += n;
+    if (warp == 0) {
+      for (int i = 0; i < n && !seq.done(); i++) {
+        produce(seq.get(), lane);
+        seq.advance();
+      }
+    }
+  }
+  // all threads, at the start of a tile (after a __syncthreads): prime the ring from a fresh sequence
+  template <class Seq>
+  __device__ __forceinline__ void prime(Seq& seq, int warp, int lane) {
+    if (warp == 0) {
+      for (int i = 0; i < NST && !seq.done(); i++) {
+        produce(seq.get(), lane);
+        seq.advance();
+      }
+    }
+  }
+};
+typedef StagePipeT<IWVI_NST> StagePipe;
+
+// ---------------------------------------------------------------------------------------------
+// stationary kernels (GPflow 1.x formulas): K(r2) and dK/dr2
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double kern_k(int kind, double r2, double variance) {
+  if (kind == IWVI_KERN_RBF) return variance * exp(-0.5 * r2);
+  const double r = sqrt(fmax(r2, 1e-40));
+  if (kind == IWVI_KERN_MATERN52) {
+    const double s5 = 2.23606797749978969641;
+    return variance * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * exp(-s5 * r);
+  }
+  if (kind == IWVI_KERN_MATERN32) {
+    const double s3 = 1.73205080756887729353;
+    return variance * (1.0 + s3 * r) * exp(-s3 * r);
+  }
+  return variance * exp(-r);
+}
+__device__ __forceinline__ void kern_k_dk(int kind, double r2, double variance, double& K, double& dK) {
+  if (kind == IWVI_KERN_RBF) { K = variance * exp(-0.5 * r2); dK = -0.5 * K; return; }
+  const bool clamped = r2 < 1e-40;
+  const double r = sqrt(fmax(r2, 1e-40));
+  if (kind == IWVI_KERN_MATERN52) {
+    const double s5 = 2.23606797749978969641;
+    const double e = exp(-s5 * r);
+    K = variance * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
+    dK = -(5.0 / 6.0) * variance * (1.0 + s5 * r) * e;
+  } else if (kind == IWVI_KERN_MATERN32) {
+    const double s3 = 1.73205080756887729353;
+    const double e = exp(-s3 * r);
+    K = variance * (1.0 + s3 * r) * e;
+    dK = -1.5 * variance * e;
+  } else {
+    const double e = exp(-r);
+    K = variance * e;
+    dK = -variance * e / (2.0 * r);
+  }
+  if (clamped) dK = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum, result valid in thread 0; `red` is >= 32 doubles of shared memory
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; i++) s += red[i];
+  }
+  return s;
+}
+
+int iwvi_check_gp_desc(const iwvi_gp_desc* d);
+
+#define IWVI_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return IWVI_ERR_LAUNCH; } while (0)

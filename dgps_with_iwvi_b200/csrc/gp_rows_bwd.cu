@@ -1,0 +1,837 @@
+// gp_rows_bwd.cu -- adjoint of the per-point stage (gp_rows_fwd.cu).  The reference obtains it from tf.gradients
+// through temp_workaround.py:44-91,142-145 and layers.py:46-48; the formulas are derived in DESIGN.md and checked
+// against autograd in tests/test_staged.py.
+//
+// Four launches:
+//   1 gp_epi_bwd_kernel   per point: un-mix the cotangents (gmean_bar, gvar_bar), mean-function part of dX,
+//                         partial sums of dW / dmfA / dmfb / dvariance.
+//   2 gp_tile_bwd_kernel  persistent, one tile of TP points per CTA iteration, shared-memory resident panel:
+//        Abar  = q_mu gmean_bar^T - 2 A (sum_r gvar_bar_r) + 2 sum_r tril(Lq_r) (U_r * gvar_bar_r)
+//        Bbar  = Lm^-T Abar                              (blocked back substitution, in place; stored for 3)
+//        G     = Bbar * dK/dr2 ; dX += 2/ls (x~ colsum(G) - G^T z~) ; dZ, dls, dvariance partials per CTA
+//   3 gp_reduce_bwd_kernel  contractions over the T points, split-K, one 64x64 output block per CTA:
+//        dLq_r = 2 tril(A diag(gvar_bar_r) U_r^T),  dLm = -tril(Bbar A^T),  dq_mu = A gmean_bar
+//   4 gp_finalize_bwd_kernel  fixed-order sums of all partials (deterministic; no floating-point atomics to HBM).
+#include "common.cuh"
+
+namespace {
+
+template <int TP> struct TileCfg {
+  static constexpr int NW = 8;
+  static constexpr int WNG = TP >= 64 ? 4 : 2;
+  static constexpr int WMG = NW / WNG;
+  static constexpr int WM = IWVI_BLK / WMG;
+  static constexpr int WN = TP / WNG;
+  static constexpr int TM = WM / 8;
+  static constexpr int TN = WN / 8;
+};
+
+#define EPI_STRIDE 1344   // >= P*R + D*P + P + 1 at the maxima (32*8 + 32*32 + 32 + 1 = 1313)
+#define EPI_PTS 256
+#define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
+
+struct BwdWs {   // workspace layout (doubles)
+  int64_t off_bbar, off_gmb, off_gvb, off_epi, off_tile, off_red, off_qred, total;
+  int Tp, ldA, n_epi, grid_tile, S, npairs, chunks_per_split, tile_stride;
+};
+__host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
+  BwdWs w;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
+  w.Tp = sv.Tp; w.ldA = sv.ldA;
+  w.n_epi = (w.Tp + EPI_PTS - 1) / EPI_PTS;
+  w.grid_tile = nsm;
+  w.npairs = al.NB * (al.NB + 1) / 2;
+  const int nchunks = w.Tp / IWVI_BLK;
+  const int items = (d.R + 1) * w.npairs;
+  int S = (3 * nsm + items - 1) / items;
+  if (S > nchunks) S = nchunks;
+  if (S < 1) S = 1;
+  w.chunks_per_split = (nchunks + S - 1) / S;
+  w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
+  w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
+  int64_t o = 0;
+  w.off_bbar = o; o += (int64_t)w.Tp * w.ldA;
+  w.off_gmb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
+  w.off_gvb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
+  w.off_epi = o;  o += (int64_t)w.n_epi * EPI_STRIDE;
+  w.off_tile = o; o += (int64_t)w.grid_tile * w.tile_stride;
+  w.off_red = o;  o += (int64_t)(d.R + 1) * w.S * w.npairs * IWVI_BLK * IWVI_BLK;
+  w.off_qred = o; o += (int64_t)w.S * al.NB * IWVI_BLK * IWVI_MAX_R;
+  w.total = o;
+  return w;
+}
+
+struct BwdParams {
+  iwvi_gp_desc d;
+  const double *Lm, *aux, *save, *X, *W, *mfA, *mfb, *eps, *d_sample, *d_mean, *d_var;
+  double *dX, *dZ, *dls, *dvariance, *dq_mu, *dq_sqrt, *dLm, *dW, *dmfA, *dmfb, *ws;
+  BwdWs wl;
+  int ntiles, grid_tile;
+};
+
+// ------------------------------------------------------------------------------------------------
+// 1. per-point epilogue adjoint
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EPI_PTS) gp_epi_bwd_kernel(const BwdParams p) {
+  __shared__ double red[32];
+  const iwvi_gp_desc& d = p.d;
+  const int T = d.T, R = d.R, P = d.P, D = d.D;
+  const SaveLayout sv = iwvi_save_layout(T, d.M, R);
+  const bool sampled = (d.flags & IWVI_FLAG_SAMPLE) != 0;
+  const double* gvar = p.save + sv.off_gvar;
+  const double* gmean = p.save + sv.off_gmean;
+  double* gmb = p.ws + p.wl.off_gmb;
+  double* gvb = p.ws + p.wl.off_gvb;
+  const int p0 = blockIdx.x * EPI_PTS;
+  const int pt = p0 + threadIdx.x;
+  double gv_sum = 0.0;
+  if (pt < p.wl.Tp) {
+    double om[IWVI_MAX_R], ov[IWVI_MAX_R];
+#pragma unroll
+    for (int r = 0; r < IWVI_MAX_R; r++) { om[r] = 0.0; ov[r] = 0.0; }
+    if (pt < T) {
+      for (int r = 0; r < R; r++) {
+        double gsb = 0.0, gm_ = 0.0, gv_ = 0.0;
+        if (d.mix) {
+          for (int q = 0; q < P; q++) {
+            const double w = p.W[q * R + r];
+            const double s_ = p.d_sample ? p.d_sample[(size_t)pt * P + q] : 0.0;
+            const double m_ = p.d_mean ? p.d_mean[(size_t)pt * P + q] : 0.0;
+            const double v_ = p.d_var ? p.d_var[(size_t)pt * P + q] : 0.0;
+            gsb += s_ * w; gm_ += m_ * w; gv_ += v_ * w * w;
+          }
+        } else {
+          gsb = p.d_sample ? p.d_sample[(size_t)pt * P + r] : 0.0;
+          gm_ = p.d_mean ? p.d_mean[(size_t)pt * P + r] : 0.0;
+          gv_ = p.d_var ? p.d_var[(size_t)pt * P + r] : 0.0;
+        }
+        gm_ += gsb;
+        if (sampled) gv_ += gsb * p.eps[(size_t)pt * R + r] / (2.0 * sqrt(gvar[(size_t)pt * R + r]));
+        om[r] = gm_; ov[r] = gv_; gv_sum += gv_;
+      }
+      // mean-function part of dX (the gram part is added by the tile kernel)
+      for (int k = 0; k < D; k++) {
+        double v = 0.0;
+        if (d.mf == IWVI_MF_IDENTITY) {
+          v = (p.d_sample ? p.d_sample[(size_t)pt * P + k] : 0.0) + (p.d_mean ? p.d_mean[(size_t)pt * P + k] : 0.0);
+        } else if (d.mf == IWVI_MF_LINEAR) {
+          for (int q = 0; q < P; q++) {
+            const double dmf = (p.d_sample ? p.d_sample[(size_t)pt * P + q] : 0.0) +
+                               (p.d_mean ? p.d_mean[(size_t)pt * P + q] : 0.0);
+            v += dmf * p.mfA[k * P + q];
+          }
+        }
+        p.dX[(size_t)pt * D + k] = v;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < IWVI_MAX_R; r++) {
+      gmb[(size_t)pt * IWVI_MAX_R + r] = om[r];
+      gvb[(size_t)pt * IWVI_MAX_R + r] = ov[r];
+    }
+  }
+  double* part = p.ws + p.wl.off_epi + (size_t)blockIdx.x * EPI_STRIDE;
+  const double tot = block_sum(gv_sum, red);
+  if (threadIdx.x == 0) part[P * R + D * P + P] = tot;
+  // partial sums over this block's points of dW, dmfA, dmfb
+  const int p1 = min(p0 + EPI_PTS, T);
+  const int nW = (d.mix && p.dW) ? P * R : 0;
+  const int nA = (d.mf == IWVI_MF_LINEAR && p.dmfA) ? D * P : 0;
+  const int nb = (d.mf == IWVI_MF_LINEAR && p.dmfb) ? P : 0;
+  for (int e = threadIdx.x; e < P * R + D * P + P; e += blockDim.x) {
+    double s = 0.0;
+    if (e < P * R) {
+      if (nW) {
+        const int q = e / R, r = e - q * R;
+        const double w = p.W[q * R + r];
+        for (int n = p0; n < p1; n++) {
+          const double gvv = gvar[(size_t)n * R + r], gmm = gmean[(size_t)n * R + r];
+          const double s_ = p.d_sample ? p.d_sample[(size_t)n * P + q] : 0.0;
+          const double m_ = p.d_mean ? p.d_mean[(size_t)n * P + q] : 0.0;
+          const double v_ = p.d_var ? p.d_var[(size_t)n * P + q] : 0.0;
+          const double gss = sampled ? gmm + p.eps[(size_t)n * R + r] * sqrt(gvv) : 0.0;
+          s += s_ * gss + m_ * gmm + 2.0 * v_ * w * gvv;
+        }
+      }
+    } else if (e < P * R + D * P) {
+      if (nA) {
+        const int e2 = e - P * R;
+        const int k = e2 / P, q = e2 - k * P;
+        for (int n = p0; n < p1; n++) {
+          const double dmf = (p.d_sample ? p.d_sample[(size_t)n * P + q] : 0.0) +
+                             (p.d_mean ? p.d_mean[(size_t)n * P + q] : 0.0);
+          s += p.X[(size_t)n * D + k] * dmf;
+        }
+      }
+    } else if (nb) {
+      const int q = e - P * R - D * P;
+      for (int n = p0; n < p1; n++)
+        s += (p.d_sample ? p.d_sample[(size_t)n * P + q] : 0.0) + (p.d_mean ? p.d_mean[(size_t)n * P + q] : 0.0);
+    }
+    part[e] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. tile kernel
+// ------------------------------------------------------------------------------------------------
+struct BwdSeq {
+  int NB, R, Mp, ldz;
+  const double *Zt, *Lm, *Dinv, *Lqp;
+  int ph, r, i, j;
+  __device__ __forceinline__ void init() { ph = 0; r = 0; i = 0; j = 0; }
+  __device__ __forceinline__ bool done() const { return ph == 3; }
+  __device__ __forceinline__ BlockSrc get() const {
+    BlockSrc b;
+    b.row_bytes = IWVI_BLK * 8; b.dst_stride = IWVI_LDS;
+    if (ph == 0) {           // tril(q_sqrt_r) block (row block i, col block j), i >= j
+      b.src = Lqp + (size_t)r * Mp * Mp + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK; b.src_stride = Mp;
+    } else if (ph == 1) {    // Lm block (row block j, col block i), j > i; j == NB: inverted diagonal block i
+      if (j < NB) { b.src = Lm + (size_t)(j * IWVI_BLK) * Mp + i * IWVI_BLK; b.src_stride = Mp; }
+      else        { b.src = Dinv + (size_t)i * IWVI_BLK * IWVI_BLK; b.src_stride = IWVI_BLK; }
+    } else {                 // scaled inducing inputs, block i
+      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.row_bytes = ldz * 8; b.src_stride = ldz; b.dst_stride = ldz;
+    }
+    return b;
+  }
+  __device__ __forceinline__ void advance() {
+    if (ph == 0) {
+      if (++i == NB) { ++j; i = j; if (j == NB) { ++r; j = 0; i = 0; if (r == R) { ph = 1; i = NB - 1; j = NB; } } }
+    } else if (ph == 1) {
+      if (j < NB) ++j;
+      else { --i; j = i + 1; if (i < 0) { ph = 2; i = 0; } }
+    } else {
+      if (++i == NB) ph = 3;
+    }
+  }
+};
+
+struct TileSmem { int panel, stages, xs, xn, gmb, gvb, gsum, gs, gr, dls, red, bars, total_doubles; };
+__host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
+  TileSmem s; int o = 0;
+  s.panel = o;  o += TP * (Mp + 4);
+  s.stages = o; o += IWVI_NST * IWVI_STAGE_DOUBLES;
+  s.xs = o;     o += TP * ldx;
+  s.xn = o;     o += TP;
+  s.gmb = o;    o += IWVI_MAX_R * TP;
+  s.gvb = o;    o += IWVI_MAX_R * TP;
+  s.gsum = o;   o += TP;
+  s.gs = o;     o += TP;
+  s.gr = o;     o += 2 * IWVI_BLK;
+  s.dls = o;    o += 32;
+  s.red = o;    o += 32;
+  s.bars = o;   o += IWVI_NST;
+  s.total_doubles = o;
+  return s;
+}
+
+template <int TP>
+__global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) {
+  using C = TileCfg<TP>;
+  static_assert(C::TN == 2, "register-resident V fragments assume two n-tiles per warp");
+  extern __shared__ __align__(16) double smem[];
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, ldA = Mp + 4, R = d.R, D = d.D, T = d.T, M = d.M;
+  const int Dk = iwvi_round_up(D, 4);
+  const int nd8 = (D + 7) / 8;
+  const TileSmem sl = tile_smem_layout(TP, Mp, ldz);
+  double* panel = smem + sl.panel;
+  double* xs = smem + sl.xs;
+  double* xn = smem + sl.xn;
+  double* gmb_s = smem + sl.gmb;
+  double* gvb_s = smem + sl.gvb;
+  double* gsum_s = smem + sl.gsum;
+  double* gs_s = smem + sl.gs;
+  double* gr_s = smem + sl.gr;
+  double* dls_s = smem + sl.dls;
+  double* red = smem + sl.red;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % C::WMG) * C::WM;
+  const int wn0 = (warp / C::WMG) * C::WN;
+
+  const double* aux = p.aux;
+  const double* zn = aux + al.off_zn;
+  const double* qmu = aux + al.off_qmu;
+  const double* consts = aux + al.off_consts;
+  const double variance = consts[IWVI_C_VARIANCE];
+  const SaveLayout sv = iwvi_save_layout(T, M, R);
+  const double* A_T = p.save + sv.off_a;
+  const double* U_T = p.save + sv.off_u;
+  const double* gmb = p.ws + p.wl.off_gmb;
+  const double* gvb = p.ws + p.wl.off_gvb;
+  double* bbar_T = p.ws + p.wl.off_bbar;
+  double* mypart = p.ws + p.wl.off_tile + (size_t)blockIdx.x * p.wl.tile_stride;
+
+  // this CTA's partial of dZ (accumulated across its tiles in global memory, exclusive owner) and dls
+  for (int idx = tid; idx < p.wl.tile_stride; idx += blockDim.x) mypart[idx] = 0.0;
+  if (tid < 32) dls_s[tid] = 0.0;
+  double dvar_acc = 0.0;
+
+  StagePipe pipe;
+  pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages);
+  BwdSeq seq;
+  seq.NB = NB; seq.R = R; seq.Mp = Mp; seq.ldz = ldz;
+  seq.Zt = aux + al.off_zt; seq.Lm = p.Lm; seq.Dinv = aux + al.off_dinv; seq.Lqp = aux + al.off_lqp;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int n0 = tile * TP;
+    __syncthreads();
+    seq.init();
+    pipe.prime(seq, warp, lane);
+
+    // ---- per-point cotangents of this tile, x tile
+    for (int idx = tid; idx < IWVI_MAX_R * TP; idx += blockDim.x) {
+      const int r = idx / TP, n = idx - r * TP;
+      gmb_s[idx] = gmb[(size_t)(n0 + n) * IWVI_MAX_R + r];
+      gvb_s[idx] = gvb[(size_t)(n0 + n) * IWVI_MAX_R + r];
+    }
+    for (int idx = tid; idx < TP * ldz; idx += blockDim.x) {
+      const int n = idx / ldz, k = idx - n * ldz;
+      double v = 0.0;
+      if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
+      xs[idx] = v;
+    }
+    if (tid < TP) gs_s[tid] = 0.0;
+    if (tid < IWVI_BLK) gr_s[tid] = 0.0;
+    __syncthreads();
+    if (tid < TP) {
+      double s = 0.0;
+      for (int k = 0; k < Dk; k++) { const double v = xs[tid * ldz + k]; s += v * v; }
+      xn[tid] = s;
+      double gsum = 0.0;
+      for (int r = 0; r < R; r++) gsum += gvb_s[r * TP + tid];
+      gsum_s[tid] = gsum;
+    }
+    __syncthreads();
+
+    // ---- Abar, part 1: q_mu gmean_bar^T - 2 A gsum   (A read from the saved point-major array, coalesced)
+    for (int idx = tid; idx < TP * Mp; idx += blockDim.x) {
+      const int n = idx / Mp, m = idx - n * Mp;
+      double v = -2.0 * A_T[(size_t)(n0 + n) * ldA + m] * gsum_s[n];
+      const double* q = qmu + (size_t)m * IWVI_MAX_R;
+      for (int r = 0; r < R; r++) v += q[r] * gmb_s[r * TP + n];
+      panel[n * ldA + m] = v;
+    }
+    __syncthreads();
+
+    // ---- Abar, part 2: += 2 tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register B-fragments per k-block j
+    for (int r = 0; r < R; r++) {
+      for (int j = 0; j < NB; j++) {
+        double vb[16][2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int n = wn0 + b * 8 + g;
+          const double sc = gvb_s[r * TP + n];
+          const double* up = U_T + ((size_t)r * sv.Tp + n0 + n) * ldA + j * IWVI_BLK + t;
+#pragma unroll
+          for (int ks = 0; ks < 16; ks++) vb[ks][b] = up[ks * 4] * sc;
+        }
+        for (int i = j; i < NB; i++) {
+          const double* st = pipe.wait();
+          double acc[C::TM][2][2];
+          acc_zero<C::TM, 2>(acc);
+          const double* ap = st + (wm0 + g) * IWVI_LDS + t;
+#pragma unroll
+          for (int ks = 0; ks < 16; ks++) {
+            double a[C::TM];
+#pragma unroll
+            for (int a_ = 0; a_ < C::TM; a_++) a[a_] = ap[a_ * 8 * IWVI_LDS + ks * 4];
+#pragma unroll
+            for (int a_ = 0; a_ < C::TM; a_++) {
+              dmma884(acc[a_][0], a[a_], vb[ks][0]);
+              dmma884(acc[a_][1], a[a_], vb[ks][1]);
+            }
+          }
+          pipe.release(seq, warp, lane);
+#pragma unroll
+          for (int a_ = 0; a_ < C::TM; a_++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+              for (int c = 0; c < 2; c++) {
+                const int m = i * IWVI_BLK + wm0 + a_ * 8 + g;
+                const int n = wn0 + b * 8 + 2 * t + c;
+                panel[n * ldA + m] += 2.0 * acc[a_][b][c];
+              }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- Bbar = Lm^-T Abar, blocked back substitution in place
+    for (int i = NB - 1; i >= 0; i--) {
+      double acc[C::TM][C::TN][2];
+      acc_zero<C::TM, C::TN>(acc);
+      for (int j = i + 1; j < NB; j++) {
+        const double* st = pipe.wait();
+        warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+        pipe.release(seq, warp, lane);
+      }
+      if (i < NB - 1) {
+#pragma unroll
+        for (int a = 0; a < C::TM; a++)
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const int m = i * IWVI_BLK + wm0 + a * 8 + g;
+              const int n = wn0 + b * 8 + 2 * t + c;
+              panel[n * ldA + m] -= acc[a][b][c];
+            }
+        __syncthreads();
+      }
+      const double* st = pipe.wait();   // inverted diagonal block i, used transposed
+      acc_zero<C::TM, C::TN>(acc);
+      warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, IWVI_BLK, lane);
+      pipe.release(seq, warp, lane);
+#pragma unroll
+      for (int a = 0; a < C::TM; a++)
+#pragma unroll
+        for (int b = 0; b < C::TN; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int m = i * IWVI_BLK + wm0 + a * 8 + g;
+            const int n = wn0 + b * 8 + 2 * t + c;
+            panel[n * ldA + m] = acc[a][b][c];
+          }
+      __syncthreads();
+    }
+
+    // ---- store Bbar (needed by the reduce kernel for dLm); rows of invalid points are zero by construction
+    {
+      double* dst = bbar_T + (size_t)n0 * ldA;
+      for (int idx = tid; idx < TP * ldA; idx += blockDim.x) {
+        const int m = idx % ldA;
+        dst[idx] = (m < Mp) ? panel[idx] : 0.0;
+      }
+    }
+    __syncthreads();
+
+    // ---- gram adjoint, block row by block row
+    double accx[4][2];
+#pragma unroll
+    for (int b = 0; b < 4; b++) { accx[b][0] = 0.0; accx[b][1] = 0.0; }
+    for (int i = 0; i < NB; i++) {
+      const double* st = pipe.wait();   // scaled inducing inputs of block i: st[m*ldz + k]
+      if (tid < IWVI_BLK) gr_s[((i + 1) & 1) * IWVI_BLK + tid] = 0.0;
+      double acc[C::TM][C::TN][2];
+      acc_zero<C::TM, C::TN>(acc);
+      warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
+      double cs[C::TN][2];
+#pragma unroll
+      for (int b = 0; b < C::TN; b++) { cs[b][0] = 0.0; cs[b][1] = 0.0; }
+#pragma unroll
+      for (int a = 0; a < C::TM; a++) {
+        double rs = 0.0;
+#pragma unroll
+        for (int b = 0; b < C::TN; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int ml = wm0 + a * 8 + g;
+            const int mg = i * IWVI_BLK + ml;
+            const int n = wn0 + b * 8 + 2 * t + c;
+            const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
+            double K, dK;
+            kern_k_dk(d.kern, r2, variance, K, dK);
+            const bool valid = (mg < M) && (n0 + n < T);
+            const double bb = panel[n * ldA + mg];
+            const double G = valid ? bb * dK : 0.0;
+            if (valid) dvar_acc += bb * K;
+            panel[n * ldA + mg] = G;
+            acc[a][b][c] = G;
+            cs[b][c] += G;
+            rs += G;
+          }
+        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+        if (t == 0) atomicAdd(&gr_s[(i & 1) * IWVI_BLK + wm0 + a * 8 + g], rs);
+      }
+#pragma unroll
+      for (int b = 0; b < C::TN; b++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          double v = cs[b][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) atomicAdd(&gs_s[wn0 + b * 8 + 2 * t + c], v);
+        }
+      // lengthscale adjoint, accumulated directly (no cancellation): sum G (x~_d - z~_d)^2
+      for (int dd = 0; dd < D; dd++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < C::TM; a++) {
+          const double zv = st[(wm0 + a * 8 + g) * ldz + dd];
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const double df = xs[(wn0 + b * 8 + 2 * t + c) * ldz + dd] - zv;
+              s += acc[a][b][c] * df * df;
+            }
+        }
+        s = warp_sum(s);
+        if (lane == 0) atomicAdd(&dls_s[dd], s);
+      }
+      __syncthreads();   // G_i visible in the panel, gr_s complete
+
+      // dX partial: accx[n][d] += sum_{m in block} G[m][n] z~[m][d]   (warp w owns points 8w..8w+7)
+      if (warp < TP / 8) {
+        const double* ap = panel + (warp * 8 + g) * ldA + i * IWVI_BLK + t;
+#pragma unroll 4
+        for (int k0 = 0; k0 < IWVI_BLK; k0 += 4) {
+          const double a = ap[k0];
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < nd8) {
+              const int dcol = b * 8 + g;
+              const double bv = (dcol < ldz) ? st[(k0 + t) * ldz + dcol] : 0.0;
+              dmma884(accx[b], a, bv);
+            }
+          }
+        }
+      }
+      // dZ partial of block row i: sum_n G[m][n] x~[n][d]   (warp w owns rows 8w..8w+7 of the block)
+      {
+        double accz[4][2];
+#pragma unroll
+        for (int b = 0; b < 4; b++) { accz[b][0] = 0.0; accz[b][1] = 0.0; }
+        const double* ap = panel + t * ldA + i * IWVI_BLK + warp * 8 + g;
+#pragma unroll 4
+        for (int k0 = 0; k0 < TP; k0 += 4) {
+          const double a = ap[k0 * ldA];
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < nd8) {
+              const int dcol = b * 8 + g;
+              const double bv = (dcol < ldz) ? xs[(k0 + t) * ldz + dcol] : 0.0;
+              dmma884(accz[b], a, bv);
+            }
+          }
+        }
+        const int ml = warp * 8 + g;
+        const int mg = i * IWVI_BLK + ml;
+        const double grv = gr_s[(i & 1) * IWVI_BLK + ml];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int dcol = b * 8 + 2 * t + c;
+            if (b < nd8 && dcol < D && mg < M) {
+              const double zv = st[ml * ldz + dcol];
+              mypart[(size_t)mg * ldz + dcol] += -2.0 * consts[IWVI_C_INVLS + dcol] * (accz[b][c] - zv * grv);
+            }
+          }
+      }
+      pipe.release(seq, warp, lane);
+    }
+
+    // ---- dX += 2/ls (x~ colsum(G) - G^T z~)
+    if (warp < TP / 8) {
+      const int n = warp * 8 + g;
+      const size_t pt = (size_t)(n0 + n);
+      if (pt < (size_t)T) {
+        const double gsv = gs_s[n];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int dcol = b * 8 + 2 * t + c;
+            if (b < nd8 && dcol < D)
+              p.dX[pt * D + dcol] += 2.0 * consts[IWVI_C_INVLS + dcol] * (xs[n * ldz + dcol] * gsv - accx[b][c]);
+          }
+      }
+    }
+  }
+
+  __syncthreads();
+  const double tot = block_sum(dvar_acc, red);
+  if (tid == 0) mypart[(size_t)Mp * ldz + 32] = tot / variance;
+  if (tid < 32) mypart[(size_t)Mp * ldz + tid] = (tid < D) ? -2.0 * consts[IWVI_C_INVLS + tid] * dls_s[tid] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. contractions over the points (split-K)
+// ------------------------------------------------------------------------------------------------
+struct RedSeq {
+  const double *Aop, *Bop;   // both point-major [Tp, ldA], already offset to their 64-column block
+  int ldA, c, c1, which;
+  __device__ __forceinline__ bool done() const { return c >= c1; }
+  __device__ __forceinline__ BlockSrc get() const {
+    BlockSrc b;
+    b.src = (which == 0 ? Aop : Bop) + (size_t)c * IWVI_BLK * ldA;
+    b.row_bytes = IWVI_BLK * 8; b.src_stride = ldA; b.dst_stride = IWVI_LDS;
+    return b;
+  }
+  __device__ __forceinline__ void advance() { if (which == 0) which = 1; else { which = 0; ++c; } }
+};
+
+#define RED_NST 4
+__global__ void __launch_bounds__(256, 1) gp_reduce_bwd_kernel(const BwdParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const int NB = al.NB, R = d.R;
+  const BwdWs& wl = p.wl;
+  const int ldA = wl.ldA;
+  double* stages = smem;
+  double* scale_s = smem + RED_NST * IWVI_STAGE_DOUBLES;        // [2][64]
+  double* gm_s = scale_s + 2 * IWVI_BLK;                        // [2][64*8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gm_s + 2 * IWVI_BLK * IWVI_MAX_R);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;     // warp tile 32 x 16 of the 64 x 64 output block
+
+  // decode the work item
+  int item = blockIdx.x;
+  const int pair = item % wl.npairs; item /= wl.npairs;
+  const int s = item % wl.S;
+  const int q = item / wl.S;                                     // q < R: dLq_q ; q == R: dLm
+  int bi = 0, acc_pairs = 0;
+  while (acc_pairs + bi + 1 <= pair) { acc_pairs += bi + 1; bi++; }
+  const int bj = pair - acc_pairs;                               // bj <= bi
+  const int c0 = s * wl.chunks_per_split;
+  const int c1 = min(c0 + wl.chunks_per_split, wl.Tp / IWVI_BLK);
+
+  const SaveLayout sv = iwvi_save_layout(d.T, d.M, R);
+  const double* A_T = p.save + sv.off_a;
+  const double* U_T = p.save + sv.off_u;
+  const double* bbar_T = p.ws + wl.off_bbar;
+  const double* gmb = p.ws + wl.off_gmb;
+  const double* gvb = p.ws + wl.off_gvb;
+  const bool is_lm = (q == R);
+  const bool do_qmu = (q == 0 && bj == 0);
+
+  StagePipeT<RED_NST> pipe;
+  pipe.setup(bars, stages);
+  RedSeq seq;
+  seq.Aop = (is_lm ? bbar_T : A_T) + bi * IWVI_BLK;
+  seq.Bop = (is_lm ? A_T : U_T + (size_t)q * sv.Tp * ldA) + bj * IWVI_BLK;
+  seq.ldA = ldA; seq.c = c0; seq.c1 = c1; seq.which = 0;
+  pipe.prime(seq, warp, lane);
+
+  double acc[4][2][2];
+  acc_zero<4, 2>(acc);
+  double accq[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++) { accq[a][0] = 0.0; accq[a][1] = 0.0; }
+
+  auto load_scales = [&](int c, int buf) {
+    if (tid < IWVI_BLK) {
+      const size_t pt = (size_t)c * IWVI_BLK + tid;
+      scale_s[buf * IWVI_BLK + tid] = is_lm ? -1.0 : 2.0 * gvb[pt * IWVI_MAX_R + q];
+    }
+    if (do_qmu) {
+      for (int idx = tid; idx < IWVI_BLK * IWVI_MAX_R; idx += blockDim.x)
+        gm_s[buf * IWVI_BLK * IWVI_MAX_R + idx] = gmb[(size_t)c * IWVI_BLK * IWVI_MAX_R + idx];
+    }
+  };
+  if (c0 < c1) load_scales(c0, 0);
+  __syncthreads();
+
+  for (int c = c0; c < c1; c++) {
+    const int buf = (c - c0) & 1;
+    if (c + 1 < c1) load_scales(c + 1, buf ^ 1);   // consumed after the barrier inside release_n
+    const double* sa = pipe.wait_ahead(0);   // [k = point][m]  -> A operand, k-major
+    const double* sb = pipe.wait_ahead(1);   // [k = point][n]  -> B operand, k-major
+    const double* ap = sa + t * IWVI_LDS + wm0 + g;
+    const double* bp = sb + t * IWVI_LDS + wn0 + g;
+    const double* sc = scale_s + buf * IWVI_BLK;
+    const double* gq = gm_s + buf * IWVI_BLK * IWVI_MAX_R;
+#pragma unroll 2
+    for (int k0 = 0; k0 < IWVI_BLK; k0 += 4) {
+      double a[4], b[2];
+      const double scl = sc[k0 + t];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
+#pragma unroll
+      for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * scl;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[j]);
+      if (do_qmu && wn0 == 0) {
+        const double bq = gq[(k0 + t) * IWVI_MAX_R + g];
+#pragma unroll
+        for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
+      }
+    }
+    pipe.release_n(seq, 2, warp, lane);
+  }
+
+  double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+        out[(wm0 + i * 8 + g) * IWVI_BLK + wn0 + j * 8 + 2 * t + c] = acc[i][j][c];
+  if (do_qmu && wn0 == 0) {
+    double* oq = p.ws + wl.off_qred + ((size_t)s * NB + bi) * IWVI_BLK * IWVI_MAX_R;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) oq[(wm0 + i * 8 + g) * IWVI_MAX_R + 2 * t + c] = accq[i][c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. fixed-order sums of the partials
+// ------------------------------------------------------------------------------------------------
+__global__ void gp_finalize_bwd_kernel(const BwdParams p) {
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const BwdWs& wl = p.wl;
+  const int M = d.M, Mp = al.Mp, R = d.R, D = d.D, P = d.P, NB = al.NB, ldz = al.ldz;
+  const int64_t n_lq = (int64_t)R * M * M, n_lm = (int64_t)Mp * Mp, n_qmu = (int64_t)M * R, n_z = (int64_t)M * D;
+  const int64_t n_small = D + 1 + P * R + D * P + P;
+  const int64_t total = n_lq + n_lm + n_qmu + n_z + n_small;
+  const double* red = p.ws + wl.off_red;
+  const double* qred = p.ws + wl.off_qred;
+  const double* tile = p.ws + wl.off_tile;
+  const double* epi = p.ws + wl.off_epi;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = e;
+    if (k < n_lq + n_lm) {
+      int q, a, b;
+      double* dst;
+      if (k < n_lq) { q = (int)(k / ((int64_t)M * M)); const int64_t rem = k - (int64_t)q * M * M; a = (int)(rem / M); b = (int)(rem - (int64_t)a * M); dst = p.dq_sqrt + k; }
+      else { k -= n_lq; q = R; a = (int)(k / Mp); b = (int)(k - (int64_t)a * Mp); dst = p.dLm + k; }
+      double s = 0.0;
+      if (a >= b) {
+        const int bi = a / IWVI_BLK, bj = b / IWVI_BLK;
+        const int pair = bi * (bi + 1) / 2 + bj;
+        const int off = (a - bi * IWVI_BLK) * IWVI_BLK + (b - bj * IWVI_BLK);
+        for (int s_ = 0; s_ < wl.S; s_++)
+          s += red[(((size_t)q * wl.S + s_) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK + off];
+      }
+      *dst = s;
+      continue;
+    }
+    k -= n_lq + n_lm;
+    if (k < n_qmu) {
+      const int m = (int)(k / R), r = (int)(k - (int64_t)m * R);
+      const int bi = m / IWVI_BLK;
+      double s = 0.0;
+      for (int s_ = 0; s_ < wl.S; s_++)
+        s += qred[((size_t)s_ * NB + bi) * IWVI_BLK * IWVI_MAX_R + (m - bi * IWVI_BLK) * IWVI_MAX_R + r];
+      p.dq_mu[k] = s;
+      continue;
+    }
+    k -= n_qmu;
+    if (k < n_z) {
+      const int m = (int)(k / D), dd = (int)(k - (int64_t)m * D);
+      double s = 0.0;
+      for (int g_ = 0; g_ < p.grid_tile; g_++) s += tile[(size_t)g_ * wl.tile_stride + (size_t)m * ldz + dd];
+      p.dZ[k] = s;
+      continue;
+    }
+    k -= n_z;
+    if (k < D) {
+      double s = 0.0;
+      for (int g_ = 0; g_ < p.grid_tile; g_++) s += tile[(size_t)g_ * wl.tile_stride + (size_t)Mp * ldz + k];
+      p.dls[k] = s;
+    } else if (k == D) {
+      double s = 0.0;
+      for (int g_ = 0; g_ < p.grid_tile; g_++) s += tile[(size_t)g_ * wl.tile_stride + (size_t)Mp * ldz + 32];
+      for (int e_ = 0; e_ < wl.n_epi; e_++) s += epi[(size_t)e_ * EPI_STRIDE + P * R + D * P + P];
+      p.dvariance[0] = s;
+    } else {
+      const int64_t j = k - D - 1;   // index into [dW | dmfA | dmfb]
+      double s = 0.0;
+      for (int e_ = 0; e_ < wl.n_epi; e_++) s += epi[(size_t)e_ * EPI_STRIDE + j];
+      if (j < P * R) { if (p.dW) p.dW[j] = s; }
+      else if (j < P * R + D * P) { if (p.dmfA) p.dmfA[j - P * R] = s; }
+      else { if (p.dmfb) p.dmfb[j - P * R - D * P] = s; }
+    }
+  }
+}
+
+int pick_bwd_tp(int Mp, int ldz, int max_smem, int* smem_bytes) {
+  const int cands[2] = {64, 32};
+  for (int c = 0; c < 2; c++) {
+    const int bytes = tile_smem_layout(cands[c], Mp, ldz).total_doubles * 8;
+    if (bytes <= max_smem) { *smem_bytes = bytes; return cands[c]; }
+  }
+  return -1;
+}
+
+}  // namespace
+
+static int device_info(int* nsm, int* max_smem) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return IWVI_ERR_LAUNCH;
+  cudaDeviceGetAttribute(nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return IWVI_OK;
+}
+
+extern "C" int64_t iwvi_gp_bwd_ws_doubles(const iwvi_gp_desc* d) {
+  if (iwvi_check_gp_desc(d) != IWVI_OK) return -1;
+  int nsm = 148, max_smem = 0;
+  if (device_info(&nsm, &max_smem) != IWVI_OK) nsm = 148;
+  return bwd_ws_layout(*d, nsm).total;
+}
+
+extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
+                                const double* X, const double* W, const double* mfA, const double* mfb,
+                                const double* eps, const double* d_sample, const double* d_mean, const double* d_var,
+                                double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu,
+                                double* dq_sqrt, double* dLm, double* dW, double* dmfA, double* dmfb, double* ws,
+                                void* stream) {
+  int rc = iwvi_check_gp_desc(d);
+  if (rc != IWVI_OK) return rc;
+  if (!Lm || !aux || !save || !X || !dX || !dZ || !dls || !dvariance || !dq_mu || !dq_sqrt || !dLm || !ws)
+    return IWVI_ERR_NULL;
+  if (d->mix && !W) return IWVI_ERR_NULL;
+  if (d->mf == IWVI_MF_LINEAR && !mfA) return IWVI_ERR_NULL;
+  if ((d->flags & IWVI_FLAG_SAMPLE) && !eps) return IWVI_ERR_NULL;
+  if (d->T == 0) return IWVI_ERR_BAD_DESC;
+  int nsm = 148, max_smem = 0;
+  rc = device_info(&nsm, &max_smem);
+  if (rc != IWVI_OK) return rc;
+  const AuxLayout al = iwvi_aux_layout(d->M, d->D, d->R);
+  BwdParams p;
+  p.d = *d; p.Lm = Lm; p.aux = aux; p.save = save; p.X = X; p.W = W; p.mfA = mfA; p.mfb = mfb; p.eps = eps;
+  p.d_sample = d_sample; p.d_mean = d_mean; p.d_var = d_var;
+  p.dX = dX; p.dZ = dZ; p.dls = dls; p.dvariance = dvariance; p.dq_mu = dq_mu; p.dq_sqrt = dq_sqrt; p.dLm = dLm;
+  p.dW = dW; p.dmfA = dmfA; p.dmfb = dmfb; p.ws = ws;
+  p.wl = bwd_ws_layout(*d, nsm);
+  int smem_bytes = 0;
+  const int TP = pick_bwd_tp(al.Mp, al.ldz, max_smem, &smem_bytes);
+  if (TP < 0) return IWVI_ERR_UNSUPPORTED;
+  p.ntiles = p.wl.Tp / TP;   // covers the zero-padded rows too, so every row of Bbar is written
+  p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  gp_epi_bwd_kernel<<<p.wl.n_epi, EPI_PTS, 0, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+
+  if (TP == 64) {
+    if (cudaFuncSetAttribute(gp_tile_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+      return IWVI_ERR_LAUNCH;
+    gp_tile_bwd_kernel<64><<<p.grid_tile, 256, smem_bytes, st>>>(p);
+  } else {
+    if (cudaFuncSetAttribute(gp_tile_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+      return IWVI_ERR_LAUNCH;
+    gp_tile_bwd_kernel<32><<<p.grid_tile, 256, smem_bytes, st>>>(p);
+  }
+  IWVI_CHECK_LAUNCH();
+
+  const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK + 2 * IWVI_BLK * IWVI_MAX_R + RED_NST) * 8;
+  if (cudaFuncSetAttribute(gp_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  const int red_grid = (d->R + 1) * p.wl.S * p.wl.npairs;
+  gp_reduce_bwd_kernel<<<red_grid, 256, red_smem, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+
+  gp_finalize_bwd_kernel<<<2 * nsm, 256, 0, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}

@@ -1,0 +1,383 @@
+// gp_rows_fwd.cu -- per-point stage of the sparse-variational conditional, forward.
+//
+// Replaces independent_multisample_sample_conditional (reference temp_workaround.py:44-91, diag branch),
+// the SharedMixedMok mixing (:142-145) and the mean-function add (layers.py:46-48) with ONE persistent kernel:
+// a CTA owns a tile of TP points, keeps the M x TP panel (Kuf -> A = Lm^-1 Kuf) resident in shared memory
+// (point-major, padded leading dimension), streams 64x64 blocks of Lm / inverted diagonal blocks / tril(q_sqrt)
+// from L2 through a bulk-TMA + mbarrier ring, and does every contraction on the FP64 tensor pipe (DMMA):
+//
+//   G  Kuf_i   = k(|z|^2 + |x|^2 - 2 z.x)                (gram: -2XZ^T GEMM + norm epilogue + kernel function)
+//   T  A_i     = Dinv_i (Kuf_i - sum_{j<i} Lm_ij A_j)    (blocked forward substitution, inverted diagonal blocks)
+//   S  fvar0   = variance - sum_m A^2 ; gmean = A^T q_mu
+//   U  U_r,i   = sum_{j>=i} Lq_r[j,i]^T A_j ; gvar_r = fvar0 + sum_m U_r^2     (never materialised unless saved)
+//   E  sample  = gmean + eps*sqrt(gvar) ; Mok mixing by W, W^2 ; + mean function
+//
+// Nothing of size M x T touches HBM unless IWVI_FLAG_SAVE asks for A and U (kept for the backward pass: on B200 an
+// HBM round trip costs less than recomputing them at the 37 TFLOP/s fp64 rate).
+#include "common.cuh"
+
+namespace {
+
+struct FwdSeq {  // order in which 64-row blocks are consumed by one tile
+  int NB, R, Mp, ldz;
+  const double *Zt, *Lm, *Dinv, *Lqp;
+  int ph, r, i, j;
+  __device__ __forceinline__ void init() { ph = 0; r = 0; i = 0; j = 0; }
+  __device__ __forceinline__ bool done() const { return ph == 3; }
+  __device__ __forceinline__ BlockSrc get() const {
+    BlockSrc b;
+    if (ph == 0) {
+      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.row_bytes = ldz * 8; b.src_stride = ldz; b.dst_stride = ldz;
+    } else if (ph == 1) {
+      if (j < i) { b.src = Lm + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK; b.src_stride = Mp; }
+      else       { b.src = Dinv + (size_t)i * IWVI_BLK * IWVI_BLK; b.src_stride = IWVI_BLK; }
+      b.row_bytes = IWVI_BLK * 8; b.dst_stride = IWVI_LDS;
+    } else {
+      b.src = Lqp + (size_t)r * Mp * Mp + (size_t)(j * IWVI_BLK) * Mp + i * IWVI_BLK;
+      b.row_bytes = IWVI_BLK * 8; b.src_stride = Mp; b.dst_stride = IWVI_LDS;
+    }
+    return b;
+  }
+  __device__ __forceinline__ void advance() {
+    if (ph == 0) {
+      if (++i == NB) { ph = 1; i = 0; j = 0; }
+    } else if (ph == 1) {
+      if (j < i) ++j;
+      else { ++i; j = 0; if (i == NB) { ph = (R > 0) ? 2 : 3; r = 0; i = 0; j = 0; } }
+    } else {
+      if (++j == NB) { ++i; j = i; if (i == NB) { ++r; i = 0; j = 0; if (r == R) ph = 3; } }
+    }
+  }
+};
+
+template <int TP> struct TileCfg {
+  static constexpr int NW = 8;
+  static constexpr int WNG = TP >= 64 ? 4 : 2;  // warps along the point axis
+  static constexpr int WMG = NW / WNG;          // warps along the 64 rows of a block
+  static constexpr int WM = IWVI_BLK / WMG;
+  static constexpr int WN = TP / WNG;
+  static constexpr int TM = WM / 8;
+  static constexpr int TN = WN / 8;
+};
+
+struct FwdParams {
+  iwvi_gp_desc d;
+  const double *Lm, *aux, *X, *W, *mfA, *mfb, *eps;
+  double *sample, *mean, *var, *save;
+  int ntiles;
+};
+
+// dynamic shared memory carve-up (doubles), shared with the host-side size computation
+struct FwdSmem {
+  int panel, stages, xs, xn, fv0, usq, gm, bars, total_doubles;
+};
+__host__ __device__ inline FwdSmem fwd_smem_layout(int TP, int Mp, int ldx) {
+  FwdSmem s; int o = 0;
+  s.panel = o;  o += TP * (Mp + 4);
+  s.stages = o; o += IWVI_NST * IWVI_STAGE_DOUBLES;
+  s.xs = o;     o += TP * ldx;
+  s.xn = o;     o += TP;
+  s.fv0 = o;    o += TP;
+  s.usq = o;    o += IWVI_MAX_R * TP;
+  s.gm = o;     o += IWVI_MAX_R * TP;
+  s.bars = o;   o += IWVI_NST;
+  s.total_doubles = o;
+  return s;
+}
+
+template <int TP>
+__global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) {
+  using C = TileCfg<TP>;
+  extern __shared__ __align__(16) double smem[];
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, ldA = Mp + 4, R = d.R, D = d.D, T = d.T;
+  const int Dk = iwvi_round_up(D, 4);
+  const FwdSmem sl = fwd_smem_layout(TP, Mp, ldz);
+  double* panel = smem + sl.panel;
+  double* xs = smem + sl.xs;
+  double* xn = smem + sl.xn;
+  double* fv0 = smem + sl.fv0;
+  double* usq = smem + sl.usq;
+  double* gms = smem + sl.gm;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % C::WMG) * C::WM;   // first block-row of this warp
+  const int wn0 = (warp / C::WMG) * C::WN;   // first point of this warp
+
+  const double* aux = p.aux;
+  const double* zn = aux + al.off_zn;
+  const double* qmu = aux + al.off_qmu;
+  const double* consts = aux + al.off_consts;
+  const double variance = consts[IWVI_C_VARIANCE];
+  const SaveLayout sv = iwvi_save_layout(T, d.M, R);
+  const bool do_save = (d.flags & IWVI_FLAG_SAVE) != 0;
+  const bool do_sample = (d.flags & IWVI_FLAG_SAMPLE) != 0;
+
+  StagePipe pipe;
+  pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages);
+  FwdSeq seq;
+  seq.NB = NB; seq.R = R; seq.Mp = Mp; seq.ldz = ldz;
+  seq.Zt = aux + al.off_zt; seq.Lm = p.Lm; seq.Dinv = aux + al.off_dinv; seq.Lqp = aux + al.off_lqp;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int n0 = tile * TP;
+    __syncthreads();  // previous tile fully done with every shared buffer
+    seq.init();
+    pipe.prime(seq, warp, lane);
+
+    // ---- x tile: xs[n][k] = X[n0+n][k] / ls[k] (zero padded), xn[n] = |xs[n]|^2
+    for (int idx = tid; idx < TP * ldz; idx += blockDim.x) {
+      const int n = idx / ldz, k = idx - n * ldz;
+      double v = 0.0;
+      if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
+      xs[idx] = v;
+    }
+    for (int idx = tid; idx < IWVI_MAX_R * TP; idx += blockDim.x) usq[idx] = 0.0;
+    __syncthreads();
+    if (tid < TP) {
+      double s = 0.0;
+      for (int k = 0; k < Dk; k++) { const double v = xs[tid * ldz + k]; s += v * v; }
+      xn[tid] = s;
+    }
+    __syncthreads();
+
+    // ---- G: gram blocks -> panel (Kuf)
+    for (int i = 0; i < NB; i++) {
+      const double* st = pipe.wait();
+      double acc[C::TM][C::TN][2];
+      acc_zero<C::TM, C::TN>(acc);
+      warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
+#pragma unroll
+      for (int a = 0; a < C::TM; a++)
+#pragma unroll
+        for (int b = 0; b < C::TN; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int mg = i * IWVI_BLK + wm0 + a * 8 + g;
+            const int n = wn0 + b * 8 + 2 * t + c;
+            const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
+            panel[n * ldA + mg] = (mg < d.M) ? kern_k(d.kern, r2, variance) : 0.0;
+          }
+      pipe.release(seq, warp, lane);
+    }
+
+    // ---- T: blocked forward substitution, in place
+    for (int i = 0; i < NB; i++) {
+      double acc[C::TM][C::TN][2];
+      acc_zero<C::TM, C::TN>(acc);
+      for (int j = 0; j < i; j++) {
+        const double* st = pipe.wait();
+        warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA,
+                                      IWVI_BLK, lane);
+        pipe.release(seq, warp, lane);
+      }
+      if (i > 0) {
+#pragma unroll
+        for (int a = 0; a < C::TM; a++)
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const int m = i * IWVI_BLK + wm0 + a * 8 + g;
+              const int n = wn0 + b * 8 + 2 * t + c;
+              panel[n * ldA + m] -= acc[a][b][c];
+            }
+        __syncthreads();
+      }
+      const double* st = pipe.wait();   // inverted diagonal block
+      acc_zero<C::TM, C::TN>(acc);
+      warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA,
+                                    IWVI_BLK, lane);
+      pipe.release(seq, warp, lane);     // (barrier) every warp has read the right-hand side
+#pragma unroll
+      for (int a = 0; a < C::TM; a++)
+#pragma unroll
+        for (int b = 0; b < C::TN; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int m = i * IWVI_BLK + wm0 + a * 8 + g;
+            const int n = wn0 + b * 8 + 2 * t + c;
+            panel[n * ldA + m] = acc[a][b][c];
+          }
+      __syncthreads();
+    }
+
+    // ---- S: fvar0 and latent means; optional save of A (contiguous tile of the point-major array)
+    for (int n = warp; n < TP; n += C::NW) {
+      double s[IWVI_MAX_R + 1];
+#pragma unroll
+      for (int r = 0; r <= IWVI_MAX_R; r++) s[r] = 0.0;
+      for (int m = lane; m < Mp; m += 32) {
+        const double a = panel[n * ldA + m];
+        s[IWVI_MAX_R] += a * a;
+        const double* q = qmu + (size_t)m * IWVI_MAX_R;
+#pragma unroll
+        for (int r = 0; r < IWVI_MAX_R; r++) s[r] += a * q[r];
+      }
+#pragma unroll
+      for (int r = 0; r <= IWVI_MAX_R; r++) s[r] = warp_sum(s[r]);
+      if (lane == 0) {
+        fv0[n] = s[IWVI_MAX_R];
+#pragma unroll
+        for (int r = 0; r < IWVI_MAX_R; r++) gms[r * TP + n] = s[r];
+      }
+    }
+    if (do_save) {
+      const int nvalid = min(TP, T - n0);       // real points of this tile
+      const int nrows = min(TP, sv.Tp - n0);    // rows of the padded array this tile owns (pad rows := 0)
+      double* dst = p.save + sv.off_a + (size_t)n0 * ldA;
+      for (int idx = tid; idx < nrows * ldA; idx += blockDim.x) {
+        const int n = idx / ldA, m = idx - n * ldA;
+        dst[idx] = (m < Mp && n < nvalid) ? panel[idx] : 0.0;
+      }
+    }
+
+    // ---- U: triangular products with tril(q_sqrt_r)^T, column sums of squares
+    for (int r = 0; r < R; r++) {
+      double csq[C::TN][2];
+#pragma unroll
+      for (int b = 0; b < C::TN; b++) { csq[b][0] = 0.0; csq[b][1] = 0.0; }
+      for (int i = 0; i < NB; i++) {
+        double acc[C::TM][C::TN][2];
+        acc_zero<C::TM, C::TN>(acc);
+        for (int j = i; j < NB; j++) {
+          const double* st = pipe.wait();
+          warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+          pipe.release(seq, warp, lane);
+        }
+#pragma unroll
+        for (int a = 0; a < C::TM; a++)
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const double u = acc[a][b][c];
+              csq[b][c] += u * u;
+              if (do_save) {
+                const int m = i * IWVI_BLK + wm0 + a * 8 + g;
+                const int n = wn0 + b * 8 + 2 * t + c;
+                if (n0 + n < sv.Tp) p.save[sv.off_u + ((size_t)r * sv.Tp + n0 + n) * ldA + m] = (n0 + n < T) ? u : 0.0;
+              }
+            }
+      }
+#pragma unroll
+      for (int b = 0; b < C::TN; b++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          double v = csq[b][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) atomicAdd(&usq[r * TP + wn0 + b * 8 + 2 * t + c], v);
+        }
+    }
+    __syncthreads();
+
+    // ---- E: per-point epilogue
+    if (tid < TP && n0 + tid < T) {
+      const int n = tid;
+      const size_t pt = (size_t)(n0 + n);
+      double gm[IWVI_MAX_R], gv[IWVI_MAX_R], gs[IWVI_MAX_R];
+      for (int r = 0; r < R; r++) {
+        gm[r] = gms[r * TP + n];
+        gv[r] = variance - fv0[n] + usq[r * TP + n];
+        gs[r] = do_sample ? gm[r] + p.eps[pt * R + r] * sqrt(gv[r]) : 0.0;
+        if (do_save) {
+          p.save[sv.off_gvar + pt * R + r] = gv[r];
+          p.save[sv.off_gmean + pt * R + r] = gm[r];
+        }
+      }
+      const int P = d.P;
+      for (int q = 0; q < P; q++) {
+        double mf = 0.0;
+        if (d.mf == IWVI_MF_IDENTITY) mf = p.X[pt * D + q];
+        else if (d.mf == IWVI_MF_LINEAR) {
+          mf = p.mfb[q];
+          for (int k = 0; k < D; k++) mf += p.X[pt * D + k] * p.mfA[k * P + q];
+        }
+        double om, ov, os;
+        if (d.mix) {
+          om = 0.0; ov = 0.0; os = 0.0;
+          for (int r = 0; r < R; r++) {
+            const double w = p.W[q * R + r];
+            om += gm[r] * w; ov += gv[r] * w * w; os += gs[r] * w;
+          }
+        } else { om = gm[q]; ov = gv[q]; os = gs[q]; }
+        p.mean[pt * P + q] = om + mf;
+        p.var[pt * P + q] = ov;
+        if (do_sample) p.sample[pt * P + q] = os + mf;
+      }
+    }
+  }
+}
+
+template <int TP>
+int launch_fwd(const FwdParams& p, int smem_bytes, int grid, cudaStream_t stream) {
+  if (cudaFuncSetAttribute(gp_rows_fwd_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  gp_rows_fwd_kernel<TP><<<grid, 256, smem_bytes, stream>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+}  // namespace
+
+int iwvi_check_gp_desc(const iwvi_gp_desc* d) {
+  if (!d) return IWVI_ERR_NULL;
+  if (d->T < 0 || d->M < 1 || d->D < 1 || d->R < 1 || d->P < 1) return IWVI_ERR_BAD_DESC;
+  if (d->M > IWVI_MAX_M || d->D > IWVI_MAX_D || d->R > IWVI_MAX_R || d->P > IWVI_MAX_P) return IWVI_ERR_UNSUPPORTED;
+  if (d->kern < 0 || d->kern > 3 || d->mf < 0 || d->mf > 2) return IWVI_ERR_BAD_DESC;
+  if (!d->mix && d->P != d->R) return IWVI_ERR_BAD_DESC;
+  if (d->mf == IWVI_MF_IDENTITY && d->P != d->D) return IWVI_ERR_BAD_DESC;
+  return IWVI_OK;
+}
+
+// pick the tile width: the largest TP whose panel fits and that still yields >= 2 tiles per SM, else smaller
+int iwvi_pick_tp(int T, int Mp, int ldz, int nsm, int max_smem, int* smem_bytes) {
+  const int cands[3] = {128, 64, 32};
+  int best = -1, best_bytes = 0;
+  for (int c = 0; c < 3; c++) {
+    const int TP = cands[c];
+    const int bytes = fwd_smem_layout(TP, Mp, ldz).total_doubles * 8;
+    if (bytes > max_smem) continue;
+    if (best < 0) { best = TP; best_bytes = bytes; }
+    const int tiles = (T + TP - 1) / TP;
+    if (tiles >= 2 * nsm || TP == 32) { best = TP; best_bytes = bytes; break; }
+    best = TP; best_bytes = bytes;
+  }
+  *smem_bytes = best_bytes;
+  return best;
+}
+
+extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
+                                const double* W, const double* mfA, const double* mfb, const double* eps,
+                                double* sample, double* mean, double* var, double* save, void* stream) {
+  int rc = iwvi_check_gp_desc(d);
+  if (rc != IWVI_OK) return rc;
+  if (!Lm || !aux || !X || !mean || !var) return IWVI_ERR_NULL;
+  if (d->mix && !W) return IWVI_ERR_NULL;
+  if (d->mf == IWVI_MF_LINEAR && (!mfA || !mfb)) return IWVI_ERR_NULL;
+  if ((d->flags & IWVI_FLAG_SAMPLE) && (!eps || !sample)) return IWVI_ERR_NULL;
+  if ((d->flags & IWVI_FLAG_SAVE) && !save) return IWVI_ERR_NULL;
+  if (d->T == 0) return IWVI_OK;
+  int dev = 0, nsm = 148, max_smem = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const AuxLayout al = iwvi_aux_layout(d->M, d->D, d->R);
+  int smem_bytes = 0;
+  const int TP = iwvi_pick_tp(d->T, al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
+  if (TP < 0) return IWVI_ERR_UNSUPPORTED;
+  FwdParams p;
+  p.d = *d; p.Lm = Lm; p.aux = aux; p.X = X; p.W = W; p.mfA = mfA; p.mfb = mfb; p.eps = eps;
+  p.sample = sample; p.mean = mean; p.var = var; p.save = save;
+  // when saving, cover the zero-padded rows of the saved arrays too (at most 128/TP - 1 extra, all-zero tiles)
+  p.ntiles = (d->flags & IWVI_FLAG_SAVE) ? iwvi_save_layout(d->T, d->M, d->R).Tp / TP : (d->T + TP - 1) / TP;
+  const int grid = p.ntiles < nsm ? p.ntiles : nsm;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (TP == 128) return launch_fwd<128>(p, smem_bytes, grid, st);
+  if (TP == 64) return launch_fwd<64>(p, smem_bytes, grid, st);
+  return launch_fwd<32>(p, smem_bytes, grid, st);
+}

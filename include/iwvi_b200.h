@@ -1,0 +1,191 @@
+/*
+ * iwvi_b200.h -- C ABI of the B200 (sm_100a) IW-ELBO hot path.
+ *
+ * Drop-in boundary for the float64 importance-weighted ELBO forward/backward of
+ * hughsalimbeni/DGPs_with_IWVI.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a contiguous row-major float64 buffer unless stated;
+ *   - the caller (PyTorch) allocates every input, output, context, save and workspace buffer; the
+ *     library never allocates or frees device memory and keeps no state between calls;
+ *   - all launches are asynchronous on the cudaStream_t passed as `stream` (void* here so that the
+ *     header is plain C); no host synchronisation happens inside the library;
+ *   - return value: 0 success; IWVI_ERR_* (negative) for a bad descriptor / unsupported size /
+ *     launch failure.  Numerical failure of the Cholesky (non-positive pivot) is reported
+ *     LAPACK-style through the device-side `info` word written by iwvi_gp_prologue_fwd
+ *     (0 = ok, i>0 = leading minor of order i is not positive definite);
+ *   - "points" are the T = B*K rows the reference calls [N,K] (IW, models.py:113) or [S*N] (VI,
+ *     models.py:50) or [S,N] (prediction, models.py:96), flattened row-major.
+ */
+#ifndef IWVI_B200_H
+#define IWVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IWVI_VERSION 100
+
+/* limits of this build */
+#define IWVI_MAX_M 512   /* inducing points per layer                 */
+#define IWVI_MAX_D 32    /* GP layer input width                       */
+#define IWVI_MAX_R 8     /* latent GPs per layer (num_outputs)        */
+#define IWVI_MAX_P 32    /* GP layer output width                      */
+#define IWVI_MAX_ENC_LAYERS 8
+#define IWVI_MAX_ENC_WIDTH 64
+#define IWVI_MAX_LW 8
+
+/* error codes */
+#define IWVI_OK 0
+#define IWVI_ERR_BAD_DESC   (-1)
+#define IWVI_ERR_UNSUPPORTED (-2)
+#define IWVI_ERR_LAUNCH     (-3)
+#define IWVI_ERR_NULL       (-4)
+
+/* kernels: gpflow.kernels.RBF / Matern12 / Matern32 / Matern52 (call sites temp_workaround.py:39,44,45) */
+#define IWVI_KERN_RBF      0
+#define IWVI_KERN_MATERN12 1
+#define IWVI_KERN_MATERN32 2
+#define IWVI_KERN_MATERN52 3
+
+/* mean functions: gpflow.mean_functions.Zero / Identity / Linear (call site layers.py:46) */
+#define IWVI_MF_ZERO     0
+#define IWVI_MF_IDENTITY 1
+#define IWVI_MF_LINEAR   2
+
+/* flags */
+#define IWVI_FLAG_SAMPLE 1  /* eps given: produce sample = mean + eps*sqrt(var) (temp_workaround.py:89-91) */
+#define IWVI_FLAG_SAVE   2  /* keep A, U, latent mean/var for the backward pass */
+
+typedef struct iwvi_gp_desc {
+  int32_t T;      /* points in this call                                    */
+  int32_t M;      /* inducing points (len(Z), layers.py:19)                 */
+  int32_t D;      /* input width D_in                                       */
+  int32_t R;      /* latent GPs = num_outputs (layers.py:16)                */
+  int32_t P;      /* output width: rows of the Mok mixing W, else == R      */
+  int32_t kern;   /* IWVI_KERN_*                                            */
+  int32_t mix;    /* 1: SharedMixedMok mixing W [P,R] (temp_workaround.py:142-145) */
+  int32_t mf;     /* IWVI_MF_*                                              */
+  int32_t flags;  /* IWVI_FLAG_*                                            */
+  int32_t reserved;
+  double  jitter; /* gpflow settings.numerics.jitter_level (temp_workaround.py:39) */
+} iwvi_gp_desc;
+
+int iwvi_version(void);
+
+/* derived sizes (host-side helpers, no device work) */
+int32_t iwvi_gp_mp(int32_t M);                         /* M padded to a multiple of 64                 */
+int32_t iwvi_gp_lda(int32_t M);                        /* leading dimension of the point-major panels  */
+int64_t iwvi_gp_aux_doubles(const iwvi_gp_desc* d);    /* size of `aux`  (doubles)                     */
+int64_t iwvi_gp_save_doubles(const iwvi_gp_desc* d);   /* size of `save` (doubles) for d->T points     */
+int64_t iwvi_gp_bwd_ws_doubles(const iwvi_gp_desc* d); /* workspace of iwvi_gp_rows_bwd (doubles)      */
+int64_t iwvi_gp_pbwd_ws_doubles(const iwvi_gp_desc* d);/* workspace of iwvi_gp_prologue_bwd (doubles)  */
+
+/*
+ * Once per GP layer per step.  Replaces temp_workaround.py:39 (Kuu + jitter), :48 (tf.cholesky) and
+ * layers.py:44 -> temp_workaround.py:167-188 -> gpflow gauss_kl (whitened KL).
+ *   Z [M,D], ls [D] (ARD lengthscales, constrained), variance [1], q_mu [M,R], q_sqrt [R,M,M]
+ *   out: Lm [Mp,Mp] lower Cholesky factor (identity on the padding), aux (opaque: inverted diagonal
+ *        blocks, padded tril(q_sqrt), scaled inducing inputs, padded q_mu, constants), kl [1], info [1] (int32).
+ */
+int iwvi_gp_prologue_fwd(const iwvi_gp_desc* d, const double* Z, const double* ls, const double* variance,
+                         const double* q_mu, const double* q_sqrt,
+                         double* Lm, double* aux, double* kl, int32_t* info, void* stream);
+
+/*
+ * Per-point stage.  Replaces independent_multisample_sample_conditional (temp_workaround.py:44-91, the
+ * full_cov=False branch the Mok path forces at :125-129 and whose diagonal is all that models.py:133
+ * keeps), the Mok mixing (:142-145) and the mean function add (layers.py:46-48).
+ *   X [T,D]; W [P,R] or NULL; mfA [D,P], mfb [P] (Linear) or NULL; eps [T,R] or NULL
+ *   out: sample [T,P] (NULL unless IWVI_FLAG_SAMPLE), mean [T,P], var [T,P]; save (IWVI_FLAG_SAVE).
+ */
+int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
+                     const double* W, const double* mfA, const double* mfb, const double* eps,
+                     double* sample, double* mean, double* var, double* save, void* stream);
+
+/*
+ * Adjoint of iwvi_gp_rows_fwd (the reference: tf.gradients through temp_workaround.py:44-91,142-145,
+ * layers.py:46-48; formulas in DESIGN.md).  Cotangents d_sample/d_mean/d_var [T,P] may be NULL.
+ *   out (overwritten): dX [T,D], dZ [M,D], dls [D], dvariance [1], dq_mu [M,R], dq_sqrt [R,M,M] (lower),
+ *        dLm [Mp,Mp] (lower), dW [P,R] (if mix), dmfA [D,P], dmfb [P] (if Linear).
+ */
+int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
+                     const double* X, const double* W, const double* mfA, const double* mfb, const double* eps,
+                     const double* d_sample, const double* d_mean, const double* d_var,
+                     double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu, double* dq_sqrt,
+                     double* dLm, double* dW, double* dmfA, double* dmfb, double* ws, void* stream);
+
+/*
+ * Adjoint of iwvi_gp_prologue_fwd: Cholesky adjoint (TF CholeskyGrad), gram adjoint of Kuu and the KL
+ * adjoint.  dLm [Mp,Mp] lower, dkl [1] (device scalar cotangent of kl).
+ *   out (overwritten): dZ [M,D], dls [D], dvariance [1], dq_mu [M,R], dq_sqrt [R,M,M].
+ */
+int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* Z,
+                         const double* ls, const double* variance, const double* q_mu, const double* q_sqrt,
+                         const double* dLm, const double* dkl,
+                         double* dZ, double* dls, double* dvariance, double* dq_mu, double* dq_sqrt,
+                         double* ws, void* stream);
+
+/* ---- LatentVariableLayer + Encoder (layers.py:72-105, :137-152) ---- */
+typedef struct iwvi_lv_desc {
+  int32_t Be;        /* distinct encoder rows                                              */
+  int32_t Kt;        /* each row serves Kt consecutive points (point = n*Kt + k); 1 = none  */
+  int32_t Df;        /* width of F                                                         */
+  int32_t Dxy;       /* encoder input width (XY_dim, layers.py:55)                          */
+  int32_t Lw;        /* latent_dim                                                         */
+  int32_t n_layers;  /* encoder layers = len(network_dims)+1 (layers.py:122)               */
+  int32_t dims[IWVI_MAX_ENC_LAYERS + 1]; /* layer_dims (layers.py:122)                     */
+  int32_t sampled;   /* 1: log q(W) - log p(W) per sample (layers.py:98-100); 0: closed-form KL (:103) */
+  int32_t f_bcast;   /* 1: F is [Be,Df], broadcast over Kt; 0: F is [Be*Kt,Df]             */
+  int32_t prior;     /* 1: no encoder, q_mu/q_sqrt = prior_mu/prior_sigma (layers.py:73-81) */
+  double  prior_mu, prior_sigma;
+} iwvi_lv_desc;
+
+int64_t iwvi_lv_param_doubles(const iwvi_lv_desc* d);  /* packed W0,b0,W1,b1,...                */
+int64_t iwvi_lv_bwd_ws_doubles(const iwvi_lv_desc* d);
+
+/* out: samples [T,Df+Lw] = [F, W], kl [T,Lw], mu [Be,Lw], sigma [Be,Lw] */
+int iwvi_lv_fwd(const iwvi_lv_desc* d, const double* F, const double* enc_in, const double* params,
+                const double* eps, double* samples, double* kl, double* mu, double* sigma, void* stream);
+/* cotangents d_samples [T,Df+Lw], d_kl [T,Lw] (either may be NULL); d_mu/d_sigma [Be,Lw] extra cotangents or NULL.
+ * out (overwritten): d_params (packed), dF ([Be,Df] if f_bcast else [T,Df]; may be NULL). */
+int iwvi_lv_bwd(const iwvi_lv_desc* d, const double* F, const double* enc_in, const double* params,
+                const double* eps, const double* mu, const double* sigma,
+                const double* d_samples, const double* d_kl, const double* d_mu, const double* d_sigma,
+                double* d_params, double* dF, double* ws, void* stream);
+
+/* ---- likelihood + K-way logsumexp (models.py:133-150; VI: models.py:66-86) ---- */
+typedef struct iwvi_elbo_desc {
+  int32_t B;          /* minibatch rows                                                     */
+  int32_t K;          /* importance samples / VI samples                                    */
+  int32_t Dy;         /* output columns                                                     */
+  int32_t Lw;         /* total local-regulariser columns (0: none)                          */
+  int32_t iw;         /* 1: logsumexp_K - log K (models.py:148); 0: mean over K (models.py:84) */
+  int32_t data_major; /* 1: point = n*K + k (models.py:113); 0: point = k*B + n (models.py:50) */
+  double  scale;      /* num_data / B_global (models.py:144-145)                            */
+} iwvi_elbo_desc;
+
+int64_t iwvi_elbo_ws_doubles(const iwvi_elbo_desc* d);
+
+/* out: elbo_data [1] = scale * sum_n logp_n, logp [B], w [B,K] (softmax over K, or 1/K) */
+int iwvi_iwelbo_fwd(const iwvi_elbo_desc* d, const double* fmean, const double* fvar, const double* Y,
+                    const double* lik_var, const double* kl_local,
+                    double* elbo_data, double* logp, double* w, double* ws, void* stream);
+/* d_elbo [1] device scalar. out: dmean, dvar [T,Dy], dkl_local [T,Lw] (or NULL), dlik [1] */
+int iwvi_iwelbo_bwd(const iwvi_elbo_desc* d, const double* fmean, const double* fvar, const double* Y,
+                    const double* lik_var, const double* w, const double* d_elbo,
+                    double* dmean, double* dvar, double* dkl_local, double* dlik, double* ws, void* stream);
+
+/* ---- counter-based N(0,1) noise, identical for any number of GPUs ----
+ * Replaces tf.random_normal at layers.py:86 and temp_workaround.py:89 (index order [n,k,c] row-major).
+ * element (point p, column c) of a [*, C] tensor uses Philox4x32-10 with key = (seed_lo, seed_hi) and
+ * counter = ((first_point + p) * C + c) >> 1, lane (.. & 1) of a Box-Muller pair. */
+int iwvi_normal_fill(double* out, int64_t n_points, int32_t C, int64_t first_point, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IWVI_B200_H */
