@@ -14,6 +14,7 @@
 #define IWVI_BLK 64            // block size of the blocked triangular algorithms
 #define IWVI_LDS 68            // leading dimension of a staged 64x64 block in shared memory (== 4 mod 16)
 #define IWVI_STAGE_DOUBLES (IWVI_BLK * IWVI_LDS)
+#define IWVI_PACK_GRID 64      // CTAs of the prologue pack kernel (== number of KL partial sums)
 
 __host__ __device__ inline int iwvi_round_up(int x, int m) { return (x + m - 1) / m * m; }
 // leading dimension of length-scaled inputs (Zt rows in aux, x tile in smem): == 4 (mod 16), >= round_up(D,4)
@@ -24,7 +25,7 @@ __host__ __device__ inline int iwvi_ldz(int D) { return D <= 20 ? 20 : 36; }
 // ---------------------------------------------------------------------------------------------
 struct AuxLayout {
   int Mp, NB, ldz, R;
-  int64_t off_dinv, off_lqp, off_zt, off_zn, off_qmu, off_consts, total;
+  int64_t off_dinv, off_lqp, off_zt, off_zn, off_qmu, off_consts, off_scratch, total;
 };
 __host__ __device__ inline AuxLayout iwvi_aux_layout(int M, int D, int R) {
   AuxLayout a;
@@ -39,6 +40,7 @@ __host__ __device__ inline AuxLayout iwvi_aux_layout(int M, int D, int R) {
   a.off_zn = o;     o += a.Mp;                                  // |Z/ls|^2
   a.off_qmu = o;    o += (int64_t)a.Mp * IWVI_MAX_R;            // q_mu padded to [Mp, 8]
   a.off_consts = o; o += 64;                                    // [0]=variance, [1..32]=1/ls[d] at [8+d], see below
+  a.off_scratch = o; o += IWVI_PACK_GRID;                       // per-CTA partial sums of the KL (fixed-order final sum)
   a.total = o;
   return a;
 }

@@ -1,0 +1,580 @@
+// gp_prologue.cu -- once-per-layer-per-step stage of a GPLayer and its adjoint.
+//
+// Forward (reference temp_workaround.py:39 Kuu + jitter, :48 tf.cholesky, layers.py:44 -> gauss_kl whitened):
+//   gp_pack_kernel   many CTAs: length-scaled inducing inputs Zt and their norms, zero-padded tril(q_sqrt), padded
+//                    q_mu, constants, per-CTA partial sums of the whitened KL.
+//   gp_chol_kernel   one CTA: left-looking blocked Cholesky of Kuu + jitter*I with 64x64 blocks.  The gram blocks
+//                    are produced on the fly (-2 Z Z^T GEMM + norm epilogue + kernel function, DMMA), the block
+//                    updates L(i,j) L(k,j)^T and the panel scaling S(i,k) Dinv_k^T run on the FP64 tensor pipe, the
+//                    64x64 diagonal factorisation and its inverse run in shared memory.  Also the final KL sum.
+// Backward (the reference: tf.gradients; TF CholeskyGrad = Phi-form below):
+//   pbwd_phi_kernel    P = Phi(Lm^T tril(dLm))                     one 64x64 block per CTA, DMMA
+//   pbwd_solve_kernel  Out = In Lm^-1 (blocked back substitution on 32-row panels, same pipeline as the row stage);
+//                      run twice: S1^T = P^T Lm^-1, then Kbar' = S1 Lm^-1
+//   pbwd_gram_kernel   Kbar = sym(Kbar'), gram adjoint of Kuu (dZ, per-row partials of dls, dvariance), KL adjoint
+//   pbwd_final_kernel  fixed-order sums of the per-row partials
+#include "common.cuh"
+
+namespace {
+
+struct ProParams {
+  iwvi_gp_desc d;
+  const double *Z, *ls, *variance, *q_mu, *q_sqrt;
+  double *Lm, *aux, *kl;
+  int32_t* info;
+};
+
+// ------------------------------------------------------------------------------------------------
+// pack
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
+  __shared__ double red[32];
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const int M = d.M, D = d.D, R = d.R, Mp = al.Mp, ldz = al.ldz;
+  double* aux = p.aux;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+  double klp = 0.0;
+  // tril(q_sqrt), zero padded; trace and log-det terms of the KL
+  const int64_t nlq = (int64_t)R * Mp * Mp;
+  for (int64_t e = gtid; e < nlq; e += gsz) {
+    const int r = (int)(e / ((int64_t)Mp * Mp));
+    const int64_t rem = e - (int64_t)r * Mp * Mp;
+    const int a = (int)(rem / Mp), b = (int)(rem - (int64_t)a * Mp);
+    double v = 0.0;
+    if (a < M && b <= a) {
+      v = p.q_sqrt[((size_t)r * M + a) * M + b];
+      klp += v * v;
+      if (a == b) klp -= log(v * v);
+    }
+    aux[al.off_lqp + e] = v;
+  }
+  // Zt = Z / ls
+  for (int64_t e = gtid; e < (int64_t)Mp * ldz; e += gsz) {
+    const int m = (int)(e / ldz), k = (int)(e - (int64_t)m * ldz);
+    aux[al.off_zt + e] = (m < M && k < D) ? p.Z[(size_t)m * D + k] / p.ls[k] : 0.0;
+  }
+  for (int64_t m = gtid; m < Mp; m += gsz) {
+    double s = 0.0;
+    if (m < M)
+      for (int k = 0; k < D; k++) { const double v = p.Z[(size_t)m * D + k] / p.ls[k]; s += v * v; }
+    aux[al.off_zn + m] = s;
+  }
+  // q_mu padded to [Mp, 8]; mahalanobis term of the KL
+  for (int64_t e = gtid; e < (int64_t)Mp * IWVI_MAX_R; e += gsz) {
+    const int m = (int)(e / IWVI_MAX_R), r = (int)(e - (int64_t)m * IWVI_MAX_R);
+    double v = 0.0;
+    if (m < M && r < R) { v = p.q_mu[(size_t)m * R + r]; klp += v * v; }
+    aux[al.off_qmu + e] = v;
+  }
+  for (int64_t e = gtid; e < 64; e += gsz) {
+    double v = 0.0;
+    if (e == IWVI_C_VARIANCE) v = p.variance[0];
+    else if (e >= IWVI_C_INVLS && e < IWVI_C_INVLS + D) v = 1.0 / p.ls[e - IWVI_C_INVLS];
+    aux[al.off_consts + e] = v;
+  }
+  const double tot = block_sum(klp, red);
+  if (threadIdx.x == 0) aux[al.off_scratch + blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky
+// ------------------------------------------------------------------------------------------------
+// copy a 64x64 block (row-major, leading dimension ld) from global into a padded shared stage
+__device__ __forceinline__ void load_block(double* dst, const double* src, int ld, int tid) {
+  for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    dst[r * IWVI_LDS + c] = src[(size_t)r * ld + c];
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const int M = d.M, Mp = al.Mp, NB = al.NB, ldz = al.ldz;
+  const int Dk = iwvi_round_up(d.D, 4);
+  double* bufA = smem;                              // [64][68]
+  double* bufB = bufA + IWVI_STAGE_DOUBLES;         // [64][68]
+  double* S = bufB + IWVI_STAGE_DOUBLES;            // [64][68] block being formed (row-major) / X of the inversion
+  double* St = S + IWVI_STAGE_DOUBLES;              // [64][68] column-major copy used by the diagonal factorisation
+  double* Dv = St + IWVI_STAGE_DOUBLES;             // [64][68] inverted diagonal block of the current column
+  double* zi = Dv + IWVI_STAGE_DOUBLES;             // [64][ldz]
+  double* zk = zi + IWVI_BLK * 36;                  // [64][ldz]
+  __shared__ int s_info;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;
+  const double* aux = p.aux;
+  const double* Zt = aux + al.off_zt;
+  const double* zn = aux + al.off_zn;
+  const double variance = p.variance[0];
+  const double jitter = d.jitter;
+  double* Lm = p.Lm;
+  double* Dinv_g = p.aux + al.off_dinv;
+  if (tid == 0) s_info = 0;
+
+  for (int k = 0; k < NB; k++) {
+    __syncthreads();
+    for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zk[idx] = Zt[(size_t)k * IWVI_BLK * ldz + idx];
+    for (int i = k; i < NB; i++) {
+      __syncthreads();
+      for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zi[idx] = Zt[(size_t)i * IWVI_BLK * ldz + idx];
+      __syncthreads();
+      // gram block (i,k) of Kuu + jitter I, identity on the padding
+      double acc[4][2][2];
+      acc_zero<4, 2>(acc);
+      warp_gemm<4, 2, 0, 0>(acc, zi + wm0 * ldz, ldz, zk + wn0 * ldz, ldz, Dk, lane);
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int mg = i * IWVI_BLK + wm0 + a * 8 + g;
+            const int ng = k * IWVI_BLK + wn0 + b * 8 + 2 * t + c;
+            double v;
+            if (mg < M && ng < M) {
+              v = kern_k(d.kern, zn[mg] + zn[ng] - 2.0 * acc[a][b][c], variance);
+              if (mg == ng) v += jitter;
+            } else {
+              v = (mg == ng) ? 1.0 : 0.0;
+            }
+            acc[a][b][c] = v;
+          }
+      // left-looking update: -= sum_{j<k} L(i,j) L(k,j)^T
+      for (int j = 0; j < k; j++) {
+        __syncthreads();
+        load_block(bufA, Lm + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
+        load_block(bufB, Lm + (size_t)(k * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
+        __syncthreads();
+        double upd[4][2][2];
+        acc_zero<4, 2>(upd);
+        warp_gemm<4, 2, 0, 0>(upd, bufA + wm0 * IWVI_LDS, IWVI_LDS, bufB + wn0 * IWVI_LDS, IWVI_LDS, IWVI_BLK, lane);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) acc[a][b][c] -= upd[a][b][c];
+      }
+      if (i == k) {
+        // ---- diagonal block: factorise in shared memory (column-major copy), then invert
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+              St[(wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wm0 + a * 8 + g] = acc[a][b][c];
+        __syncthreads();
+        const int row = tid & 63, cg = tid >> 6;
+        for (int j = 0; j < IWVI_BLK; j++) {
+          __syncthreads();   // trailing update of column j-1 is visible
+          const double djj = St[j * IWVI_LDS + j];
+          if (tid == 0 && !(djj > 0.0) && s_info == 0) s_info = k * IWVI_BLK + j + 1;
+          const double piv = sqrt(djj);
+          __syncthreads();
+          if (tid < IWVI_BLK) {
+            if (tid == j) St[j * IWVI_LDS + j] = piv;
+            else if (tid > j) St[j * IWVI_LDS + tid] /= piv;
+          }
+          __syncthreads();
+          const double lij = St[j * IWVI_LDS + row];
+          for (int c = j + 1 + cg; c <= row; c += 4) St[c * IWVI_LDS + row] -= lij * St[j * IWVI_LDS + c];
+        }
+        __syncthreads();
+        // L(k,k) to global (upper part zero) and row-major copy in S
+        for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
+          const int r = idx >> 6, c = idx & 63;
+          const double v = (c <= r) ? St[c * IWVI_LDS + r] : 0.0;
+          S[r * IWVI_LDS + c] = v;
+          Lm[(size_t)(k * IWVI_BLK + r) * Mp + k * IWVI_BLK + c] = v;
+        }
+        __syncthreads();
+        // inverse by forward substitution, one column per thread: Dv[i][c] = (L^-1)[i][c]
+        if (tid < IWVI_BLK) {
+          const int c = tid;
+          for (int i2 = 0; i2 < IWVI_BLK; i2++) {
+            double s0 = 0.0, s1 = 0.0;
+            int j = 0;
+            for (; j + 1 < i2; j += 2) {
+              s0 += S[i2 * IWVI_LDS + j] * Dv[j * IWVI_LDS + c];
+              s1 += S[i2 * IWVI_LDS + j + 1] * Dv[(j + 1) * IWVI_LDS + c];
+            }
+            if (j < i2) s0 += S[i2 * IWVI_LDS + j] * Dv[j * IWVI_LDS + c];
+            Dv[i2 * IWVI_LDS + c] = (i2 < c) ? 0.0 : ((i2 == c ? 1.0 : 0.0) - (s0 + s1)) / S[i2 * IWVI_LDS + i2];
+          }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
+          const int r = idx >> 6, c = idx & 63;
+          Dinv_g[(size_t)k * IWVI_BLK * IWVI_BLK + idx] = Dv[r * IWVI_LDS + c];
+        }
+        // zero the blocks to the right of the diagonal
+        for (int jb = k + 1; jb < NB; jb++)
+          for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
+            const int r = idx >> 6, c = idx & 63;
+            Lm[(size_t)(k * IWVI_BLK + r) * Mp + jb * IWVI_BLK + c] = 0.0;
+          }
+      } else {
+        // ---- L(i,k) = S(i,k) Dinv_k^T
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+              S[(wm0 + a * 8 + g) * IWVI_LDS + wn0 + b * 8 + 2 * t + c] = acc[a][b][c];
+        __syncthreads();
+        double out[4][2][2];
+        acc_zero<4, 2>(out);
+        warp_gemm<4, 2, 0, 0>(out, S + wm0 * IWVI_LDS, IWVI_LDS, Dv + wn0 * IWVI_LDS, IWVI_LDS, IWVI_BLK, lane);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+              Lm[(size_t)(i * IWVI_BLK + wm0 + a * 8 + g) * Mp + k * IWVI_BLK + wn0 + b * 8 + 2 * t + c] = out[a][b][c];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < IWVI_PACK_GRID; i++) s += aux[al.off_scratch + i];
+    p.kl[0] = 0.5 * (s - (double)M * (double)d.R);
+    p.info[0] = s_info;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct PbwdWs { int64_t off_p, off_s1, off_dls, off_dvar, total; };
+__host__ __device__ inline PbwdWs pbwd_ws_layout(int Mp) {
+  PbwdWs w; int64_t o = 0;
+  w.off_p = o;   o += (int64_t)Mp * Mp;     // P, later Kbar'
+  w.off_s1 = o;  o += (int64_t)Mp * Mp;     // S1^T
+  w.off_dls = o; o += (int64_t)Mp * 32;     // per-row partials of dls
+  w.off_dvar = o; o += Mp;                  // per-row partials of dvariance
+  w.total = o;
+  return w;
+}
+
+struct PbwdParams {
+  iwvi_gp_desc d;
+  const double *Lm, *aux, *Z, *ls, *variance, *q_mu, *q_sqrt, *dLm, *dkl;
+  double *dZ, *dls, *dvariance, *dq_mu, *dq_sqrt, *ws;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(256, 1) pbwd_phi_kernel(const PbwdParams p) {
+  extern __shared__ __align__(16) double smem[];
+  double* bufA = smem;
+  double* bufB = smem + IWVI_STAGE_DOUBLES;
+  const AuxLayout al = iwvi_aux_layout(p.d.M, p.d.D, p.d.R);
+  const int Mp = al.Mp, NB = al.NB;
+  const PbwdWs wl = pbwd_ws_layout(Mp);
+  double* P = p.ws + wl.off_p;
+  const int bi = blockIdx.x / NB, bj = blockIdx.x % NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;
+  double acc[4][2][2];
+  acc_zero<4, 2>(acc);
+  if (bi >= bj) {
+    for (int l = bi; l < NB; l++) {
+      __syncthreads();
+      load_block(bufA, p.Lm + (size_t)(l * IWVI_BLK) * Mp + bi * IWVI_BLK, Mp, tid);
+      load_block(bufB, p.dLm + (size_t)(l * IWVI_BLK) * Mp + bj * IWVI_BLK, Mp, tid);
+      __syncthreads();
+      warp_gemm<4, 2, 1, 1>(acc, bufA + wm0, IWVI_LDS, bufB + wn0, IWVI_LDS, IWVI_BLK, lane);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int m = bi * IWVI_BLK + wm0 + a * 8 + g;
+        const int n = bj * IWVI_BLK + wn0 + b * 8 + 2 * t + c;
+        double v = acc[a][b][c];
+        if (m < n) v = 0.0;
+        else if (m == n) v *= 0.5;
+        P[(size_t)m * Mp + n] = v;
+      }
+}
+
+struct SolveSeq {   // blocks of the back substitution: for i = NB-1..0: Lm(j,i) j = i+1..NB-1, then Dinv_i
+  int NB, Mp;
+  const double *Lm, *Dinv;
+  int i, j;
+  bool fin;
+  __device__ __forceinline__ void init() { i = NB - 1; j = NB; fin = false; }
+  __device__ __forceinline__ bool done() const { return fin; }
+  __device__ __forceinline__ BlockSrc get() const {
+    BlockSrc b;
+    b.row_bytes = IWVI_BLK * 8; b.dst_stride = IWVI_LDS;
+    if (j < NB) { b.src = Lm + (size_t)(j * IWVI_BLK) * Mp + i * IWVI_BLK; b.src_stride = Mp; }
+    else        { b.src = Dinv + (size_t)i * IWVI_BLK * IWVI_BLK; b.src_stride = IWVI_BLK; }
+    return b;
+  }
+  __device__ __forceinline__ void advance() {
+    if (j < NB) ++j;
+    else { --i; j = i + 1; if (i < 0) fin = true; }
+  }
+};
+
+#define PS_TP 32
+// Out[n][:] = (Lm^-T In_n), In_n = row n of In (TRANS == 0) or column n of In (TRANS == 1); i.e. Out = In' Lm^-1
+template <int TRANS>
+__global__ void __launch_bounds__(256, 1) pbwd_solve_kernel(const PbwdParams p, const double* In, double* Out) {
+  extern __shared__ __align__(16) double smem[];
+  const AuxLayout al = iwvi_aux_layout(p.d.M, p.d.D, p.d.R);
+  const int Mp = al.Mp, NB = al.NB, ldA = Mp + 4;
+  double* panel = smem;                                       // [PS_TP][ldA]
+  double* stages = panel + PS_TP * ldA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + IWVI_NST * IWVI_STAGE_DOUBLES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // 8 warps: 4 along the 64 block rows (16 each), 2 along the 32 panel rows (16 each)
+  const int wm0 = (warp & 3) * 16, wn0 = (warp >> 2) * 16;
+  const int n0 = blockIdx.x * PS_TP;
+
+  StagePipe pipe;
+  pipe.setup(bars, stages);
+  SolveSeq seq;
+  seq.NB = NB; seq.Mp = Mp; seq.Lm = p.Lm; seq.Dinv = p.aux + al.off_dinv;
+  seq.init();
+  pipe.prime(seq, warp, lane);
+
+  if (TRANS) {
+    for (int idx = tid; idx < PS_TP * Mp; idx += 256) {
+      const int m = idx / PS_TP, n = idx - m * PS_TP;
+      panel[n * ldA + m] = In[(size_t)m * Mp + n0 + n];
+    }
+  } else {
+    for (int idx = tid; idx < PS_TP * Mp; idx += 256) {
+      const int n = idx / Mp, m = idx - n * Mp;
+      panel[n * ldA + m] = In[(size_t)(n0 + n) * Mp + m];
+    }
+  }
+  __syncthreads();
+
+  for (int i = NB - 1; i >= 0; i--) {
+    double acc[2][2][2];
+    acc_zero<2, 2>(acc);
+    for (int j = i + 1; j < NB; j++) {
+      const double* st = pipe.wait();
+      warp_gemm<2, 2, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+      pipe.release(seq, warp, lane);
+    }
+    if (i < NB - 1) {
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] -= acc[a][b][c];
+      __syncthreads();
+    }
+    const double* st = pipe.wait();
+    acc_zero<2, 2>(acc);
+    warp_gemm<2, 2, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, IWVI_BLK, lane);
+    pipe.release(seq, warp, lane);
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+          panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = acc[a][b][c];
+    __syncthreads();
+  }
+  for (int idx = tid; idx < PS_TP * Mp; idx += 256) {
+    const int n = idx / Mp, m = idx - n * Mp;
+    Out[(size_t)(n0 + n) * Mp + m] = panel[n * ldA + m];
+  }
+}
+
+// one warp per inducing point i: gram adjoint of Kuu; grid-stride KL adjoint
+__global__ void __launch_bounds__(256) pbwd_gram_kernel(const PbwdParams p) {
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const int M = d.M, D = d.D, R = d.R, Mp = al.Mp, ldz = al.ldz;
+  const PbwdWs wl = pbwd_ws_layout(Mp);
+  const double* Kp = p.ws + wl.off_p;
+  const double* Zt = p.aux + al.off_zt;
+  const double* zn = p.aux + al.off_zn;
+  const double* consts = p.aux + al.off_consts;
+  const double variance = consts[IWVI_C_VARIANCE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 8 + warp;
+  if (i < Mp) {
+    double dz[IWVI_MAX_D], dl[IWVI_MAX_D];
+#pragma unroll
+    for (int k = 0; k < IWVI_MAX_D; k++) { dz[k] = 0.0; dl[k] = 0.0; }
+    double dv = 0.0;
+    if (i < M) {
+      const double* zi = Zt + (size_t)i * ldz;
+      for (int j = lane; j < M; j += 32) {
+        const double* zj = Zt + (size_t)j * ldz;
+        const double kb = 0.5 * (Kp[(size_t)i * Mp + j] + Kp[(size_t)j * Mp + i]);
+        double dot = 0.0;
+        for (int k = 0; k < D; k++) dot += zi[k] * zj[k];
+        double K, dK;
+        kern_k_dk(d.kern, zn[i] + zn[j] - 2.0 * dot, variance, K, dK);
+        dv += kb * K;
+        if (j != i) {
+          const double G = kb * dK;
+#pragma unroll
+          for (int k = 0; k < IWVI_MAX_D; k++) {
+            if (k < D) {
+              const double df = zi[k] - zj[k];
+              dz[k] += G * df;
+              dl[k] += G * df * df;
+            }
+          }
+        }
+      }
+    }
+    dv = warp_sum(dv);
+#pragma unroll
+    for (int k = 0; k < IWVI_MAX_D; k++) {
+      if (k < D) { dz[k] = warp_sum(dz[k]); dl[k] = warp_sum(dl[k]); }
+    }
+    if (lane == 0) {
+      p.ws[wl.off_dvar + i] = dv;
+#pragma unroll
+      for (int k = 0; k < IWVI_MAX_D; k++) {
+        if (k < D) {
+          const double il = consts[IWVI_C_INVLS + k];
+          p.ws[wl.off_dls + (size_t)i * 32 + k] = -2.0 * il * dl[k];
+          if (i < M) {
+            const double v = 4.0 * il * dz[k];
+            if (p.accumulate) p.dZ[(size_t)i * D + k] += v; else p.dZ[(size_t)i * D + k] = v;
+          }
+        }
+      }
+    }
+  }
+  // KL adjoint
+  const double dkl = p.dkl[0];
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = gtid; e < (int64_t)R * M * M; e += gsz) {
+    const int64_t rem = e % ((int64_t)M * M);
+    const int a = (int)(rem / M), b = (int)(rem - (int64_t)a * M);
+    double v = 0.0;
+    if (b <= a) {
+      const double q = p.q_sqrt[e];
+      v = dkl * (a == b ? q - 1.0 / q : q);
+    }
+    if (p.accumulate) p.dq_sqrt[e] += v; else p.dq_sqrt[e] = v;
+  }
+  for (int64_t e = gtid; e < (int64_t)M * R; e += gsz) {
+    const double v = dkl * p.q_mu[e];
+    if (p.accumulate) p.dq_mu[e] += v; else p.dq_mu[e] = v;
+  }
+}
+
+__global__ void pbwd_final_kernel(const PbwdParams p) {
+  const AuxLayout al = iwvi_aux_layout(p.d.M, p.d.D, p.d.R);
+  const PbwdWs wl = pbwd_ws_layout(al.Mp);
+  const int k = threadIdx.x;
+  if (k < p.d.D) {
+    double s = 0.0;
+    for (int i = 0; i < p.d.M; i++) s += p.ws[wl.off_dls + (size_t)i * 32 + k];
+    if (p.accumulate) p.dls[k] += s; else p.dls[k] = s;
+  } else if (k == 32) {
+    double s = 0.0;
+    for (int i = 0; i < p.d.M; i++) s += p.ws[wl.off_dvar + i];
+    s /= p.aux[al.off_consts + IWVI_C_VARIANCE];
+    if (p.accumulate) p.dvariance[0] += s; else p.dvariance[0] = s;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int iwvi_version(void) { return IWVI_VERSION; }
+extern "C" int32_t iwvi_gp_mp(int32_t M) { return iwvi_round_up(M, IWVI_BLK); }
+extern "C" int32_t iwvi_gp_lda(int32_t M) { return iwvi_round_up(M, IWVI_BLK) + 4; }
+extern "C" int64_t iwvi_gp_aux_doubles(const iwvi_gp_desc* d) {
+  if (iwvi_check_gp_desc(d) != IWVI_OK) return -1;
+  return iwvi_aux_layout(d->M, d->D, d->R).total;
+}
+extern "C" int64_t iwvi_gp_save_doubles(const iwvi_gp_desc* d) {
+  if (iwvi_check_gp_desc(d) != IWVI_OK) return -1;
+  return iwvi_save_layout(d->T, d->M, d->R).total;
+}
+extern "C" int64_t iwvi_gp_pbwd_ws_doubles(const iwvi_gp_desc* d) {
+  if (iwvi_check_gp_desc(d) != IWVI_OK) return -1;
+  return pbwd_ws_layout(iwvi_round_up(d->M, IWVI_BLK)).total;
+}
+
+extern "C" int iwvi_gp_prologue_fwd(const iwvi_gp_desc* d, const double* Z, const double* ls, const double* variance,
+                                    const double* q_mu, const double* q_sqrt, double* Lm, double* aux, double* kl,
+                                    int32_t* info, void* stream) {
+  int rc = iwvi_check_gp_desc(d);
+  if (rc != IWVI_OK) return rc;
+  if (!Z || !ls || !variance || !q_mu || !q_sqrt || !Lm || !aux || !kl || !info) return IWVI_ERR_NULL;
+  ProParams p;
+  p.d = *d; p.Z = Z; p.ls = ls; p.variance = variance; p.q_mu = q_mu; p.q_sqrt = q_sqrt;
+  p.Lm = Lm; p.aux = aux; p.kl = kl; p.info = info;
+  cudaStream_t st = (cudaStream_t)stream;
+  gp_pack_kernel<<<IWVI_PACK_GRID, 256, 0, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  const int smem_bytes = (5 * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK * 36) * 8;
+  if (cudaFuncSetAttribute(gp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  gp_chol_kernel<<<1, 256, smem_bytes, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* Z,
+                                    const double* ls, const double* variance, const double* q_mu,
+                                    const double* q_sqrt, const double* dLm, const double* dkl, double* dZ,
+                                    double* dls, double* dvariance, double* dq_mu, double* dq_sqrt, double* ws,
+                                    void* stream) {
+  int rc = iwvi_check_gp_desc(d);
+  if (rc != IWVI_OK) return rc;
+  if (!Lm || !aux || !Z || !ls || !variance || !q_mu || !q_sqrt || !dLm || !dkl || !dZ || !dls || !dvariance ||
+      !dq_mu || !dq_sqrt || !ws)
+    return IWVI_ERR_NULL;
+  const AuxLayout al = iwvi_aux_layout(d->M, d->D, d->R);
+  const PbwdWs wl = pbwd_ws_layout(al.Mp);
+  PbwdParams p;
+  p.d = *d; p.Lm = Lm; p.aux = aux; p.Z = Z; p.ls = ls; p.variance = variance; p.q_mu = q_mu; p.q_sqrt = q_sqrt;
+  p.dLm = dLm; p.dkl = dkl; p.dZ = dZ; p.dls = dls; p.dvariance = dvariance; p.dq_mu = dq_mu; p.dq_sqrt = dq_sqrt;
+  p.ws = ws; p.accumulate = (d->flags & IWVI_FLAG_ACCUM) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int phi_smem = 2 * IWVI_STAGE_DOUBLES * 8;
+  if (cudaFuncSetAttribute(pbwd_phi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phi_smem) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  pbwd_phi_kernel<<<al.NB * al.NB, 256, phi_smem, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  const int smem_bytes = (PS_TP * (al.Mp + 4) + IWVI_NST * IWVI_STAGE_DOUBLES + IWVI_NST) * 8;
+  if (cudaFuncSetAttribute(pbwd_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  // S1^T = P^T Lm^-1 (panel rows = columns of P), then Kbar' = S1 Lm^-1 (panel rows = rows of S1 = columns of S1^T)
+  pbwd_solve_kernel<1><<<al.Mp / PS_TP, 256, smem_bytes, st>>>(p, ws + wl.off_p, ws + wl.off_s1);
+  IWVI_CHECK_LAUNCH();
+  pbwd_solve_kernel<1><<<al.Mp / PS_TP, 256, smem_bytes, st>>>(p, ws + wl.off_s1, ws + wl.off_p);
+  IWVI_CHECK_LAUNCH();
+  pbwd_gram_kernel<<<(al.Mp + 7) / 8, 256, 0, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  pbwd_final_kernel<<<1, 64, 0, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}

@@ -217,9 +217,9 @@ __host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
   s.gmb = o;    o += IWVI_MAX_R * TP;
   s.gvb = o;    o += IWVI_MAX_R * TP;
   s.gsum = o;   o += TP;
-  s.gs = o;     o += TP;
-  s.gr = o;     o += 2 * IWVI_BLK;
-  s.dls = o;    o += 32;
+  s.gs = o;     o += 4 * TP;               // [WMG][TP] column sums of G per warp row group
+  s.gr = o;     o += 2 * 4 * IWVI_BLK;     // [2][WNG][64] row sums of G per warp column group, double buffered
+  s.dls = o;    o += 8 * 32;               // [warp][32]
   s.red = o;    o += 32;
   s.bars = o;   o += IWVI_NST;
   s.total_doubles = o;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
 
   // this CTA's partial of dZ (accumulated across its tiles in global memory, exclusive owner) and dls
   for (int idx = tid; idx < p.wl.tile_stride; idx += blockDim.x) mypart[idx] = 0.0;
-  if (tid < 32) dls_s[tid] = 0.0;
+  dls_s[tid] = 0.0;
   double dvar_acc = 0.0;
 
   StagePipe pipe;
@@ -295,8 +295,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
       if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
       xs[idx] = v;
     }
-    if (tid < TP) gs_s[tid] = 0.0;
-    if (tid < IWVI_BLK) gr_s[tid] = 0.0;
+    for (int idx = tid; idx < 4 * TP; idx += blockDim.x) gs_s[idx] = 0.0;
     __syncthreads();
     if (tid < TP) {
       double s = 0.0;
@@ -417,7 +416,6 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
     for (int b = 0; b < 4; b++) { accx[b][0] = 0.0; accx[b][1] = 0.0; }
     for (int i = 0; i < NB; i++) {
       const double* st = pipe.wait();   // scaled inducing inputs of block i: st[m*ldz + k]
-      if (tid < IWVI_BLK) gr_s[((i + 1) & 1) * IWVI_BLK + tid] = 0.0;
       double acc[C::TM][C::TN][2];
       acc_zero<C::TM, C::TN>(acc);
       warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
@@ -448,7 +446,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
           }
         rs += __shfl_xor_sync(0xffffffffu, rs, 1);
         rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-        if (t == 0) atomicAdd(&gr_s[(i & 1) * IWVI_BLK + wm0 + a * 8 + g], rs);
+        if (t == 0) gr_s[((i & 1) * C::WNG + warp / C::WMG) * IWVI_BLK + wm0 + a * 8 + g] = rs;
       }
 #pragma unroll
       for (int b = 0; b < C::TN; b++)
@@ -458,7 +456,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) atomicAdd(&gs_s[wn0 + b * 8 + 2 * t + c], v);
+          if (g == 0) gs_s[(warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c] += v;
         }
       // lengthscale adjoint, accumulated directly (no cancellation): sum G (x~_d - z~_d)^2
       for (int dd = 0; dd < D; dd++) {
@@ -475,7 +473,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
             }
         }
         s = warp_sum(s);
-        if (lane == 0) atomicAdd(&dls_s[dd], s);
+        if (lane == 0) dls_s[warp * 32 + dd] += s;
       }
       __syncthreads();   // G_i visible in the panel, gr_s complete
 
@@ -515,7 +513,9 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
         }
         const int ml = warp * 8 + g;
         const int mg = i * IWVI_BLK + ml;
-        const double grv = gr_s[(i & 1) * IWVI_BLK + ml];
+        double grv = 0.0;
+#pragma unroll
+        for (int wg = 0; wg < C::WNG; wg++) grv += gr_s[((i & 1) * C::WNG + wg) * IWVI_BLK + ml];
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
@@ -535,7 +535,9 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
       const int n = warp * 8 + g;
       const size_t pt = (size_t)(n0 + n);
       if (pt < (size_t)T) {
-        const double gsv = gs_s[n];
+        double gsv = 0.0;
+#pragma unroll
+        for (int wg = 0; wg < C::WMG; wg++) gsv += gs_s[wg * TP + n];
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
@@ -551,7 +553,11 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
   __syncthreads();
   const double tot = block_sum(dvar_acc, red);
   if (tid == 0) mypart[(size_t)Mp * ldz + 32] = tot / variance;
-  if (tid < 32) mypart[(size_t)Mp * ldz + tid] = (tid < D) ? -2.0 * consts[IWVI_C_INVLS + tid] * dls_s[tid] : 0.0;
+  if (tid < 32) {
+    double s = 0.0;
+    for (int w = 0; w < C::NW; w++) s += dls_s[w * 32 + tid];
+    mypart[(size_t)Mp * ldz + tid] = (tid < D) ? -2.0 * consts[IWVI_C_INVLS + tid] * s : 0.0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -78,7 +78,7 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int TP, int Mp, int ldx) {
   s.xs = o;     o += TP * ldx;
   s.xn = o;     o += TP;
   s.fv0 = o;    o += TP;
-  s.usq = o;    o += IWVI_MAX_R * TP;
+  s.usq = o;    o += IWVI_MAX_R * TP * (TP >= 64 ? 2 : 4);   // one slot per warp row group: fixed-order sums
   s.gm = o;     o += IWVI_MAX_R * TP;
   s.bars = o;   o += IWVI_NST;
   s.total_doubles = o;
@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
       if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
       xs[idx] = v;
     }
-    for (int idx = tid; idx < IWVI_MAX_R * TP; idx += blockDim.x) usq[idx] = 0.0;
     __syncthreads();
     if (tid < TP) {
       double s = 0.0;
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) atomicAdd(&usq[r * TP + wn0 + b * 8 + 2 * t + c], v);
+          if (g == 0) usq[(r * C::WMG + warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c] = v;
         }
     }
     __syncthreads();
@@ -282,7 +281,10 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
       double gm[IWVI_MAX_R], gv[IWVI_MAX_R], gs[IWVI_MAX_R];
       for (int r = 0; r < R; r++) {
         gm[r] = gms[r * TP + n];
-        gv[r] = variance - fv0[n] + usq[r * TP + n];
+        double us = 0.0;
+#pragma unroll
+        for (int wg = 0; wg < C::WMG; wg++) us += usq[(r * C::WMG + wg) * TP + n];
+        gv[r] = variance - fv0[n] + us;
         gs[r] = do_sample ? gm[r] + p.eps[pt * R + r] * sqrt(gv[r]) : 0.0;
         if (do_save) {
           p.save[sv.off_gvar + pt * R + r] = gv[r];

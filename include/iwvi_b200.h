@@ -26,6 +26,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
 
 #define IWVI_VERSION 100
 
@@ -59,6 +62,7 @@ extern "C" {
 /* flags */
 #define IWVI_FLAG_SAMPLE 1  /* eps given: produce sample = mean + eps*sqrt(var) (temp_workaround.py:89-91) */
 #define IWVI_FLAG_SAVE   2  /* keep A, U, latent mean/var for the backward pass */
+#define IWVI_FLAG_ACCUM  4  /* iwvi_gp_prologue_bwd adds into its outputs instead of overwriting them */
 
 typedef struct iwvi_gp_desc {
   int32_t T;      /* points in this call                                    */
@@ -121,7 +125,8 @@ int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux,
 /*
  * Adjoint of iwvi_gp_prologue_fwd: Cholesky adjoint (TF CholeskyGrad), gram adjoint of Kuu and the KL
  * adjoint.  dLm [Mp,Mp] lower, dkl [1] (device scalar cotangent of kl).
- *   out (overwritten): dZ [M,D], dls [D], dvariance [1], dq_mu [M,R], dq_sqrt [R,M,M].
+ *   out (overwritten, or added to under IWVI_FLAG_ACCUM so that the outputs of iwvi_gp_rows_bwd can be passed
+ *        straight in): dZ [M,D], dls [D], dvariance [1], dq_mu [M,R], dq_sqrt [R,M,M].
  */
 int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* Z,
                          const double* ls, const double* variance, const double* q_mu, const double* q_sqrt,
@@ -185,6 +190,20 @@ int iwvi_iwelbo_bwd(const iwvi_elbo_desc* d, const double* fmean, const double* 
  * counter = ((first_point + p) * C + c) >> 1, lane (.. & 1) of a Box-Muller pair. */
 int iwvi_normal_fill(double* out, int64_t n_points, int32_t C, int64_t first_point, uint64_t seed, void* stream);
 
+/* ---- optimiser step either side of the path (experiments/build_models.py:284-295) ----
+ * gpflow.transforms.positive (Log1pe): theta = softplus(x) + 1e-6 for the first n entries. */
+int iwvi_positive_fwd(const double* x, double* theta, int64_t n, void* stream);
+/* tf.train.AdamOptimizer(lr) defaults on the flat unconstrained parameter buffer x [n], maximising the ELBO:
+ * grad_elbo [n] holds d ELBO / d (constrained value); the first n_pos entries are `positive`-transformed (the chain
+ * rule factor sigmoid(x) is applied here and theta_pos [n_pos] is refreshed after the update).  mask [n] (0/1) or
+ * NULL freezes entries (set_trainable(False), build_models.py:209,213,225-227).  t = 1, 2, ... is the step count. */
+int iwvi_adam_step(double* x, const double* grad_elbo, double* m, double* v, const double* mask, double* theta_pos,
+                   int64_t n, int64_t n_pos, double lr, double beta1, double beta2, double eps, int64_t t,
+                   void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif
