@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""IW-ELBO training throughput on B200 (BASELINE.json metric: IW-ELBO train steps/s and KxN samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl b200|reference]
+
+One step = IW-ELBO forward + hand-written backward on one minibatch + (N>1) one NCCL all-reduce of the flat fp64
+gradient bucket + fused Adam update.  Synthetic data of the BASELINE config shape; float64 throughout.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the flop/byte conventions."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs -> (configuration, N, D, M, K, B per GPU, lik_variance)
+    'c1': dict(configuration='L1', N=200, D=1, M=50, K=20, B=200, lik_variance=0.1),
+    'c2': dict(configuration='L1_G5', N=10000, D=8, M=100, K=20, B=512, lik_variance=0.01),
+    'c3': dict(configuration='L1_G5_G5', N=100000, D=16, M=256, K=50, B=512, lik_variance=0.01),
+    'c4': dict(configuration='L1_G5', N=16384, D=8, M=512, K=256, B=4096, lik_variance=0.01),
+    'c5': dict(configuration='L1_G5_G5', N=1000000, D=8, M=256, K=50, B=512, lik_variance=0.01),
+}
+FP64_DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200 (profiles/FP64_PEAK_r01.md); MEASURED_PEAKS.json has no fp64 entry
+
+
+def make_data(N, D, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, D))
+    w = rng.standard_normal((D, 1)) / np.sqrt(D)
+    Y = np.sin(X @ w) + 0.1 * rng.standard_normal((N, 1))
+    return X, Y
+
+
+def layer_shapes(configuration, D):
+    """[(D_in, R)] for every GP layer of a configuration string (experiments/build_models.py:201-241)."""
+    out = []
+    D_in = D
+    for tok in [t for t in configuration.split('_') if t]:
+        c, d = tok[0], int(tok[1:])
+        if c == 'L':
+            D_in += d
+        else:
+            out.append((D_in, d))
+            D_in = D
+    out.append((D_in, 1))
+    return out
+
+
+def fwd_flops(T, M, D, R):
+    """SURVEY.md 8(d) triangular-aware convention, per GP layer forward."""
+    return T * ((1 + R) * M * M + 2 * M * (D + 2 * R + 1))
+
+
+def step_flops(cfg, B):
+    T = B * cfg['K']
+    f = sum(fwd_flops(T, cfg['M'], D, R) for D, R in layer_shapes(cfg['configuration'], cfg['D']))
+    return 3 * f
+
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'power_w_max': float(max(pw)),
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (float64 torch-CPU restatement of the reference, op for op) -- the reference itself needs
+# TensorFlow 1.x + GPflow 1.x, which cannot be installed here.
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_eval_time(cfg, spec, X, Y, B_sample, reps, warm=1, reference_style=True):
+    import torch
+    from oracle import iwvi_oracle as O
+    from oracle import synthetic as S
+    K = cfg['K']
+    Xb, Yb = X[:B_sample], Y[:B_sample]
+    eps = S.make_noise(spec, (B_sample, K), seed=0)
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        O.iw_elbo_and_grads(spec, Xb, Yb, eps, reference_style=reference_style)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def cpu_sample_rows(cfg):
+    """Rows of the minibatch the CPU arm evaluates per step, bounded so that one evaluation stays within seconds and
+    the materialised [B,R,M,K] / [B,R,K,K] tensors of the reference formulation stay within host memory."""
+    per_row = cfg['K'] * cfg['M'] * 6 * 8 * 6 + 2 * cfg['K'] * cfg['K'] * 8 * 6
+    budget = 6e9
+    return int(max(8, min(cfg['B'], budget // per_row)))
+
+
+def oracle_spec(cfg, X, Y):
+    from oracle import synthetic as S
+    return S.make_spec(X, cfg['configuration'], cfg['M'], cfg['K'], lik_variance=cfg['lik_variance'], seed=0, perturb=0.0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    cfg = CONFIGS[args.config]
+    X, Y = make_data(min(cfg['N'], 20000), cfg['D'], seed=0)
+    spec = oracle_spec(cfg, X, Y)
+    spec['num_data'] = cfg['N']
+    Bs = cpu_sample_rows(cfg)
+    times, threads = cpu_eval_time(cfg, spec, X, Y, Bs, reps=args.steps, warm=max(args.warmup, 1))
+    sec = float(np.mean(times))
+    value = Bs * cfg['K'] / sec
+    out = {
+        'impl': 'reference', 'metric': 'iw_elbo_train_KxN_samples_per_s', 'value': value, 'unit': 'KxN samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'steps_per_s': (Bs / cfg['B']) / sec, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.config, cfg, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': 'KxN samples/s', 'cores': threads, 'kind': 'port',
+                         'sample': 'oracle/iwvi_oracle.py (torch-CPU fp64 op-for-op restatement, reference-style KxK final '
+                                   'layer) forward+autograd on %d of %d minibatch rows x K=%d, no optimiser step; the '
+                                   'reference needs TF1/GPflow1 which cannot be installed here' % (Bs, cfg['B'], cfg['K'])},
+        'e2e': {'value': value, 'unit': 'KxN samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(name, cfg, gpus):
+    return {'workload': '%s: %s N=%d D=%d M=%d K=%d B=%d/GPU (BASELINE.json configs)' % (
+        name, cfg['configuration'], cfg['N'], cfg['D'], cfg['M'], cfg['K'], cfg['B']),
+        'global_batch_rows': cfg['B'] * gpus, 'points_per_gpu_step': cfg['B'] * cfg['K'],
+        'parallelism': 'dp%d rows sharded, one all-reduce of the flat fp64 gradient bucket' % gpus,
+        'optimizer': 'adam (fused kernel)',
+        'l2': 'no explicit flush: each step streams its own A/U panels (> 126 MB L2) and rewrites every buffer'}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--config', default='c3', choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from dgps_with_iwvi_b200 import capi
+    from dgps_with_iwvi_b200 import _lib as LIB
+    from dgps_with_iwvi_b200.build_models import build_model, spec_from_model
+    from dgps_with_iwvi_b200.models import Minibatch
+    from dgps_with_iwvi_b200.training import Trainer
+
+    cfg = CONFIGS[args.config]
+    B, K, N = cfg['B'], cfg['K'], cfg['N']
+    Bg = B * world
+    X, Y = make_data(N, cfg['D'], seed=0)
+    model = build_model(X, Y, cfg['configuration'], M=cfg['M'], num_IW_samples=K, minibatch_size=Bg,
+                        likelihood_variance=cfg['lik_variance'], mode='IWAE', seed=0)
+    trainer = Trainer(model, B, lr=5e-3, seed=0)
+    eng = trainer.engine
+    dev = eng.dev
+    stream_idx = Minibatch(N, Bg, seed=0)          # same stream on every rank; each takes its contiguous slice
+
+    def next_idx():
+        return stream_idx.next()[rank * B:(rank + 1) * B]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs: the dataset lives in HBM, minibatches are gathered there ----
+    Xd, Yd = model.X, model.Y
+
+    def step_resident():
+        idx = torch.as_tensor(next_idx(), device=dev)
+        return trainer.step_device(Xd[idx], Yd[idx])
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step_resident()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = capi.LAUNCHES - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    eng.check_info()
+    last_elbo = float(loss.item())
+
+    # ---- end to end: pinned host minibatch in, ELBO (float) out, every step ----
+    Xh, Yh = torch.as_tensor(X).pin_memory(), torch.as_tensor(Y).pin_memory()
+    stage = [(torch.empty(B, cfg['D'], dtype=torch.float64).pin_memory(), torch.empty(B, 1, dtype=torch.float64).pin_memory())
+             for _ in range(2)]
+
+    def step_e2e(i):
+        idx = torch.as_tensor(next_idx())
+        xs, ys = stage[i % 2]
+        torch.index_select(Xh, 0, idx, out=xs)
+        torch.index_select(Yh, 0, idx, out=ys)
+        return trainer.step(xs, ys)        # H2D copies + step + D2H of the ELBO
+
+    for i in range(max(args.warmup // 2, 3)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    ev1.record()
+    barrier()
+    ms_e2e = max(ev0.elapsed_time(ev1), 0.0)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timing of the three DMMA kernels of one GP layer (CUDA events on the launching stream) ----
+    kern = kernel_timings(eng, capi, LIB, torch)
+    sec = ms / 1e3 / args.steps
+    value = Bg * K / sec
+    flops = step_flops(cfg, B)
+    dom = max(kern, key=lambda k: k['ms'] * k['launches_per_step'])
+    out = {
+        'metric': 'iw_elbo_train_KxN_samples_per_s', 'value': value, 'unit': 'KxN samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'steps_per_s': 1.0 / sec,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.config, cfg, world),
+        'clocks': clocks,
+        'e2e': {'value': Bg * K / (ms_e2e / 1e3 / args.steps), 'unit': 'KxN samples/s',
+                'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': B * (cfg['D'] + 1) * 8 + 0,
+                'd2h_bytes_per_step': 8},
+        'gpu_launches': launches,
+        'step_algorithmic_gflop_per_gpu': flops / 1e9,
+        'step_tflops_per_gpu': flops / sec / 1e12,
+        'step_frac_of_fp64_dmma_peak': flops / sec / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+        'roofline': {'bound': 'tensor', 'kernel': dom['kernel'], 'achieved': dom['tflops'], 'peak': FP64_DMMA_PEAK_TFLOPS,
+                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / FP64_DMMA_PEAK_TFLOPS, 'traffic': None,
+                     'peak_source': 'FP64 DMMA issue-rate probe measured on this pool (profiles/FP64_PEAK_r01.md); '
+                                    'MEASURED_PEAKS.json carries only bf16 and HBM'},
+        'kernels': kern,
+        'elbo_last': last_elbo,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        spec = spec_from_model(model)
+        Bs = cpu_sample_rows(cfg)
+        times, threads = cpu_eval_time(cfg, spec, X, Y, Bs, reps=3, warm=1)
+        v = Bs * K / float(np.mean(times))
+        out['cpu_baseline'] = {'value': v, 'unit': 'KxN samples/s', 'cores': threads, 'kind': 'port',
+                               'ms_per_eval': float(np.mean(times)) * 1e3,
+                               'sample': 'oracle (torch-CPU fp64 restatement of the reference, KxK final layer) '
+                                         'forward+autograd on %d of %d minibatch rows x K=%d, 3 evals after 1 warm-up, no '
+                                         'optimiser step' % (Bs, B, K)}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_timings(eng, capi, LIB, torch, reps=5):
+    """Times gp_rows_fwd_kernel, gp_tile_bwd_kernel and gp_reduce_bwd_kernel of the widest inner GP layer alone, on the
+    buffers the last step left behind.  Algorithmic flops per launch:
+      rows_fwd : T[(1+R)M^2 + 2M(D+2R+1)]           tile_bwd : T[(1+R)M^2 + 2M(3D+R+1)]
+      reduce   : T(1+R)M^2 (1 + 1/NB)  (lower-triangular block pairs only) + 2TMR"""
+    gps = [r for r in eng.recs if r['type'] == 'gp']
+    r = max(gps, key=lambda q: q['R'] * q['M'] * q['M'])
+    n_like = len(gps)
+    T, M, D, R = eng.T, r['M'], r['D'], r['R']
+    NB = r['Mp'] // 64
+    flat, layer, base, feat = eng.flat, r['layer'], r['base'], r['feat']
+    W = flat.cview(layer.kern.W) if r['mix'] else None
+    lin = r['mf'] == 'Linear'
+    mfA = flat.cview(layer.mean_function.A) if lin else None
+    mfb = flat.cview(layer.mean_function.b) if lin else None
+    scratch = [torch.zeros_like(flat.gview(p)) for p in (feat.Z, base.lengthscales, base.variance, layer.q_mu, layer.q_sqrt)]
+    if scratch[1].numel() != D:
+        scratch[1] = torch.zeros(D, dtype=torch.float64, device=eng.dev)
+    dW = torch.zeros_like(W) if r['mix'] else None
+    dA = torch.zeros_like(mfA) if lin else None
+    db = torch.zeros_like(mfb) if lin else None
+    d_s = torch.randn(T, r['P'], dtype=torch.float64, device=eng.dev)
+
+    def fwd():
+        capi.gp_rows_fwd(r['d'], r['Lm'], r['aux'], r['Fin'], W, mfA, mfb, r['eps'], r['sample'], r['mean'], r['var'],
+                         r['save'])
+
+    def bwd(flag):
+        d = capi.with_flags(r['d'], r['d'].flags | flag)
+        capi.gp_rows_bwd(d, r['Lm'], r['aux'], r['save'], r['Fin'], W, mfA, mfb, r['eps'],
+                         d_s if r['sampled'] else None, None if r['sampled'] else d_s, None if r['sampled'] else d_s,
+                         r['dX'], scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], r['dLm'], dW, dA, db,
+                         eng.bwd_ws)
+
+    bwd(0)
+    cases = [
+        ('gp_rows_fwd_kernel', fwd, T * ((1 + R) * M * M + 2 * M * (D + 2 * R + 1))),
+        ('gp_tile_bwd_kernel', lambda: bwd(LIB.FLAG_ONLY_TILE if hasattr(LIB, 'FLAG_ONLY_TILE') else 32),
+         T * ((1 + R) * M * M + 2 * M * (3 * D + R + 1))),
+        ('gp_reduce_bwd_kernel', lambda: bwd(64), T * (1 + R) * M * M * (1 + 1.0 / NB) + 2 * T * M * R),
+    ]
+    out = []
+    for name, fn, fl in cases:
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out.append({'kernel': name, 'layer': 'M=%d D=%d R=%d T=%d' % (M, D, R, T), 'ms': ms, 'gflop': fl / 1e9,
+                    'tflops': fl / (ms * 1e-3) / 1e12, 'frac_of_fp64_dmma_peak': fl / (ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                    'launches_per_step': n_like})
+    return out
+
+
+if __name__ == '__main__':
+    main()

@@ -9,6 +9,14 @@ from . import _lib as L
 
 F64 = torch.float64
 
+# kernels launched so far through this module (each entry point's launch count is fixed by csrc/*.cu)
+LAUNCHES = 0
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _ptr(t):
     if t is None:
@@ -88,11 +96,13 @@ def elbo_ws_doubles(d):
 
 
 def gp_prologue_fwd(d, Z, ls, variance, q_mu, q_sqrt, Lm, aux, kl, info):
+    _count(2)
     L.check(L.load().iwvi_gp_prologue_fwd(C.byref(d), _ptr(Z), _ptr(ls), _ptr(variance), _ptr(q_mu), _ptr(q_sqrt),
                                           _ptr(Lm), _ptr(aux), _ptr(kl), _ptr(info), _stream()), 'iwvi_gp_prologue_fwd')
 
 
 def gp_rows_fwd(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save):
+    _count(1)
     L.check(L.load().iwvi_gp_rows_fwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(X), _ptr(W), _ptr(mfA), _ptr(mfb),
                                       _ptr(eps), _ptr(sample), _ptr(mean), _ptr(var), _ptr(save), _stream()),
             'iwvi_gp_rows_fwd')
@@ -100,6 +110,8 @@ def gp_rows_fwd(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save):
 
 def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu, dq_sqrt,
                 dLm, dW, dmfA, dmfb, ws):
+    only = d.flags & 240
+    _count(bin(only).count('1') if only else 4)
     L.check(L.load().iwvi_gp_rows_bwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(save), _ptr(X), _ptr(W), _ptr(mfA),
                                       _ptr(mfb), _ptr(eps), _ptr(d_sample), _ptr(d_mean), _ptr(d_var), _ptr(dX),
                                       _ptr(dZ), _ptr(dls), _ptr(dvariance), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(dLm),
@@ -107,6 +119,7 @@ def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, 
 
 
 def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls, dvariance, dq_mu, dq_sqrt, ws):
+    _count(5)
     L.check(L.load().iwvi_gp_prologue_bwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(Z), _ptr(ls), _ptr(variance),
                                           _ptr(q_mu), _ptr(q_sqrt), _ptr(dLm), _ptr(dkl), _ptr(dZ), _ptr(dls),
                                           _ptr(dvariance), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(ws), _stream()),
@@ -114,37 +127,44 @@ def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls
 
 
 def lv_fwd(d, F, enc_in, params, eps, samples, kl, mu, sigma):
+    _count(1)
     L.check(L.load().iwvi_lv_fwd(C.byref(d), _ptr(F), _ptr(enc_in), _ptr(params), _ptr(eps), _ptr(samples), _ptr(kl),
                                  _ptr(mu), _ptr(sigma), _stream()), 'iwvi_lv_fwd')
 
 
 def lv_bwd(d, F, enc_in, params, eps, mu, sigma, d_samples, d_kl, d_mu, d_sigma, d_params, dF, ws):
+    _count(1 if d.prior else 2)
     L.check(L.load().iwvi_lv_bwd(C.byref(d), _ptr(F), _ptr(enc_in), _ptr(params), _ptr(eps), _ptr(mu), _ptr(sigma),
                                  _ptr(d_samples), _ptr(d_kl), _ptr(d_mu), _ptr(d_sigma), _ptr(d_params), _ptr(dF),
                                  _ptr(ws), _stream()), 'iwvi_lv_bwd')
 
 
 def iwelbo_fwd(d, fmean, fvar, Y, lik_var, kl_local, elbo_data, logp, w, ws):
+    _count(2)
     L.check(L.load().iwvi_iwelbo_fwd(C.byref(d), _ptr(fmean), _ptr(fvar), _ptr(Y), _ptr(lik_var), _ptr(kl_local),
                                      _ptr(elbo_data), _ptr(logp), _ptr(w), _ptr(ws), _stream()), 'iwvi_iwelbo_fwd')
 
 
 def iwelbo_bwd(d, fmean, fvar, Y, lik_var, w, d_elbo, dmean, dvar, dkl_local, dlik, ws):
+    _count(2)
     L.check(L.load().iwvi_iwelbo_bwd(C.byref(d), _ptr(fmean), _ptr(fvar), _ptr(Y), _ptr(lik_var), _ptr(w),
                                      _ptr(d_elbo), _ptr(dmean), _ptr(dvar), _ptr(dkl_local), _ptr(dlik), _ptr(ws),
                                      _stream()), 'iwvi_iwelbo_bwd')
 
 
 def normal_fill(out, n_points, C_, first_point, seed):
+    _count(1)
     L.check(L.load().iwvi_normal_fill(_ptr(out), int(n_points), int(C_), int(first_point),
                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()), 'iwvi_normal_fill')
 
 
 def positive_fwd(x, theta, n):
+    _count(1)
     L.check(L.load().iwvi_positive_fwd(_ptr(x), _ptr(theta), int(n), _stream()), 'iwvi_positive_fwd')
 
 
 def adam_step(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr, beta1, beta2, eps, t):
+    _count(1)
     L.check(L.load().iwvi_adam_step(_ptr(x), _ptr(grad_elbo), _ptr(m), _ptr(v), _ptr(mask), _ptr(theta_pos), int(n),
                                     int(n_pos), float(lr), float(beta1), float(beta2), float(eps), int(t), _stream()),
             'iwvi_adam_step')

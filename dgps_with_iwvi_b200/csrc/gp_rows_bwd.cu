@@ -815,11 +815,15 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   p.ntiles = p.wl.Tp / TP;   // covers the zero-padded rows too, so every row of Bbar is written
   p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
   cudaStream_t st = (cudaStream_t)stream;
+  const int only = d->flags & IWVI_FLAG_ONLY_MASK;
 
-  gp_epi_bwd_kernel<<<p.wl.n_epi, EPI_PTS, 0, st>>>(p);
-  IWVI_CHECK_LAUNCH();
+  if (!only || (only & IWVI_FLAG_ONLY_EPI)) {
+    gp_epi_bwd_kernel<<<p.wl.n_epi, EPI_PTS, 0, st>>>(p);
+    IWVI_CHECK_LAUNCH();
+  }
 
-  if (TP == 64) {
+  if (only && !(only & IWVI_FLAG_ONLY_TILE)) {
+  } else if (TP == 64) {
     if (cudaFuncSetAttribute(gp_tile_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
       return IWVI_ERR_LAUNCH;
     gp_tile_bwd_kernel<64><<<p.grid_tile, 256, smem_bytes, st>>>(p);
@@ -830,14 +834,17 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   }
   IWVI_CHECK_LAUNCH();
 
-  const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK + 2 * IWVI_BLK * IWVI_MAX_R + RED_NST) * 8;
-  if (cudaFuncSetAttribute(gp_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem) != cudaSuccess)
-    return IWVI_ERR_LAUNCH;
-  const int red_grid = (d->R + 1) * p.wl.S * p.wl.npairs;
-  gp_reduce_bwd_kernel<<<red_grid, 256, red_smem, st>>>(p);
-  IWVI_CHECK_LAUNCH();
-
-  gp_finalize_bwd_kernel<<<2 * nsm, 256, 0, st>>>(p);
-  IWVI_CHECK_LAUNCH();
+  if (!only || (only & IWVI_FLAG_ONLY_REDUCE)) {
+    const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK + 2 * IWVI_BLK * IWVI_MAX_R + RED_NST) * 8;
+    if (cudaFuncSetAttribute(gp_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem) != cudaSuccess)
+      return IWVI_ERR_LAUNCH;
+    const int red_grid = (d->R + 1) * p.wl.S * p.wl.npairs;
+    gp_reduce_bwd_kernel<<<red_grid, 256, red_smem, st>>>(p);
+    IWVI_CHECK_LAUNCH();
+  }
+  if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {
+    gp_finalize_bwd_kernel<<<2 * nsm, 256, 0, st>>>(p);
+    IWVI_CHECK_LAUNCH();
+  }
   return IWVI_OK;
 }

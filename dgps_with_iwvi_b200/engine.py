@@ -1,0 +1,378 @@
+"""Execution plan of the IW-ELBO hot path: one object per (model, B, K, mode) that owns every device buffer the C ABI
+needs (the library itself never allocates) and strings the stages together, forward and backward, without autograd:
+
+    forward : gp_prologue_fwd (all GP layers) -> [lv_fwd | gp_rows_fwd]* -> iwelbo_fwd
+    backward: iwelbo_bwd -> [gp_rows_bwd + gp_prologue_bwd | lv_bwd]* (reversed)
+
+This is reference models.py:112-150 (DGP_IWVI._build_likelihood), models.py:49-86 (DGP_VI) and models.py:93-107
+(prediction) plus the tf.gradients call the optimisers make (build_models.py:293-295), on a flat parameter buffer:
+gradients with respect to the *constrained* values land in one flat float64 bucket (`flat.g`) whose last slot carries
+the ELBO itself, so that data-parallel training needs a single all-reduce (training.py)."""
+import numpy as np
+import torch
+
+from . import _lib as LIB
+from . import capi
+from .params import Log1pe
+
+F64 = torch.float64
+
+
+def _ceil_even(n):
+    return (n + 1) // 2 * 2
+
+
+class FlatParams:
+    """All parameters of a model in one unconstrained float64 buffer `x` (positive-transformed entries first),
+    their constrained values (`theta_pos` for the positive block, `x` itself elsewhere), the gradient bucket `g`
+    (+1 slot for the ELBO) and the trainable mask.  Parameter objects are re-bound to views of `x`."""
+
+    def __init__(self, model):
+        named = list(model.named_parameters())
+        pos = [(n, p) for n, p in named if isinstance(p.transform, Log1pe)]
+        rest = [(n, p) for n, p in named if not isinstance(p.transform, Log1pe)]
+        self.entries = {}
+        off = 0
+        for n, p in pos:
+            self.entries[id(p)] = (n, off, p.size, p.shape, True)
+            off += p.size
+        self.n_pos = off
+        off = _ceil_even(off)
+        for n, p in rest:
+            self.entries[id(p)] = (n, off, p.size, p.shape, False)
+            off = _ceil_even(off + p.size)
+        self.n = off
+        dev = named[0][1].unconstrained.device
+        self.device = dev
+        self.x = torch.zeros(self.n, dtype=F64, device=dev)
+        self.theta_pos = torch.zeros(max(self.n_pos, 1), dtype=F64, device=dev)
+        self.g = torch.zeros(self.n + 2, dtype=F64, device=dev)
+        self.mask = torch.zeros(self.n, dtype=F64, device=dev)
+        self.params = [p for _, p in pos + rest]
+        for p in self.params:
+            _, o, sz, shape, _ = self.entries[id(p)]
+            p._rebind(self.x[o:o + sz].view(shape))
+        self.refresh_mask()
+
+    @staticmethod
+    def of(model):
+        flat = model.__dict__.get('_flat')
+        if flat is None:
+            flat = FlatParams(model)
+            object.__setattr__(model, '_flat', flat)
+        return flat
+
+    def refresh_mask(self):
+        self.mask.zero_()
+        for p in self.params:
+            _, o, sz, _, _ = self.entries[id(p)]
+            if p.trainable:
+                self.mask[o:o + sz] = 1.0
+
+    def refresh_constrained(self):
+        if self.n_pos:
+            capi.positive_fwd(self.x, self.theta_pos, self.n_pos)
+
+    def cview(self, p):
+        """Constrained value of parameter p as a view (valid after refresh_constrained)."""
+        _, o, sz, shape, is_pos = self.entries[id(p)]
+        src = self.theta_pos if is_pos else self.x
+        return src[o:o + sz].view(shape if shape else (1,))
+
+    def gview(self, p):
+        _, o, sz, shape, _ = self.entries[id(p)]
+        return self.g[o:o + sz].view(shape if shape else (1,))
+
+    @property
+    def loss_slot(self):
+        return self.g[self.n:self.n + 1]
+
+    def grads_by_name(self):
+        return {self.entries[id(p)][0]: self.gview(p).detach().clone() for p in self.params}
+
+
+def layer_seed(seed, step, layer):
+    return (int(seed) * 0x9E3779B97F4A7C15 + int(step) * 0xBF58476D1CE4E5B9 + (layer + 1) * 0x94D049BB133111EB) \
+        & 0xFFFFFFFFFFFFFFFF
+
+
+class Engine:
+    """mode 'iw'      : DGP_IWVI._build_likelihood, points = [B, K] data-major (models.py:113-116)
+       mode 'vi'      : DGP_VI._build_likelihood,   points = [S*B] sample-major (models.py:50-53), K := S
+       mode 'predict' : propagate without amortisation inputs, points = [S, N] (models.py:93-107), B := N, K := S"""
+
+    def __init__(self, model, B, K, mode='iw', world_size=1, rank=0):
+        from .layers import GPLayer, LatentVariableLayer
+        if not torch.cuda.is_available():
+            raise RuntimeError('dgps_with_iwvi_b200: no CUDA device -- the IW-ELBO path has no CPU fallback')
+        LIB.load()
+        assert mode in ('iw', 'vi', 'predict')
+        self.model, self.B, self.K, self.mode = model, int(B), int(K), mode
+        self.world_size, self.rank = int(world_size), int(rank)
+        self.T = T = self.B * self.K
+        self.flat = flat = FlatParams.of(model)
+        dev = flat.device
+        self.dev = dev
+        self.Dx, self.Dy = int(model.Dx), int(model.Dy)
+        self.train = mode != 'predict'
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        self.X = z(self.B, self.Dx)
+        self.Y = z(self.B, self.Dy)
+        self.XY = z(self.B, self.Dx + self.Dy)
+        layers = list(model.layers)
+        self.n_gp = sum(isinstance(l, GPLayer) for l in layers)
+        self.kls = z(max(self.n_gp, 1))
+        self.infos = torch.zeros(max(self.n_gp, 1), dtype=torch.int32, device=dev)
+        self.one = torch.ones(1, dtype=F64, device=dev)
+        self.dkl = torch.full((1,), -1.0 / self.world_size, dtype=F64, device=dev)
+        self.recs = []
+        D_cur = self.Dx
+        gi = 0
+        max_bwd_ws = max_pbwd_ws = max_lv_ws = 0
+        for li, layer in enumerate(layers):
+            last = li == len(layers) - 1
+            if isinstance(layer, LatentVariableLayer):
+                Lw = layer.latent_dim
+                first = li == 0
+                prior = mode == 'predict'
+                bcast = first and mode == 'iw'
+                Be, Kt = (self.B, self.K) if bcast else (T, 1)
+                enc = layer.encoder
+                d = capi.lv_desc(Be, Kt, D_cur, self.Dx + self.Dy, Lw, None if prior else enc.layer_dims,
+                                 sampled=(mode == 'iw'), f_bcast=bcast, prior=prior,
+                                 prior_mu=layer.prior_mu, prior_sigma=layer.prior_sigma)
+                r = dict(type='lv', layer=layer, d=d, idx=li, Lw=Lw, Df=D_cur, bcast=bcast, Be=Be, first=first,
+                         samples=z(T, D_cur + Lw), kl=z(T, Lw), eps=z(T, Lw), mu=z(Be, Lw), sigma=z(Be, Lw),
+                         enc_in=None if (bcast or prior) else z(T, self.Dx + self.Dy))
+                if not prior:
+                    ps = [p for pair in zip(enc.Ws, enc.bs) for p in pair]
+                    offs = [flat.entries[id(p)][1] for p in ps]
+                    sizes = [_ceil_even(flat.entries[id(p)][2]) for p in ps]
+                    n_par = capi.lv_param_doubles(d)
+                    contiguous = all(offs[i] + sizes[i] == offs[i + 1] for i in range(len(ps) - 1)) and \
+                        all(flat.entries[id(p)][2] % 2 == 0 for p in ps[:-1])
+                    r['packed_view'] = contiguous
+                    if contiguous:
+                        r['params'] = flat.x[offs[0]:offs[0] + n_par]
+                        r['d_params'] = flat.g[offs[0]:offs[0] + n_par]
+                    else:   # odd-sized tensors leave alignment gaps in the flat buffer: pack/unpack around the call
+                        r['params'] = z(n_par)
+                        r['d_params'] = z(n_par)
+                        r['plist'] = ps
+                    if self.train:
+                        max_lv_ws = max(max_lv_ws, capi.lv_bwd_ws_doubles(d))
+                        r['dF'] = None if first else z(T, D_cur)
+                D_cur += Lw
+            else:
+                kern = layer.kern
+                mix = hasattr(kern, 'W')
+                base = kern.kernel if mix else kern
+                feat = layer.feature.feat if hasattr(layer.feature, 'feat') else layer.feature
+                M, R = layer.num_inducing, layer.num_outputs
+                P = kern.W.shape[0] if mix else R
+                D = D_cur
+                assert feat.Z.shape == (M, D), 'inducing inputs %s do not match layer input width %d' % (feat.Z.shape, D)
+                mfk = layer.mean_function.kind
+                sample = not last   # the final layer's sample is never consumed (models.py:133-150, :96-97)
+                flags = (LIB.FLAG_SAMPLE if sample else 0) | (LIB.FLAG_SAVE if self.train else 0)
+                d = capi.gp_desc(T, M, D, R, P, base.kind, mix, mfk, flags, layer.jitter)
+                Mp = capi.gp_mp(M)
+                r = dict(type='gp', layer=layer, d=d, idx=li, gi=gi, M=M, R=R, P=P, D=D, mix=mix, mf=mfk, Mp=Mp,
+                         sampled=sample, base=base, feat=feat, ard=base.ARD or D == 1,
+                         Lm=z(Mp, Mp), aux=z(capi.gp_aux_doubles(d)), kl=self.kls[gi:gi + 1],
+                         info=self.infos[gi:gi + 1], mean=z(T, P), var=z(T, P),
+                         sample=z(T, P) if sample else None, eps=z(T, R) if sample else None,
+                         ls_vec=None if (base.ARD or D == 1) else z(D))
+                if self.train:
+                    r['save'] = z(capi.gp_save_doubles(d))
+                    r['dLm'] = z(Mp, Mp)
+                    r['dX'] = z(T, D)
+                    r['dls_vec'] = None if r['ard'] else z(D)
+                    max_bwd_ws = max(max_bwd_ws, capi.gp_bwd_ws_doubles(d))
+                    max_pbwd_ws = max(max_pbwd_ws, capi.gp_pbwd_ws_doubles(d))
+                gi += 1
+                D_cur = P
+            self.recs.append(r)
+        assert self.recs[-1]['type'] == 'gp', 'the last layer must be a GPLayer'
+        assert D_cur == self.Dy, 'final layer width %d != Dy %d' % (D_cur, self.Dy)
+        self.lv_recs = [r for r in self.recs if r['type'] == 'lv']
+        self.Lw_total = sum(r['Lw'] for r in self.lv_recs)
+        if mode != 'predict':
+            scale = float(model.num_data) / float(self.B * self.world_size)
+            self.ed = capi.elbo_desc(self.B, self.K, self.Dy, self.Lw_total, mode == 'iw', mode == 'iw', scale)
+            self.w = z(self.B, self.K)
+            self.logp = z(self.B)
+            self.elbo_data = z(1)
+            self.elbo_ws = z(capi.elbo_ws_doubles(self.ed))
+            self.kl_cat = z(T, self.Lw_total) if len(self.lv_recs) > 1 else None
+            self.dmean, self.dvar = z(T, self.Dy), z(T, self.Dy)
+            self.dkl_local = z(T, self.Lw_total) if self.Lw_total else None
+            self.bwd_ws = z(max(max_bwd_ws, 1))
+            self.pbwd_ws = z(max(max_pbwd_ws, 1))
+            self.lv_ws = z(max(max_lv_ws, 1))
+        self.X_tiled = None
+        if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
+            self.X_tiled = z(T, self.Dx)
+
+    # ------------------------------------------------------------------------------------------
+    def _cv(self, p):
+        return self.flat.cview(p)
+
+    def set_batch(self, X, Y=None):
+        """X [B, Dx], Y [B, Dy]: device or host tensors / arrays (copied into the plan's buffers)."""
+        X = torch.as_tensor(X, dtype=F64)
+        self.X.copy_(X.reshape(self.B, self.Dx), non_blocking=True)
+        if Y is not None:
+            Y = torch.as_tensor(Y, dtype=F64)
+            self.Y.copy_(Y.reshape(self.B, self.Dy), non_blocking=True)
+            self.XY[:, :self.Dx].copy_(self.X)
+            self.XY[:, self.Dx:].copy_(self.Y)
+
+    def _tile(self, A, out):
+        if self.mode == 'iw':      # data-major: point = n*K + k
+            out.view(self.B, self.K, -1).copy_(A[:, None, :].expand(self.B, self.K, A.shape[1]))
+        else:                      # sample-major: point = s*B + n
+            out.view(self.K, self.B, -1).copy_(A[None, :, :].expand(self.K, self.B, A.shape[1]))
+
+    def draw_noise(self, eps=None, seed=0, step=0, row0=0):
+        """eps: list with one entry per layer (None where no noise is consumed) of arrays shaped [*, C] in point
+        order, or None to draw counter-based noise keyed by (seed, step, layer) and the GLOBAL point index."""
+        for r in self.recs:
+            buf = r.get('eps')
+            if buf is None:
+                continue
+            if eps is not None:
+                e = eps[r['idx']]
+                buf.copy_(torch.as_tensor(np.asarray(e), dtype=F64).reshape(buf.shape), non_blocking=True)
+            else:
+                if self.mode == 'iw':
+                    capi.normal_fill(buf, self.T, buf.shape[1], int(row0) * self.K, layer_seed(seed, step, r['idx']))
+                else:
+                    capi.normal_fill(buf, self.T, buf.shape[1], 0, layer_seed(seed, step + 7919 * int(row0), r['idx']))
+
+    def forward(self):
+        flat = self.flat
+        flat.refresh_constrained()
+        for r in self.recs:
+            if r['type'] != 'gp':
+                continue
+            base, feat, layer = r['base'], r['feat'], r['layer']
+            if r['ard']:
+                ls = self._cv(base.lengthscales)
+            else:
+                r['ls_vec'].copy_(self._cv(base.lengthscales).expand(r['D']))
+                ls = r['ls_vec']
+            r['ls'] = ls
+            capi.gp_prologue_fwd(r['d'], self._cv(feat.Z), ls, self._cv(base.variance), self._cv(layer.q_mu),
+                                 self._cv(layer.q_sqrt), r['Lm'], r['aux'], r['kl'], r['info'])
+        F = None
+        if self.X_tiled is not None:
+            self._tile(self.X, self.X_tiled)
+            F = self.X_tiled
+        for r in self.recs:
+            if r['type'] == 'lv':
+                layer = r['layer']
+                if r['d'].prior:
+                    capi.lv_fwd(r['d'], F, None, None, r['eps'], r['samples'], r['kl'], r['mu'], r['sigma'])
+                else:
+                    if not r['packed_view']:
+                        torch.cat([self._cv(p).reshape(-1) for p in r['plist']], out=r['params'])
+                    if r['bcast']:
+                        Fin, enc_in = self.X, self.XY
+                    else:
+                        self._tile(self.XY, r['enc_in'])
+                        Fin, enc_in = F, r['enc_in']
+                    r['Fin'] = Fin
+                    capi.lv_fwd(r['d'], Fin, enc_in, r['params'], r['eps'], r['samples'], r['kl'], r['mu'], r['sigma'])
+                F = r['samples']
+            else:
+                layer, base = r['layer'], r['base']
+                r['Fin'] = F
+                capi.gp_rows_fwd(r['d'], r['Lm'], r['aux'], F,
+                                 self._cv(layer.kern.W) if r['mix'] else None,
+                                 self._cv(layer.mean_function.A) if r['mf'] == 'Linear' else None,
+                                 self._cv(layer.mean_function.b) if r['mf'] == 'Linear' else None,
+                                 r['eps'], r['sample'], r['mean'], r['var'], r.get('save'))
+                F = r['sample']
+        last = self.recs[-1]
+        if self.mode == 'predict':
+            return last['mean'], last['var']
+        if len(self.lv_recs) > 1:
+            torch.cat([r['kl'] for r in self.lv_recs], 1, out=self.kl_cat)
+            kl_local = self.kl_cat
+        elif self.lv_recs:
+            kl_local = self.lv_recs[0]['kl']
+        else:
+            kl_local = None
+        lik = self._cv(self.model.likelihood.variance)
+        capi.iwelbo_fwd(self.ed, last['mean'], last['var'], self.Y, lik, kl_local, self.elbo_data, self.logp, self.w,
+                        self.elbo_ws)
+        # ELBO of this rank's shard; the global KL enters with weight 1/world_size so that a SUM all-reduce is exact
+        torch.sub(self.elbo_data, self.kls[:self.n_gp].sum().reshape(1), alpha=1.0 / self.world_size,
+                  out=flat.loss_slot)
+        return flat.loss_slot
+
+    def backward(self):
+        flat = self.flat
+        last = self.recs[-1]
+        lik_p = self.model.likelihood.variance
+        capi.iwelbo_bwd(self.ed, last['mean'], last['var'], self.Y, self._cv(lik_p), self.w, self.one, self.dmean,
+                        self.dvar, self.dkl_local, flat.gview(lik_p), self.elbo_ws)
+        d_next = None          # cotangent of the current layer's output samples
+        lv_off = self.Lw_total
+        for r in reversed(self.recs):
+            if r['type'] == 'gp':
+                layer, base, feat = r['layer'], r['base'], r['feat']
+                is_last = r is last
+                gls = flat.gview(base.lengthscales) if r['ard'] else r['dls_vec']
+                W = self._cv(layer.kern.W) if r['mix'] else None
+                lin = r['mf'] == 'Linear'
+                mfA = self._cv(layer.mean_function.A) if lin else None
+                mfb = self._cv(layer.mean_function.b) if lin else None
+                outs = (flat.gview(feat.Z), gls, flat.gview(base.variance), flat.gview(layer.q_mu),
+                        flat.gview(layer.q_sqrt))
+                capi.gp_rows_bwd(r['d'], r['Lm'], r['aux'], r['save'], r['Fin'], W, mfA, mfb, r['eps'],
+                                 d_next if r['sampled'] else None,
+                                 self.dmean if is_last else None, self.dvar if is_last else None,
+                                 r['dX'], outs[0], outs[1], outs[2], outs[3], outs[4], r['dLm'],
+                                 flat.gview(layer.kern.W) if r['mix'] else None,
+                                 flat.gview(layer.mean_function.A) if lin else None,
+                                 flat.gview(layer.mean_function.b) if lin else None, self.bwd_ws)
+                capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), r['Lm'], r['aux'], self._cv(feat.Z),
+                                     r['ls'], self._cv(base.variance), self._cv(layer.q_mu), self._cv(layer.q_sqrt),
+                                     r['dLm'], self.dkl, outs[0], outs[1], outs[2], outs[3], outs[4], self.pbwd_ws)
+                if not r['ard']:
+                    torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                d_next = r['dX']
+            else:
+                Lw = r['Lw']
+                lv_off -= Lw
+                if len(self.lv_recs) > 1:
+                    d_kl = self.dkl_local[:, lv_off:lv_off + Lw].contiguous()
+                else:
+                    d_kl = self.dkl_local
+                enc_in = self.XY if r['bcast'] else r['enc_in']
+                capi.lv_bwd(r['d'], r['Fin'], enc_in, r['params'], r['eps'], r['mu'], r['sigma'], d_next, d_kl, None,
+                            None, r['d_params'], r.get('dF'), self.lv_ws)
+                if not r['packed_view']:
+                    o = 0
+                    for p in r['plist']:
+                        flat.gview(p).copy_(r['d_params'][o:o + p.size].view(flat.gview(p).shape))
+                        o += p.size
+                d_next = r.get('dF')
+        return flat.g
+
+    def elbo_and_grads(self, X, Y, eps=None, seed=0, step=0, row0=0):
+        self.set_batch(X, Y)
+        self.draw_noise(eps, seed, step, row0)
+        loss = self.forward()
+        self.backward()
+        return loss
+
+    def check_info(self):
+        """Raises if a Cholesky failed (LAPACK-style info from the device).  Synchronises."""
+        info = self.infos[:self.n_gp].cpu().numpy()
+        if (info != 0).any():
+            i = int(np.nonzero(info)[0][0])
+            raise RuntimeError('Cholesky of Kuu failed in GP layer %d: leading minor of order %d is not positive '
+                               'definite' % (i, int(info[i])))

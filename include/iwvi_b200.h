@@ -63,6 +63,13 @@ extern "C" {
 #define IWVI_FLAG_SAMPLE 1  /* eps given: produce sample = mean + eps*sqrt(var) (temp_workaround.py:89-91) */
 #define IWVI_FLAG_SAVE   2  /* keep A, U, latent mean/var for the backward pass */
 #define IWVI_FLAG_ACCUM  4  /* iwvi_gp_prologue_bwd adds into its outputs instead of overwriting them */
+/* measurement aid for iwvi_gp_rows_bwd: when any of these is set only the selected kernels of its four-launch
+ * sequence run (on buffers a complete call has already filled), so each can be timed alone with CUDA events */
+#define IWVI_FLAG_ONLY_EPI    16
+#define IWVI_FLAG_ONLY_TILE   32
+#define IWVI_FLAG_ONLY_REDUCE 64
+#define IWVI_FLAG_ONLY_FINAL  128
+#define IWVI_FLAG_ONLY_MASK   (16 | 32 | 64 | 128)
 
 typedef struct iwvi_gp_desc {
   int32_t T;      /* points in this call                                    */
