@@ -24,22 +24,27 @@ __host__ __device__ inline int iwvi_ldz(int D) { return D <= 20 ? 20 : 36; }
 // aux layout (doubles), written by the prologue, read by the row kernels
 // ---------------------------------------------------------------------------------------------
 struct AuxLayout {
-  int Mp, NB, ldz, R;
-  int64_t off_dinv, off_lqp, off_zt, off_zn, off_qmu, off_consts, off_scratch, total;
+  int Mp, NB, ldz, R, npairs;
+  int64_t off_lmb, off_lqb, off_zt, off_zn, off_qmu, off_consts, off_scratch, total;
 };
+// index of the lower block (i, j), i >= j, in the block-major arrays
+__host__ __device__ inline int iwvi_pair(int i, int j) { return i * (i + 1) / 2 + j; }
 __host__ __device__ inline AuxLayout iwvi_aux_layout(int M, int D, int R) {
   AuxLayout a;
   a.Mp = iwvi_round_up(M, IWVI_BLK);
   a.NB = a.Mp / IWVI_BLK;
   a.ldz = iwvi_ldz(D);
   a.R = R;
+  a.npairs = a.NB * (a.NB + 1) / 2;
   int64_t o = 0;
-  a.off_dinv = o;   o += (int64_t)a.NB * IWVI_BLK * IWVI_BLK;   // inverted diagonal blocks of Lm
-  a.off_lqp = o;    o += (int64_t)R * a.Mp * a.Mp;              // tril(q_sqrt), zero padded
+  // block-major, padded [64][68] copies (one bulk-TMA transaction each): strictly-lower blocks of Lm, with the
+  // INVERTED diagonal blocks of Lm in the diagonal slots; lower blocks of tril(q_sqrt_r)
+  a.off_lmb = o;    o += (int64_t)a.npairs * IWVI_STAGE_DOUBLES;
+  a.off_lqb = o;    o += (int64_t)R * a.npairs * IWVI_STAGE_DOUBLES;
   a.off_zt = o;     o += (int64_t)a.Mp * a.ldz;                 // Z / ls, zero padded
   a.off_zn = o;     o += a.Mp;                                  // |Z/ls|^2
   a.off_qmu = o;    o += (int64_t)a.Mp * IWVI_MAX_R;            // q_mu padded to [Mp, 8]
-  a.off_consts = o; o += 64;                                    // [0]=variance, [1..32]=1/ls[d] at [8+d], see below
+  a.off_consts = o; o += 64;                                    // [0]=variance, 1/ls[d] at [8+d]
   a.off_scratch = o; o += IWVI_PACK_GRID;                       // per-CTA partial sums of the KL (fixed-order final sum)
   a.total = o;
   return a;
@@ -47,20 +52,26 @@ __host__ __device__ inline AuxLayout iwvi_aux_layout(int M, int D, int R) {
 #define IWVI_C_VARIANCE 0
 #define IWVI_C_INVLS 8   // consts[8 + d] = 1 / ls[d], d < 32
 
-// save layout (doubles): A_T [Tp, ldA], U_T [R, Tp, ldA], gvar [T, R], gmean [T, R]; Tp = T rounded up to 128,
-// rows T..Tp-1 are written as zeros by the forward kernel so that whole 64-row blocks can be bulk-copied.
-struct SaveLayout { int64_t off_a, off_u, off_gvar, off_gmean, total; int ldA; int Tp; };
+// save layout (doubles): A and U_r are kept block-major, [chunk of 64 points][m-block][64 points][68] (so that every
+// 64x64 operand block of the backward contractions is ONE contiguous bulk-TMA transaction), then gvar [T, R] and
+// gmean [T, R].  Tp = T rounded up to 128; points T..Tp-1 are written as zeros by the forward kernel.
+struct SaveLayout { int64_t off_a, off_u, off_gvar, off_gmean, total, u_stride; int NB; int Tp; };
 __host__ __device__ inline SaveLayout iwvi_save_layout(int T, int M, int R) {
   SaveLayout s;
-  s.ldA = iwvi_round_up(M, IWVI_BLK) + 4;
+  s.NB = iwvi_round_up(M, IWVI_BLK) / IWVI_BLK;
   s.Tp = iwvi_round_up(T, 128);
+  s.u_stride = (int64_t)(s.Tp / IWVI_BLK) * s.NB * IWVI_STAGE_DOUBLES;
   int64_t o = 0;
-  s.off_a = o;     o += (int64_t)s.Tp * s.ldA;
-  s.off_u = o;     o += (int64_t)R * s.Tp * s.ldA;
+  s.off_a = o;     o += s.u_stride;
+  s.off_u = o;     o += (int64_t)R * s.u_stride;
   s.off_gvar = o;  o += (int64_t)T * R;
   s.off_gmean = o; o += (int64_t)T * R;
   s.total = o;
   return s;
+}
+// offset of element (point n, inducing index m) inside a block-major [Tp x Mp] array
+__host__ __device__ inline int64_t iwvi_blk_off(int n, int m, int NB) {
+  return ((int64_t)((n >> 6) * NB + (m >> 6)) * IWVI_BLK + (n & 63)) * IWVI_LDS + (m & 63);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -137,7 +148,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // A 2-deep (NST) ring of 64-row blocks filled by warp 0 with bulk TMA; arrival through mbarriers,
 // release through the block-wide barrier that the algorithms need anyway between dependent steps.
 #define IWVI_NST 2
-struct BlockSrc { const double* src; int row_bytes; int src_stride; int dst_stride; };
+struct BlockSrc { const double* src; uint32_t bytes; };   // one contiguous block, copied verbatim into a stage
 
 template <int NST>
 struct StagePipeT {
@@ -154,16 +165,13 @@ struct StagePipeT {
     }
     __syncthreads();
   }
-  // warp 0 only (all 32 lanes): issue one block into the next stage
+  // warp 0 only: issue one block into the next stage
   __device__ __forceinline__ void produce(const BlockSrc& b, int lane) {
     const uint32_t s = it_p % NST;
-    uint64_t* bar = &bars[s];
-    double* dst = stages + (size_t)s * IWVI_STAGE_DOUBLES;
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(IWVI_BLK * b.row_bytes));
-    __syncwarp();
-#pragma unroll
-    for (int r = lane; r < IWVI_BLK; r += 32)
-      bulk_g2s(dst + (size_t)r * b.dst_stride, b.src + (size_t)r * b.src_stride, (uint32_t)b.row_bytes, bar);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[s], b.bytes);
+      bulk_g2s(stages + (size_t)s * IWVI_STAGE_DOUBLES, b.src, b.bytes, &bars[s]);
+    }
     it_p++;
   }
   // all threads: wait for the oldest outstanding block, return its stage
@@ -214,6 +222,60 @@ struct StagePipeT {
   }
 };
 typedef StagePipeT<IWVI_NST> StagePipe;
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised ring: a dedicated producer warp streams 64-row blocks through an NST-deep ring with bulk TMA;
+// consumer warps wait on full[s] (transaction count) and hand a stage back by arriving on empty[s] (one arrival per
+// consumer warp).  No block-wide barrier is involved, so consumers only synchronise where data really flows
+// between warps (named barriers, below), and the producer's issue cost is off the consumers' critical path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NST>
+struct RingT {
+  uint64_t* full;    // [NST]
+  uint64_t* empty;   // [NST]
+  double* stages;    // [NST][IWVI_STAGE_DOUBLES]
+  uint32_t it;       // blocks consumed (consumer copy) or produced (producer copy) so far
+
+  // all threads of the CTA, once, before the roles split
+  __device__ __forceinline__ void setup(uint64_t* bars, double* s, int n_consumer_warps) {
+    full = bars; empty = bars + NST; stages = s; it = 0;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < NST; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], n_consumer_warps); }
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  // producer warp: wait until the stage is free, then issue the block (one bulk-TMA transaction)
+  __device__ __forceinline__ void produce(const BlockSrc& b, int lane) {
+    const uint32_t s = it % NST;
+    if (lane == 0) {
+      mbar_wait(&empty[s], ((it / NST) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(&full[s], b.bytes);
+      bulk_g2s(stages + (size_t)s * IWVI_STAGE_DOUBLES, b.src, b.bytes, &full[s]);
+    }
+    it++;
+  }
+  // consumer warps: oldest outstanding block (offset k blocks ahead, k < NST)
+  __device__ __forceinline__ const double* wait(uint32_t k = 0) {
+    const uint32_t i2 = it + k, s = i2 % NST;
+    mbar_wait(&full[s], (i2 / NST) & 1u);
+    return stages + (size_t)s * IWVI_STAGE_DOUBLES;
+  }
+  // consumer warps: this warp is done with the n oldest blocks
+  __device__ __forceinline__ void release(int lane, int n = 1) {
+    __syncwarp();
+    if (lane == 0)
+      for (int k = 0; k < n; k++) mbar_arrive(&empty[(it + k) % NST]);
+    it += n;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // stationary kernels (GPflow 1.x formulas): K(r2) and dK/dr2

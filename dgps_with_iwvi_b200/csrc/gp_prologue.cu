@@ -36,19 +36,25 @@ __global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
   double klp = 0.0;
-  // tril(q_sqrt), zero padded; trace and log-det terms of the KL
-  const int64_t nlq = (int64_t)R * Mp * Mp;
+  // tril(q_sqrt) as block-major padded [64][68] lower blocks; trace and log-det terms of the KL
+  const int64_t nlq = (int64_t)R * al.npairs * IWVI_STAGE_DOUBLES;
   for (int64_t e = gtid; e < nlq; e += gsz) {
-    const int r = (int)(e / ((int64_t)Mp * Mp));
-    const int64_t rem = e - (int64_t)r * Mp * Mp;
-    const int a = (int)(rem / Mp), b = (int)(rem - (int64_t)a * Mp);
+    const int r = (int)(e / ((int64_t)al.npairs * IWVI_STAGE_DOUBLES));
+    int64_t rem = e - (int64_t)r * al.npairs * IWVI_STAGE_DOUBLES;
+    const int pr = (int)(rem / IWVI_STAGE_DOUBLES);
+    rem -= (int64_t)pr * IWVI_STAGE_DOUBLES;
+    const int row = (int)(rem / IWVI_LDS), col = (int)(rem - (int64_t)row * IWVI_LDS);
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= pr) bi++;
+    const int bj = pr - bi * (bi + 1) / 2;
+    const int a = bi * IWVI_BLK + row, b = bj * IWVI_BLK + col;
     double v = 0.0;
-    if (a < M && b <= a) {
+    if (col < IWVI_BLK && a < M && b <= a) {
       v = p.q_sqrt[((size_t)r * M + a) * M + b];
       klp += v * v;
       if (a == b) klp -= log(v * v);
     }
-    aux[al.off_lqp + e] = v;
+    aux[al.off_lqb + e] = v;
   }
   // Zt = Z / ls
   for (int64_t e = gtid; e < (int64_t)Mp * ldz; e += gsz) {
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   const double variance = p.variance[0];
   const double jitter = d.jitter;
   double* Lm = p.Lm;
-  double* Dinv_g = p.aux + al.off_dinv;
+  double* Lmb = p.aux + al.off_lmb;   // block-major padded copies: L(i,k) for i > k, inverted diagonal blocks at (k,k)
   if (tid == 0) s_info = 0;
 
   for (int k = 0; k < NB; k++) {
@@ -209,9 +215,9 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
           }
         }
         __syncthreads();
-        for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
-          const int r = idx >> 6, c = idx & 63;
-          Dinv_g[(size_t)k * IWVI_BLK * IWVI_BLK + idx] = Dv[r * IWVI_LDS + c];
+        for (int idx = tid; idx < IWVI_STAGE_DOUBLES; idx += 256) {
+          const int c = idx % IWVI_LDS;
+          Lmb[(size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES + idx] = (c < IWVI_BLK) ? Dv[idx] : 0.0;
         }
         // zero the blocks to the right of the diagonal
         for (int jb = k + 1; jb < NB; jb++)
@@ -238,8 +244,11 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
 #pragma unroll
           for (int b = 0; b < 2; b++)
 #pragma unroll
-            for (int c = 0; c < 2; c++)
-              Lm[(size_t)(i * IWVI_BLK + wm0 + a * 8 + g) * Mp + k * IWVI_BLK + wn0 + b * 8 + 2 * t + c] = out[a][b][c];
+            for (int c = 0; c < 2; c++) {
+              const int rr = wm0 + a * 8 + g, cc = wn0 + b * 8 + 2 * t + c;
+              Lm[(size_t)(i * IWVI_BLK + rr) * Mp + k * IWVI_BLK + cc] = out[a][b][c];
+              Lmb[(size_t)iwvi_pair(i, k) * IWVI_STAGE_DOUBLES + rr * IWVI_LDS + cc] = out[a][b][c];
+            }
       }
     }
   }
@@ -312,17 +321,16 @@ __global__ void __launch_bounds__(256, 1) pbwd_phi_kernel(const PbwdParams p) {
 }
 
 struct SolveSeq {   // blocks of the back substitution: for i = NB-1..0: Lm(j,i) j = i+1..NB-1, then Dinv_i
-  int NB, Mp;
-  const double *Lm, *Dinv;
+  int NB;
+  const double* Lmb;
   int i, j;
   bool fin;
   __device__ __forceinline__ void init() { i = NB - 1; j = NB; fin = false; }
   __device__ __forceinline__ bool done() const { return fin; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
-    b.row_bytes = IWVI_BLK * 8; b.dst_stride = IWVI_LDS;
-    if (j < NB) { b.src = Lm + (size_t)(j * IWVI_BLK) * Mp + i * IWVI_BLK; b.src_stride = Mp; }
-    else        { b.src = Dinv + (size_t)i * IWVI_BLK * IWVI_BLK; b.src_stride = IWVI_BLK; }
+    b.bytes = IWVI_STAGE_DOUBLES * 8;
+    b.src = Lmb + (size_t)(j < NB ? iwvi_pair(j, i) : iwvi_pair(i, i)) * IWVI_STAGE_DOUBLES;
     return b;
   }
   __device__ __forceinline__ void advance() {
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(256, 1) pbwd_solve_kernel(const PbwdParams p, 
   StagePipe pipe;
   pipe.setup(bars, stages);
   SolveSeq seq;
-  seq.NB = NB; seq.Mp = Mp; seq.Lm = p.Lm; seq.Dinv = p.aux + al.off_dinv;
+  seq.NB = NB; seq.Lmb = p.aux + al.off_lmb;
   seq.init();
   pipe.prime(seq, warp, lane);
 

@@ -29,16 +29,19 @@ template <int TP> struct TileCfg {
 #define EPI_STRIDE 1344   // >= P*R + D*P + P + 1 at the maxima (32*8 + 32*32 + 32 + 1 = 1313)
 #define EPI_PTS 256
 #define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
+#define TILE_THREADS 288    // 8 consumer warps + 1 producer warp
+#define BAR_ALL 1
+#define BAR_COL 2
 
 struct BwdWs {   // workspace layout (doubles)
   int64_t off_bbar, off_gmb, off_gvb, off_epi, off_tile, off_red, off_qred, total;
-  int Tp, ldA, n_epi, grid_tile, S, npairs, chunks_per_split, tile_stride;
+  int Tp, n_epi, grid_tile, S, npairs, chunks_per_split, tile_stride;
 };
 __host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   BwdWs w;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
-  w.Tp = sv.Tp; w.ldA = sv.ldA;
+  w.Tp = sv.Tp;
   w.n_epi = (w.Tp + EPI_PTS - 1) / EPI_PTS;
   w.grid_tile = nsm;
   w.npairs = al.NB * (al.NB + 1) / 2;
@@ -51,7 +54,7 @@ __host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
   int64_t o = 0;
-  w.off_bbar = o; o += (int64_t)w.Tp * w.ldA;
+  w.off_bbar = o; o += sv.u_stride;            // Bbar, block-major like the saved A
   w.off_gmb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_gvb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_epi = o;  o += (int64_t)w.n_epi * EPI_STRIDE;
@@ -177,21 +180,20 @@ __global__ void __launch_bounds__(EPI_PTS) gp_epi_bwd_kernel(const BwdParams p) 
 // 2. tile kernel
 // ------------------------------------------------------------------------------------------------
 struct BwdSeq {
-  int NB, R, Mp, ldz;
-  const double *Zt, *Lm, *Dinv, *Lqp;
+  int NB, R, npairs, ldz;
+  const double *Zt, *Lmb, *Lqb;
   int ph, r, i, j;
   __device__ __forceinline__ void init() { ph = 0; r = 0; i = 0; j = 0; }
   __device__ __forceinline__ bool done() const { return ph == 3; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
-    b.row_bytes = IWVI_BLK * 8; b.dst_stride = IWVI_LDS;
+    b.bytes = IWVI_STAGE_DOUBLES * 8;
     if (ph == 0) {           // tril(q_sqrt_r) block (row block i, col block j), i >= j
-      b.src = Lqp + (size_t)r * Mp * Mp + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK; b.src_stride = Mp;
+      b.src = Lqb + ((size_t)r * npairs + iwvi_pair(i, j)) * IWVI_STAGE_DOUBLES;
     } else if (ph == 1) {    // Lm block (row block j, col block i), j > i; j == NB: inverted diagonal block i
-      if (j < NB) { b.src = Lm + (size_t)(j * IWVI_BLK) * Mp + i * IWVI_BLK; b.src_stride = Mp; }
-      else        { b.src = Dinv + (size_t)i * IWVI_BLK * IWVI_BLK; b.src_stride = IWVI_BLK; }
+      b.src = Lmb + (size_t)(j < NB ? iwvi_pair(j, i) : iwvi_pair(i, i)) * IWVI_STAGE_DOUBLES;
     } else {                 // scaled inducing inputs, block i
-      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.row_bytes = ldz * 8; b.src_stride = ldz; b.dst_stride = ldz;
+      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.bytes = (uint32_t)(IWVI_BLK * ldz * 8);
     }
     return b;
   }
@@ -221,13 +223,13 @@ __host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
   s.gr = o;     o += 2 * 4 * IWVI_BLK;     // [2][WNG][64] row sums of G per warp column group, double buffered
   s.dls = o;    o += 8 * 32;               // [warp][32]
   s.red = o;    o += 32;
-  s.bars = o;   o += IWVI_NST;
+  s.bars = o;   o += 2 * IWVI_NST;
   s.total_doubles = o;
   return s;
 }
 
 template <int TP>
-__global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdParams p) {
   using C = TileCfg<TP>;
   static_assert(C::TN == 2, "register-resident V fragments assume two n-tiles per warp");
   extern __shared__ __align__(16) double smem[];
@@ -249,11 +251,27 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
   double* red = smem + sl.red;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* aux = p.aux;
+
+  RingT<IWVI_NST> pipe;
+  pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages, C::NW);
+  if (warp == C::NW) {
+    // producer warp: the block sequence is the same for every tile
+    BwdSeq seq;
+    seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
+    seq.Zt = aux + al.off_zt; seq.Lmb = aux + al.off_lmb; seq.Lqb = aux + al.off_lqb;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      seq.init();
+      while (!seq.done()) { pipe.produce(seq.get(), lane); seq.advance(); }
+    }
+    return;
+  }
+
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp % C::WMG) * C::WM;
   const int wn0 = (warp / C::WMG) * C::WN;
+  const int colbar = BAR_COL + warp / C::WMG;
 
-  const double* aux = p.aux;
   const double* zn = aux + al.off_zn;
   const double* qmu = aux + al.off_qmu;
   const double* consts = aux + al.off_consts;
@@ -267,36 +285,28 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
   double* mypart = p.ws + p.wl.off_tile + (size_t)blockIdx.x * p.wl.tile_stride;
 
   // this CTA's partial of dZ (accumulated across its tiles in global memory, exclusive owner) and dls
-  for (int idx = tid; idx < p.wl.tile_stride; idx += blockDim.x) mypart[idx] = 0.0;
+  for (int idx = tid; idx < p.wl.tile_stride; idx += 256) mypart[idx] = 0.0;
   dls_s[tid] = 0.0;
   double dvar_acc = 0.0;
 
-  StagePipe pipe;
-  pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages);
-  BwdSeq seq;
-  seq.NB = NB; seq.R = R; seq.Mp = Mp; seq.ldz = ldz;
-  seq.Zt = aux + al.off_zt; seq.Lm = p.Lm; seq.Dinv = aux + al.off_dinv; seq.Lqp = aux + al.off_lqp;
-
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
-    __syncthreads();
-    seq.init();
-    pipe.prime(seq, warp, lane);
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- per-point cotangents of this tile, x tile
-    for (int idx = tid; idx < IWVI_MAX_R * TP; idx += blockDim.x) {
+    for (int idx = tid; idx < IWVI_MAX_R * TP; idx += 256) {
       const int r = idx / TP, n = idx - r * TP;
       gmb_s[idx] = gmb[(size_t)(n0 + n) * IWVI_MAX_R + r];
       gvb_s[idx] = gvb[(size_t)(n0 + n) * IWVI_MAX_R + r];
     }
-    for (int idx = tid; idx < TP * ldz; idx += blockDim.x) {
+    for (int idx = tid; idx < TP * ldz; idx += 256) {
       const int n = idx / ldz, k = idx - n * ldz;
       double v = 0.0;
       if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
       xs[idx] = v;
     }
-    for (int idx = tid; idx < 4 * TP; idx += blockDim.x) gs_s[idx] = 0.0;
-    __syncthreads();
+    for (int idx = tid; idx < 4 * TP; idx += 256) gs_s[idx] = 0.0;
+    named_bar_sync(BAR_ALL, 256);
     if (tid < TP) {
       double s = 0.0;
       for (int k = 0; k < Dk; k++) { const double v = xs[tid * ldz + k]; s += v * v; }
@@ -305,17 +315,17 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
       for (int r = 0; r < R; r++) gsum += gvb_s[r * TP + tid];
       gsum_s[tid] = gsum;
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- Abar, part 1: q_mu gmean_bar^T - 2 A gsum   (A read from the saved point-major array, coalesced)
-    for (int idx = tid; idx < TP * Mp; idx += blockDim.x) {
+    for (int idx = tid; idx < TP * Mp; idx += 256) {
       const int n = idx / Mp, m = idx - n * Mp;
-      double v = -2.0 * A_T[(size_t)(n0 + n) * ldA + m] * gsum_s[n];
+      double v = -2.0 * A_T[iwvi_blk_off(n0 + n, m, NB)] * gsum_s[n];
       const double* q = qmu + (size_t)m * IWVI_MAX_R;
       for (int r = 0; r < R; r++) v += q[r] * gmb_s[r * TP + n];
       panel[n * ldA + m] = v;
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- Abar, part 2: += 2 tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register B-fragments per k-block j
     for (int r = 0; r < R; r++) {
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
         for (int b = 0; b < 2; b++) {
           const int n = wn0 + b * 8 + g;
           const double sc = gvb_s[r * TP + n];
-          const double* up = U_T + ((size_t)r * sv.Tp + n0 + n) * ldA + j * IWVI_BLK + t;
+          const double* up = U_T + r * sv.u_stride + iwvi_blk_off(n0 + n, j * IWVI_BLK, NB) + t;
 #pragma unroll
           for (int ks = 0; ks < 16; ks++) vb[ks][b] = up[ks * 4] * sc;
         }
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
               dmma884(acc[a_][1], a[a_], vb[ks][1]);
             }
           }
-          pipe.release(seq, warp, lane);
+          pipe.release(lane);
 #pragma unroll
           for (int a_ = 0; a_ < C::TM; a_++)
 #pragma unroll
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
         }
       }
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- Bbar = Lm^-T Abar, blocked back substitution in place
     for (int i = NB - 1; i >= 0; i--) {
@@ -368,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
       for (int j = i + 1; j < NB; j++) {
         const double* st = pipe.wait();
         warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
-        pipe.release(seq, warp, lane);
+        pipe.release(lane);
       }
       if (i < NB - 1) {
 #pragma unroll
@@ -381,12 +391,13 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
               const int n = wn0 + b * 8 + 2 * t + c;
               panel[n * ldA + m] -= acc[a][b][c];
             }
-        __syncthreads();
+        named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = pipe.wait();   // inverted diagonal block i, used transposed
       acc_zero<C::TM, C::TN>(acc);
       warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, IWVI_BLK, lane);
-      pipe.release(seq, warp, lane);
+      pipe.release(lane);
+      named_bar_sync(colbar, C::WMG * 32);   // every warp of the column group has read the right-hand side
 #pragma unroll
       for (int a = 0; a < C::TM; a++)
 #pragma unroll
@@ -397,18 +408,16 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
             const int n = wn0 + b * 8 + 2 * t + c;
             panel[n * ldA + m] = acc[a][b][c];
           }
-      __syncthreads();
+      named_bar_sync(colbar, C::WMG * 32);
     }
 
     // ---- store Bbar (needed by the reduce kernel for dLm); rows of invalid points are zero by construction
-    {
-      double* dst = bbar_T + (size_t)n0 * ldA;
-      for (int idx = tid; idx < TP * ldA; idx += blockDim.x) {
-        const int m = idx % ldA;
-        dst[idx] = (m < Mp) ? panel[idx] : 0.0;
-      }
+    named_bar_sync(BAR_ALL, 256);
+    for (int idx = tid; idx < TP * Mp; idx += 256) {
+      const int n = idx / Mp, m = idx - n * Mp;
+      bbar_T[iwvi_blk_off(n0 + n, m, NB)] = panel[n * ldA + m];
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- gram adjoint, block row by block row
     double accx[4][2];
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
         s = warp_sum(s);
         if (lane == 0) dls_s[warp * 32 + dd] += s;
       }
-      __syncthreads();   // G_i visible in the panel, gr_s complete
+      named_bar_sync(BAR_ALL, 256);   // G_i visible in the panel, gr_s complete
 
       // dX partial: accx[n][d] += sum_{m in block} G[m][n] z~[m][d]   (warp w owns points 8w..8w+7)
       if (warp < TP / 8) {
@@ -527,7 +536,7 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
             }
           }
       }
-      pipe.release(seq, warp, lane);
+      pipe.release(lane);
     }
 
     // ---- dX += 2/ls (x~ colsum(G) - G^T z~)
@@ -550,9 +559,17 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
     }
   }
 
-  __syncthreads();
-  const double tot = block_sum(dvar_acc, red);
-  if (tid == 0) mypart[(size_t)Mp * ldz + 32] = tot / variance;
+  named_bar_sync(BAR_ALL, 256);
+  {
+    const double v = warp_sum(dvar_acc);
+    if (lane == 0) red[warp] = v;
+    named_bar_sync(BAR_ALL, 256);
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < C::NW; w++) tot += red[w];
+      mypart[(size_t)Mp * ldz + 32] = tot / variance;
+    }
+  }
   if (tid < 32) {
     double s = 0.0;
     for (int w = 0; w < C::NW; w++) s += dls_s[w * 32 + tid];
@@ -564,34 +581,30 @@ __global__ void __launch_bounds__(256, 1) gp_tile_bwd_kernel(const BwdParams p) 
 // 3. contractions over the points (split-K)
 // ------------------------------------------------------------------------------------------------
 struct RedSeq {
-  const double *Aop, *Bop;   // both point-major [Tp, ldA], already offset to their 64-column block
-  int ldA, c, c1, which;
+  const double *Aop, *Bop;   // block-major [chunk][m-block][64][68], already offset to their m-block
+  int NB, c, c1, which;
   __device__ __forceinline__ bool done() const { return c >= c1; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
-    b.src = (which == 0 ? Aop : Bop) + (size_t)c * IWVI_BLK * ldA;
-    b.row_bytes = IWVI_BLK * 8; b.src_stride = ldA; b.dst_stride = IWVI_LDS;
+    b.src = (which == 0 ? Aop : Bop) + (size_t)c * NB * IWVI_STAGE_DOUBLES;
+    b.bytes = IWVI_STAGE_DOUBLES * 8;
     return b;
   }
   __device__ __forceinline__ void advance() { if (which == 0) which = 1; else { which = 0; ++c; } }
 };
 
 #define RED_NST 4
-__global__ void __launch_bounds__(256, 1) gp_reduce_bwd_kernel(const BwdParams p) {
+#define RED_THREADS 288   // 8 consumer warps + 1 producer warp
+__global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const int NB = al.NB, R = d.R;
   const BwdWs& wl = p.wl;
-  const int ldA = wl.ldA;
   double* stages = smem;
-  double* scale_s = smem + RED_NST * IWVI_STAGE_DOUBLES;        // [2][64]
-  double* gm_s = scale_s + 2 * IWVI_BLK;                        // [2][64*8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gm_s + 2 * IWVI_BLK * IWVI_MAX_R);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RED_NST * IWVI_STAGE_DOUBLES);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;     // warp tile 32 x 16 of the 64 x 64 output block
 
   // decode the work item
   int item = blockIdx.x;
@@ -613,13 +626,18 @@ __global__ void __launch_bounds__(256, 1) gp_reduce_bwd_kernel(const BwdParams p
   const bool is_lm = (q == R);
   const bool do_qmu = (q == 0 && bj == 0);
 
-  StagePipeT<RED_NST> pipe;
-  pipe.setup(bars, stages);
-  RedSeq seq;
-  seq.Aop = (is_lm ? bbar_T : A_T) + bi * IWVI_BLK;
-  seq.Bop = (is_lm ? A_T : U_T + (size_t)q * sv.Tp * ldA) + bj * IWVI_BLK;
-  seq.ldA = ldA; seq.c = c0; seq.c1 = c1; seq.which = 0;
-  pipe.prime(seq, warp, lane);
+  RingT<RED_NST> pipe;
+  pipe.setup(bars, stages, 8);
+  if (warp == 8) {
+    RedSeq seq;
+    seq.Aop = (is_lm ? bbar_T : A_T) + (size_t)bi * IWVI_STAGE_DOUBLES;
+    seq.Bop = (is_lm ? A_T : U_T + (size_t)q * sv.u_stride) + (size_t)bj * IWVI_STAGE_DOUBLES;
+    seq.NB = NB; seq.c = c0; seq.c1 = c1; seq.which = 0;
+    while (!seq.done()) { pipe.produce(seq.get(), lane); seq.advance(); }
+    return;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;     // warp tile 32 x 16 of the 64 x 64 output block
 
   double acc[4][2][2];
   acc_zero<4, 2>(acc);
@@ -627,32 +645,16 @@ __global__ void __launch_bounds__(256, 1) gp_reduce_bwd_kernel(const BwdParams p
 #pragma unroll
   for (int a = 0; a < 4; a++) { accq[a][0] = 0.0; accq[a][1] = 0.0; }
 
-  auto load_scales = [&](int c, int buf) {
-    if (tid < IWVI_BLK) {
-      const size_t pt = (size_t)c * IWVI_BLK + tid;
-      scale_s[buf * IWVI_BLK + tid] = is_lm ? -1.0 : 2.0 * gvb[pt * IWVI_MAX_R + q];
-    }
-    if (do_qmu) {
-      for (int idx = tid; idx < IWVI_BLK * IWVI_MAX_R; idx += blockDim.x)
-        gm_s[buf * IWVI_BLK * IWVI_MAX_R + idx] = gmb[(size_t)c * IWVI_BLK * IWVI_MAX_R + idx];
-    }
-  };
-  if (c0 < c1) load_scales(c0, 0);
-  __syncthreads();
-
   for (int c = c0; c < c1; c++) {
-    const int buf = (c - c0) & 1;
-    if (c + 1 < c1) load_scales(c + 1, buf ^ 1);   // consumed after the barrier inside release_n
-    const double* sa = pipe.wait_ahead(0);   // [k = point][m]  -> A operand, k-major
-    const double* sb = pipe.wait_ahead(1);   // [k = point][n]  -> B operand, k-major
+    const double* sa = pipe.wait(0);   // [k = point][m]  -> A operand, k-major
+    const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major
     const double* ap = sa + t * IWVI_LDS + wm0 + g;
     const double* bp = sb + t * IWVI_LDS + wn0 + g;
-    const double* sc = scale_s + buf * IWVI_BLK;
-    const double* gq = gm_s + buf * IWVI_BLK * IWVI_MAX_R;
+    const size_t pt0 = (size_t)c * IWVI_BLK + t;
 #pragma unroll 2
     for (int k0 = 0; k0 < IWVI_BLK; k0 += 4) {
       double a[4], b[2];
-      const double scl = sc[k0 + t];
+      const double scl = is_lm ? -1.0 : 2.0 * __ldg(gvb + (pt0 + k0) * IWVI_MAX_R + q);
 #pragma unroll
       for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
 #pragma unroll
@@ -662,12 +664,12 @@ __global__ void __launch_bounds__(256, 1) gp_reduce_bwd_kernel(const BwdParams p
 #pragma unroll
         for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[j]);
       if (do_qmu && wn0 == 0) {
-        const double bq = gq[(k0 + t) * IWVI_MAX_R + g];
+        const double bq = __ldg(gmb + (pt0 + k0) * IWVI_MAX_R + g);
 #pragma unroll
         for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
       }
     }
-    pipe.release_n(seq, 2, warp, lane);
+    pipe.release(lane, 2);
   }
 
   double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;
@@ -826,20 +828,20 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   } else if (TP == 64) {
     if (cudaFuncSetAttribute(gp_tile_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
       return IWVI_ERR_LAUNCH;
-    gp_tile_bwd_kernel<64><<<p.grid_tile, 256, smem_bytes, st>>>(p);
+    gp_tile_bwd_kernel<64><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);
   } else {
     if (cudaFuncSetAttribute(gp_tile_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
       return IWVI_ERR_LAUNCH;
-    gp_tile_bwd_kernel<32><<<p.grid_tile, 256, smem_bytes, st>>>(p);
+    gp_tile_bwd_kernel<32><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);
   }
   IWVI_CHECK_LAUNCH();
 
   if (!only || (only & IWVI_FLAG_ONLY_REDUCE)) {
-    const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK + 2 * IWVI_BLK * IWVI_MAX_R + RED_NST) * 8;
+    const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * RED_NST) * 8;
     if (cudaFuncSetAttribute(gp_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem) != cudaSuccess)
       return IWVI_ERR_LAUNCH;
     const int red_grid = (d->R + 1) * p.wl.S * p.wl.npairs;
-    gp_reduce_bwd_kernel<<<red_grid, 256, red_smem, st>>>(p);
+    gp_reduce_bwd_kernel<<<red_grid, RED_THREADS, red_smem, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
   if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {

@@ -18,23 +18,20 @@
 
 namespace {
 
-struct FwdSeq {  // order in which 64-row blocks are consumed by one tile
-  int NB, R, Mp, ldz;
-  const double *Zt, *Lm, *Dinv, *Lqp;
+struct FwdSeq {  // order in which blocks are consumed by one tile
+  int NB, R, npairs, ldz;
+  const double *Zt, *Lmb, *Lqb;
   int ph, r, i, j;
   __device__ __forceinline__ void init() { ph = 0; r = 0; i = 0; j = 0; }
   __device__ __forceinline__ bool done() const { return ph == 3; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
-    if (ph == 0) {
-      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.row_bytes = ldz * 8; b.src_stride = ldz; b.dst_stride = ldz;
-    } else if (ph == 1) {
-      if (j < i) { b.src = Lm + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK; b.src_stride = Mp; }
-      else       { b.src = Dinv + (size_t)i * IWVI_BLK * IWVI_BLK; b.src_stride = IWVI_BLK; }
-      b.row_bytes = IWVI_BLK * 8; b.dst_stride = IWVI_LDS;
-    } else {
-      b.src = Lqp + (size_t)r * Mp * Mp + (size_t)(j * IWVI_BLK) * Mp + i * IWVI_BLK;
-      b.row_bytes = IWVI_BLK * 8; b.src_stride = Mp; b.dst_stride = IWVI_LDS;
+    if (ph == 0) {          // scaled inducing inputs of block i
+      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.bytes = (uint32_t)(IWVI_BLK * ldz * 8);
+    } else if (ph == 1) {   // Lm(i,j), j < i; then the inverted diagonal block (slot (i,i))
+      b.src = Lmb + (size_t)iwvi_pair(i, j) * IWVI_STAGE_DOUBLES; b.bytes = IWVI_STAGE_DOUBLES * 8;
+    } else {                // tril(q_sqrt_r) block (j, i), j >= i
+      b.src = Lqb + ((size_t)r * npairs + iwvi_pair(j, i)) * IWVI_STAGE_DOUBLES; b.bytes = IWVI_STAGE_DOUBLES * 8;
     }
     return b;
   }
@@ -80,13 +77,17 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int TP, int Mp, int ldx) {
   s.fv0 = o;    o += TP;
   s.usq = o;    o += IWVI_MAX_R * TP * (TP >= 64 ? 2 : 4);   // one slot per warp row group: fixed-order sums
   s.gm = o;     o += IWVI_MAX_R * TP;
-  s.bars = o;   o += IWVI_NST;
+  s.bars = o;   o += 2 * IWVI_NST;
   s.total_doubles = o;
   return s;
 }
 
+#define FWD_THREADS 288   // 8 consumer warps + 1 producer warp
+#define BAR_ALL 1         // named barrier of the 256 consumer threads
+#define BAR_COL 2         // + column-group index: the WMG warps that share a set of points
+
 template <int TP>
-__global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdParams p) {
   using C = TileCfg<TP>;
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
@@ -102,11 +103,27 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
   double* gms = smem + sl.gm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* aux = p.aux;
+
+  RingT<IWVI_NST> ring;
+  ring.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages, C::NW);
+
+  if (warp == C::NW) {
+    // ---- producer warp: streams the tile-independent block sequence once per tile, running ahead of the consumers
+    FwdSeq seq;
+    seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
+    seq.Zt = aux + al.off_zt; seq.Lmb = aux + al.off_lmb; seq.Lqb = aux + al.off_lqb;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      seq.init();
+      while (!seq.done()) { ring.produce(seq.get(), lane); seq.advance(); }
+    }
+    return;
+  }
+
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp % C::WMG) * C::WM;   // first block-row of this warp
   const int wn0 = (warp / C::WMG) * C::WN;   // first point of this warp
-
-  const double* aux = p.aux;
+  const int colbar = BAR_COL + warp / C::WMG;
   const double* zn = aux + al.off_zn;
   const double* qmu = aux + al.off_qmu;
   const double* consts = aux + al.off_consts;
@@ -115,39 +132,32 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
   const bool do_save = (d.flags & IWVI_FLAG_SAVE) != 0;
   const bool do_sample = (d.flags & IWVI_FLAG_SAMPLE) != 0;
 
-  StagePipe pipe;
-  pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages);
-  FwdSeq seq;
-  seq.NB = NB; seq.R = R; seq.Mp = Mp; seq.ldz = ldz;
-  seq.Zt = aux + al.off_zt; seq.Lm = p.Lm; seq.Dinv = aux + al.off_dinv; seq.Lqp = aux + al.off_lqp;
-
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
-    __syncthreads();  // previous tile fully done with every shared buffer
-    seq.init();
-    pipe.prime(seq, warp, lane);
+    named_bar_sync(BAR_ALL, 256);  // previous tile fully done with every shared buffer
 
     // ---- x tile: xs[n][k] = X[n0+n][k] / ls[k] (zero padded), xn[n] = |xs[n]|^2
-    for (int idx = tid; idx < TP * ldz; idx += blockDim.x) {
+    for (int idx = tid; idx < TP * ldz; idx += 256) {
       const int n = idx / ldz, k = idx - n * ldz;
       double v = 0.0;
       if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
       xs[idx] = v;
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
     if (tid < TP) {
       double s = 0.0;
       for (int k = 0; k < Dk; k++) { const double v = xs[tid * ldz + k]; s += v * v; }
       xn[tid] = s;
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- G: gram blocks -> panel (Kuf)
     for (int i = 0; i < NB; i++) {
-      const double* st = pipe.wait();
+      const double* st = ring.wait();
       double acc[C::TM][C::TN][2];
       acc_zero<C::TM, C::TN>(acc);
       warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
+      ring.release(lane);
 #pragma unroll
       for (int a = 0; a < C::TM; a++)
 #pragma unroll
@@ -159,20 +169,20 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
             const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
             panel[n * ldA + mg] = (mg < d.M) ? kern_k(d.kern, r2, variance) : 0.0;
           }
-      pipe.release(seq, warp, lane);
     }
+    named_bar_sync(colbar, C::WMG * 32);
 
-    // ---- T: blocked forward substitution, in place
+    // ---- T: blocked forward substitution, in place.  Data only flows between the WMG warps of a column group.
     for (int i = 0; i < NB; i++) {
       double acc[C::TM][C::TN][2];
-      acc_zero<C::TM, C::TN>(acc);
-      for (int j = 0; j < i; j++) {
-        const double* st = pipe.wait();
-        warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA,
-                                      IWVI_BLK, lane);
-        pipe.release(seq, warp, lane);
-      }
       if (i > 0) {
+        acc_zero<C::TM, C::TN>(acc);
+        for (int j = 0; j < i; j++) {
+          const double* st = ring.wait();
+          warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA,
+                                        IWVI_BLK, lane);
+          ring.release(lane);
+        }
 #pragma unroll
         for (int a = 0; a < C::TM; a++)
 #pragma unroll
@@ -183,13 +193,14 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
               const int n = wn0 + b * 8 + 2 * t + c;
               panel[n * ldA + m] -= acc[a][b][c];
             }
-        __syncthreads();
+        named_bar_sync(colbar, C::WMG * 32);
       }
-      const double* st = pipe.wait();   // inverted diagonal block
+      const double* st = ring.wait();   // inverted diagonal block
       acc_zero<C::TM, C::TN>(acc);
       warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA,
                                     IWVI_BLK, lane);
-      pipe.release(seq, warp, lane);     // (barrier) every warp has read the right-hand side
+      ring.release(lane);
+      named_bar_sync(colbar, C::WMG * 32);   // every warp of the group has read the right-hand side
 #pragma unroll
       for (int a = 0; a < C::TM; a++)
 #pragma unroll
@@ -200,8 +211,9 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
             const int n = wn0 + b * 8 + 2 * t + c;
             panel[n * ldA + m] = acc[a][b][c];
           }
-      __syncthreads();
+      named_bar_sync(colbar, C::WMG * 32);
     }
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- S: fvar0 and latent means; optional save of A (contiguous tile of the point-major array)
     for (int n = warp; n < TP; n += C::NW) {
@@ -225,15 +237,15 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
     }
     if (do_save) {
       const int nvalid = min(TP, T - n0);       // real points of this tile
-      const int nrows = min(TP, sv.Tp - n0);    // rows of the padded array this tile owns (pad rows := 0)
-      double* dst = p.save + sv.off_a + (size_t)n0 * ldA;
-      for (int idx = tid; idx < nrows * ldA; idx += blockDim.x) {
-        const int n = idx / ldA, m = idx - n * ldA;
-        dst[idx] = (m < Mp && n < nvalid) ? panel[idx] : 0.0;
+      const int nrows = min(TP, sv.Tp - n0);    // points of the padded array this tile owns (pad points := 0)
+      double* dst = p.save + sv.off_a;
+      for (int idx = tid; idx < nrows * Mp; idx += 256) {
+        const int n = idx / Mp, m = idx - n * Mp;
+        dst[iwvi_blk_off(n0 + n, m, NB)] = (n < nvalid) ? panel[n * ldA + m] : 0.0;
       }
     }
 
-    // ---- U: triangular products with tril(q_sqrt_r)^T, column sums of squares
+    // ---- U: triangular products with tril(q_sqrt_r)^T, column sums of squares (no inter-warp data flow)
     for (int r = 0; r < R; r++) {
       double csq[C::TN][2];
 #pragma unroll
@@ -242,9 +254,9 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
         double acc[C::TM][C::TN][2];
         acc_zero<C::TM, C::TN>(acc);
         for (int j = i; j < NB; j++) {
-          const double* st = pipe.wait();
+          const double* st = ring.wait();
           warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
-          pipe.release(seq, warp, lane);
+          ring.release(lane);
         }
 #pragma unroll
         for (int a = 0; a < C::TM; a++)
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
               if (do_save) {
                 const int m = i * IWVI_BLK + wm0 + a * 8 + g;
                 const int n = wn0 + b * 8 + 2 * t + c;
-                if (n0 + n < sv.Tp) p.save[sv.off_u + ((size_t)r * sv.Tp + n0 + n) * ldA + m] = (n0 + n < T) ? u : 0.0;
+                if (n0 + n < sv.Tp) p.save[sv.off_u + r * sv.u_stride + iwvi_blk_off(n0 + n, m, NB)] = (n0 + n < T) ? u : 0.0;
               }
             }
       }
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(256, 1) gp_rows_fwd_kernel(const FwdParams p) 
           if (g == 0) usq[(r * C::WMG + warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c] = v;
         }
     }
-    __syncthreads();
+    named_bar_sync(BAR_ALL, 256);
 
     // ---- E: per-point epilogue
     if (tid < TP && n0 + tid < T) {
@@ -319,7 +331,7 @@ template <int TP>
 int launch_fwd(const FwdParams& p, int smem_bytes, int grid, cudaStream_t stream) {
   if (cudaFuncSetAttribute(gp_rows_fwd_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
-  gp_rows_fwd_kernel<TP><<<grid, 256, smem_bytes, stream>>>(p);
+  gp_rows_fwd_kernel<TP><<<grid, FWD_THREADS, smem_bytes, stream>>>(p);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }
