@@ -645,31 +645,44 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
 #pragma unroll
   for (int a = 0; a < 4; a++) { accq[a][0] = 0.0; accq[a][1] = 0.0; }
 
+  // per-point scale factors of this lane's k indices (k = 4*ks + t), prefetched one chunk ahead so that their
+  // global-memory latency hides behind the previous chunk's DMMAs
+  double sc[16], scn[16];
+  auto load_scales = [&](int c, double (&s_)[16]) {
+    const size_t pt0 = (size_t)c * IWVI_BLK + t;
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) {
+      s_[ks] = is_lm ? -1.0 : 2.0 * __ldg(gvb + (pt0 + 4 * ks) * IWVI_MAX_R + q);
+    }
+  };
+  load_scales(c0, sc);
   for (int c = c0; c < c1; c++) {
+    if (c + 1 < c1) load_scales(c + 1, scn);
     const double* sa = pipe.wait(0);   // [k = point][m]  -> A operand, k-major
     const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major
     const double* ap = sa + t * IWVI_LDS + wm0 + g;
     const double* bp = sb + t * IWVI_LDS + wn0 + g;
-    const size_t pt0 = (size_t)c * IWVI_BLK + t;
-#pragma unroll 2
-    for (int k0 = 0; k0 < IWVI_BLK; k0 += 4) {
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) {
+      const int k0 = 4 * ks;
       double a[4], b[2];
-      const double scl = is_lm ? -1.0 : 2.0 * __ldg(gvb + (pt0 + k0) * IWVI_MAX_R + q);
 #pragma unroll
       for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
 #pragma unroll
-      for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * scl;
+      for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * sc[ks];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[j]);
-      if (do_qmu && wn0 == 0) {
-        const double bq = __ldg(gmb + (pt0 + k0) * IWVI_MAX_R + g);
+      if (do_qmu && wn0 == 0) {   // few CTAs: dq_mu = A gmean_bar rides along
+        const double bq = __ldg(gmb + ((size_t)c * IWVI_BLK + t + k0) * IWVI_MAX_R + g);
 #pragma unroll
         for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
       }
     }
     pipe.release(lane, 2);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) sc[ks] = scn[ks];
   }
 
   double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;

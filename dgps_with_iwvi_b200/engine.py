@@ -189,7 +189,7 @@ class Engine:
                     r['dX'] = z(T, D)
                     r['dls_vec'] = None if r['ard'] else z(D)
                     max_bwd_ws = max(max_bwd_ws, capi.gp_bwd_ws_doubles(d))
-                    max_pbwd_ws = max(max_pbwd_ws, capi.gp_pbwd_ws_doubles(d))
+                    r['pbwd_ws'] = z(capi.gp_pbwd_ws_doubles(d))   # per layer: prologue adjoints overlap on side streams
                 gi += 1
                 D_cur = P
             self.recs.append(r)
@@ -208,8 +208,14 @@ class Engine:
             self.dmean, self.dvar = z(T, self.Dy), z(T, self.Dy)
             self.dkl_local = z(T, self.Lw_total) if self.Lw_total else None
             self.bwd_ws = z(max(max_bwd_ws, 1))
-            self.pbwd_ws = z(max(max_pbwd_ws, 1))
             self.lv_ws = z(max(max_lv_ws, 1))
+        # once-per-layer prologue stages (Cholesky, KL and their adjoints) depend only on the parameters: they run on
+        # side streams, concurrently with each other and with the per-point stages of other layers
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(self.n_gp)]
+        self.ev_start = torch.cuda.Event()
+        self.ev_pro = [torch.cuda.Event() for _ in range(self.n_gp)]
+        self.ev_rows = [torch.cuda.Event() for _ in range(self.n_gp)]
+        self.ev_pbwd = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.X_tiled = None
         if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
             self.X_tiled = z(T, self.Dx)
@@ -253,18 +259,24 @@ class Engine:
     def forward(self):
         flat = self.flat
         flat.refresh_constrained()
+        main = torch.cuda.current_stream()
+        self.ev_start.record(main)
         for r in self.recs:
             if r['type'] != 'gp':
                 continue
             base, feat, layer = r['base'], r['feat'], r['layer']
-            if r['ard']:
-                ls = self._cv(base.lengthscales)
-            else:
-                r['ls_vec'].copy_(self._cv(base.lengthscales).expand(r['D']))
-                ls = r['ls_vec']
-            r['ls'] = ls
-            capi.gp_prologue_fwd(r['d'], self._cv(feat.Z), ls, self._cv(base.variance), self._cv(layer.q_mu),
-                                 self._cv(layer.q_sqrt), r['Lm'], r['aux'], r['kl'], r['info'])
+            side = self.side[r['gi']]
+            side.wait_event(self.ev_start)
+            with torch.cuda.stream(side):
+                if r['ard']:
+                    ls = self._cv(base.lengthscales)
+                else:
+                    r['ls_vec'].copy_(self._cv(base.lengthscales).expand(r['D']))
+                    ls = r['ls_vec']
+                r['ls'] = ls
+                capi.gp_prologue_fwd(r['d'], self._cv(feat.Z), ls, self._cv(base.variance), self._cv(layer.q_mu),
+                                     self._cv(layer.q_sqrt), r['Lm'], r['aux'], r['kl'], r['info'])
+                self.ev_pro[r['gi']].record(side)
         F = None
         if self.X_tiled is not None:
             self._tile(self.X, self.X_tiled)
@@ -288,6 +300,7 @@ class Engine:
             else:
                 layer, base = r['layer'], r['base']
                 r['Fin'] = F
+                main.wait_event(self.ev_pro[r['gi']])
                 capi.gp_rows_fwd(r['d'], r['Lm'], r['aux'], F,
                                  self._cv(layer.kern.W) if r['mix'] else None,
                                  self._cv(layer.mean_function.A) if r['mf'] == 'Linear' else None,
@@ -331,18 +344,28 @@ class Engine:
                 mfb = self._cv(layer.mean_function.b) if lin else None
                 outs = (flat.gview(feat.Z), gls, flat.gview(base.variance), flat.gview(layer.q_mu),
                         flat.gview(layer.q_sqrt))
+                # gradients of frozen W / mean-function parameters are not formed (set_trainable(False),
+                # build_models.py:209,225-227): passing NULL skips their reductions
+                gW = flat.gview(layer.kern.W) if (r['mix'] and layer.kern.W.trainable) else None
+                gA = flat.gview(layer.mean_function.A) if (lin and layer.mean_function.A.trainable) else None
+                gb = flat.gview(layer.mean_function.b) if (lin and layer.mean_function.b.trainable) else None
                 capi.gp_rows_bwd(r['d'], r['Lm'], r['aux'], r['save'], r['Fin'], W, mfA, mfb, r['eps'],
                                  d_next if r['sampled'] else None,
                                  self.dmean if is_last else None, self.dvar if is_last else None,
-                                 r['dX'], outs[0], outs[1], outs[2], outs[3], outs[4], r['dLm'],
-                                 flat.gview(layer.kern.W) if r['mix'] else None,
-                                 flat.gview(layer.mean_function.A) if lin else None,
-                                 flat.gview(layer.mean_function.b) if lin else None, self.bwd_ws)
-                capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), r['Lm'], r['aux'], self._cv(feat.Z),
-                                     r['ls'], self._cv(base.variance), self._cv(layer.q_mu), self._cv(layer.q_sqrt),
-                                     r['dLm'], self.dkl, outs[0], outs[1], outs[2], outs[3], outs[4], self.pbwd_ws)
-                if not r['ard']:
-                    torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                                 r['dX'], outs[0], outs[1], outs[2], outs[3], outs[4], r['dLm'], gW, gA, gb, self.bwd_ws)
+                main = torch.cuda.current_stream()
+                gi = r['gi']
+                self.ev_rows[gi].record(main)
+                side = self.side[gi]
+                side.wait_event(self.ev_rows[gi])
+                with torch.cuda.stream(side):
+                    capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), r['Lm'], r['aux'], self._cv(feat.Z),
+                                         r['ls'], self._cv(base.variance), self._cv(layer.q_mu),
+                                         self._cv(layer.q_sqrt), r['dLm'], self.dkl, outs[0], outs[1], outs[2],
+                                         outs[3], outs[4], r['pbwd_ws'])
+                    if not r['ard']:
+                        torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                    self.ev_pbwd[gi].record(side)
                 d_next = r['dX']
             else:
                 Lw = r['Lw']
@@ -360,6 +383,9 @@ class Engine:
                         flat.gview(p).copy_(r['d_params'][o:o + p.size].view(flat.gview(p).shape))
                         o += p.size
                 d_next = r.get('dF')
+        main = torch.cuda.current_stream()
+        for ev in self.ev_pbwd:
+            main.wait_event(ev)
         return flat.g
 
     def elbo_and_grads(self, X, Y, eps=None, seed=0, step=0, row0=0):
