@@ -48,6 +48,8 @@ SIGNATURES = {
     'iwvi_gp_rows_fwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 12),
     'iwvi_gp_rows_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 23),
     'iwvi_gp_prologue_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 16),
+    'iwvi_gauss_kl_fwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 4),
+    'iwvi_gauss_kl_bwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 6),
     'iwvi_lv_param_doubles': (C.c_int64, [C.POINTER(LvDesc)]),
     'iwvi_lv_bwd_ws_doubles': (C.c_int64, [C.POINTER(LvDesc)]),
     'iwvi_lv_fwd': (C.c_int, [C.POINTER(LvDesc)] + [P] * 9),

@@ -126,6 +126,17 @@ def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls
             'iwvi_gp_prologue_bwd')
 
 
+def gauss_kl_fwd(M, R, q_mu, q_sqrt, kl):
+    _count(1)
+    L.check(L.load().iwvi_gauss_kl_fwd(int(M), int(R), _ptr(q_mu), _ptr(q_sqrt), _ptr(kl), _stream()), 'iwvi_gauss_kl_fwd')
+
+
+def gauss_kl_bwd(M, R, q_mu, q_sqrt, dkl, dq_mu, dq_sqrt):
+    _count(1)
+    L.check(L.load().iwvi_gauss_kl_bwd(int(M), int(R), _ptr(q_mu), _ptr(q_sqrt), _ptr(dkl), _ptr(dq_mu), _ptr(dq_sqrt),
+                                       _stream()), 'iwvi_gauss_kl_bwd')
+
+
 def lv_fwd(d, F, enc_in, params, eps, samples, kl, mu, sigma):
     _count(1)
     L.check(L.load().iwvi_lv_fwd(C.byref(d), _ptr(F), _ptr(enc_in), _ptr(params), _ptr(eps), _ptr(samples), _ptr(kl),

@@ -509,6 +509,38 @@ __global__ void pbwd_final_kernel(const PbwdParams p) {
   }
 }
 
+// standalone whitened KL (reference temp_workaround.py:167-188 -> gpflow gauss_kl with K=None) for operator-level callers;
+// the training path gets the same number from gp_pack_kernel/gp_chol_kernel.  One CTA, fixed-order reduction.
+__global__ void __launch_bounds__(1024) gauss_kl_fwd_kernel(int M, int R, const double* q_mu, const double* q_sqrt, double* kl) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t e = threadIdx.x; e < (int64_t)R * M * M; e += blockDim.x) {
+    const int64_t rem = e % ((int64_t)M * M);
+    const int a = (int)(rem / M), b = (int)(rem - (int64_t)a * M);
+    if (b <= a) {
+      const double v = q_sqrt[e];
+      s += v * v;
+      if (a == b) s -= log(v * v);
+    }
+  }
+  for (int64_t e = threadIdx.x; e < (int64_t)M * R; e += blockDim.x) s += q_mu[e] * q_mu[e];
+  const double tot = block_sum(s, red);
+  if (threadIdx.x == 0) kl[0] = 0.5 * (tot - (double)M * (double)R);
+}
+__global__ void gauss_kl_bwd_kernel(int M, int R, const double* q_mu, const double* q_sqrt, const double* dkl,
+                                    double* dq_mu, double* dq_sqrt) {
+  const double g = dkl[0];
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = gtid; e < (int64_t)R * M * M; e += gsz) {
+    const int64_t rem = e % ((int64_t)M * M);
+    const int a = (int)(rem / M), b = (int)(rem - (int64_t)a * M);
+    double v = 0.0;
+    if (b <= a) { const double q = q_sqrt[e]; v = g * (a == b ? q - 1.0 / q : q); }
+    dq_sqrt[e] = v;
+  }
+  for (int64_t e = gtid; e < (int64_t)M * R; e += gsz) dq_mu[e] = g * q_mu[e];
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -583,6 +615,23 @@ extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, con
   pbwd_gram_kernel<<<(al.Mp + 7) / 8, 256, 0, st>>>(p);
   IWVI_CHECK_LAUNCH();
   pbwd_final_kernel<<<1, 64, 0, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_gauss_kl_fwd(int32_t M, int32_t R, const double* q_mu, const double* q_sqrt, double* kl, void* stream) {
+  if (M < 1 || R < 1) return IWVI_ERR_BAD_DESC;
+  if (!q_mu || !q_sqrt || !kl) return IWVI_ERR_NULL;
+  gauss_kl_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(M, R, q_mu, q_sqrt, kl);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_gauss_kl_bwd(int32_t M, int32_t R, const double* q_mu, const double* q_sqrt, const double* dkl,
+                                 double* dq_mu, double* dq_sqrt, void* stream) {
+  if (M < 1 || R < 1) return IWVI_ERR_BAD_DESC;
+  if (!q_mu || !q_sqrt || !dkl || !dq_mu || !dq_sqrt) return IWVI_ERR_NULL;
+  gauss_kl_bwd_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(M, R, q_mu, q_sqrt, dkl, dq_mu, dq_sqrt);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }

@@ -1,0 +1,331 @@
+"""Operator-level boundary of the hot path: the functions the reference's layers call (reference
+dgps_with_iwvi/temp_workaround.py -- same module name, same function names and argument meaning):
+
+    multisample_sample_conditional(Xnew, feat, kern, f, full_cov=, full_output_cov=, q_sqrt=, white=)   :118-161
+    independent_multisample_sample_conditional(...)                                                    :12-98
+    gauss_kl(q_mu, q_sqrt, K=None)                                                                     :167-188
+
+plus the two helpers layers.py needs (Encoder.__call__ layers.py:137-152, LatentVariableLayer.propagate :72-105).
+Each is a torch.autograd.Function whose forward and backward call the C ABI (include/iwvi_b200.h) on CUDA tensors,
+so `layer.propagate` composes with torch autograd exactly as the reference's composes with tf.gradients.  Whole
+models train through engine.Engine instead (same C ABI, no autograd graph, preallocated buffers).
+
+Extra keyword arguments the reference gets implicitly: `eps` (the N(0,1) draw of tf.random_normal at :89 / layers.py:86;
+drawn with torch.randn when omitted), `mean_function` and `jitter` (the reference adds the mean function in
+GPLayer.propagate, layers.py:46-48; here it is fused into the per-point kernel).
+
+Not on the hot path and therefore not in CUDA (raise NotImplementedError): white=False (:63-65, never taken,
+layers.py:42), q_sqrt=None (:174-184, SGHMC only), 2-D diagonal q_sqrt (:72-73), full_output_cov=True.  full_cov=True
+(:55-57,82-83, whose joint sampler :92-96 has a shape bug and is dead code in training) is served
+forward-only from the saved A / U panels with library GEMMs, for predict_f_full_cov and API completeness."""
+import numpy as np
+import torch
+
+from . import _lib as LIB
+from . import capi
+from .params import Parameter
+
+F64 = torch.float64
+
+
+def _t(v, dev=None):
+    """Constrained value of a Parameter, or a tensor / array, as a float64 tensor on the CUDA device."""
+    if v is None:
+        return None
+    if isinstance(v, Parameter):
+        v = v.value
+    v = torch.as_tensor(v, dtype=F64) if not torch.is_tensor(v) else v
+    if not v.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError('dgps_with_iwvi_b200: no CUDA device -- the conditional has no CPU fallback')
+        v = v.cuda()
+    return v
+
+
+def _c(t):
+    return None if t is None else t.detach().contiguous()
+
+
+def _unblock(save, off, Tp, NB):
+    """Block-major [Tp/64][NB][64][68] panel (csrc/common.cuh SaveLayout) -> [Tp, 64*NB] row-major view copy."""
+    v = save[off:off + (Tp // 64) * NB * 64 * 68].view(Tp // 64, NB, 64, 68)[..., :64]
+    return v.permute(0, 2, 1, 3).reshape(Tp, NB * 64)
+
+
+class _GPConditional(torch.autograd.Function):
+    """iwvi_gp_prologue_fwd + iwvi_gp_rows_fwd; backward = iwvi_gp_rows_bwd + iwvi_gp_prologue_bwd."""
+
+    @staticmethod
+    def forward(ctx, X, Z, ls, variance, q_mu, q_sqrt, W, mfA, mfb, eps, meta):
+        LIB.load()
+        dev = X.device
+        T, D = X.shape
+        M, R = q_mu.shape
+        mix = W is not None
+        P = W.shape[0] if mix else R
+        sample = eps is not None
+        flags = (LIB.FLAG_SAMPLE if sample else 0) | LIB.FLAG_SAVE
+        d = capi.gp_desc(T, M, D, R, P, meta['kern'], mix, meta['mf'], flags, meta['jitter'])
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        Mp = capi.gp_mp(M)
+        Lm, aux, kl = z(Mp, Mp), z(capi.gp_aux_doubles(d)), z(1)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        Xc, Zc, lsc, vc, qmc, qsc = _c(X), _c(Z), _c(ls), _c(variance).reshape(1), _c(q_mu), _c(q_sqrt)
+        Wc, Ac, bc, ec = _c(W), _c(mfA), _c(mfb), _c(eps)
+        capi.gp_prologue_fwd(d, Zc, lsc, vc, qmc, qsc, Lm, aux, kl, info)
+        mean, var = z(T, P), z(T, P)
+        smp = z(T, P) if sample else None
+        save = z(capi.gp_save_doubles(d))
+        capi.gp_rows_fwd(d, Lm, aux, Xc, Wc, Ac, bc, ec, smp, mean, var, save)
+        if meta.get('check', True):
+            i = int(info.item())
+            if i:
+                raise RuntimeError('Cholesky of Kuu failed: leading minor of order %d is not positive definite' % i)
+        ctx.d, ctx.meta = d, meta
+        ctx.saved = (Xc, Zc, lsc, vc, qmc, qsc, Wc, Ac, bc, ec, Lm, aux, save)
+        ctx.var_shape = variance.shape
+        meta['_save'] = (save, Lm, aux, d)   # for the forward-only full-covariance branch
+        if smp is None:
+            smp = mean.new_zeros(0)
+        ctx.mark_non_differentiable(kl)
+        return smp, mean, var, kl
+
+    @staticmethod
+    def backward(ctx, d_sample, d_mean, d_var, _d_kl):
+        Xc, Zc, lsc, vc, qmc, qsc, Wc, Ac, bc, ec, Lm, aux, save = ctx.saved
+        d = ctx.d
+        dev = Xc.device
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        T, D = Xc.shape
+        M, R = qmc.shape
+        Mp = Lm.shape[0]
+        sampled = ec is not None
+        dX, dZ, dls, dv, dqm, dqs, dLm = z(T, D), z(M, D), z(D), z(1), z(M, R), z(R, M, M), z(Mp, Mp)
+        dW = z(*Wc.shape) if Wc is not None else None
+        dA = z(*Ac.shape) if Ac is not None else None
+        db = z(*bc.shape) if bc is not None else None
+        ws = z(capi.gp_bwd_ws_doubles(d))
+        capi.gp_rows_bwd(d, Lm, aux, save, Xc, Wc, Ac, bc, ec,
+                         _c(d_sample) if (sampled and d_sample is not None and d_sample.numel()) else None,
+                         _c(d_mean), _c(d_var), dX, dZ, dls, dv, dqm, dqs, dLm, dW, dA, db, ws)
+        capi.gp_prologue_bwd(capi.with_flags(d, d.flags | LIB.FLAG_ACCUM), Lm, aux, Zc, lsc, vc, qmc, qsc, dLm, z(1),
+                             dZ, dls, dv, dqm, dqs, z(capi.gp_pbwd_ws_doubles(d)))
+        return dX, dZ, dls, dv.reshape(ctx.var_shape), dqm, dqs, dW, dA, db, None, None
+
+
+def _kern_parts(kern):
+    mix = hasattr(kern, 'W')
+    base = kern.kernel if mix else kern
+    return mix, base
+
+
+def _torch_K(kind, X, X2, ls, variance):
+    """Stationary kernel matrix in torch (GPflow 1.x formulas) -- only for the forward-only full-cov branch."""
+    Xs, X2s = X / ls, X2 / ls
+    r2 = (Xs * Xs).sum(-1)[..., :, None] + (X2s * X2s).sum(-1)[..., None, :] - 2.0 * Xs @ X2s.transpose(-1, -2)
+    if kind == 'RBF':
+        return variance * torch.exp(-0.5 * r2)
+    r = torch.sqrt(torch.clamp(r2, min=1e-40))
+    if kind == 'Matern12':
+        return variance * torch.exp(-r)
+    if kind == 'Matern32':
+        return variance * (1.0 + 3.0 ** 0.5 * r) * torch.exp(-3.0 ** 0.5 * r)
+    return variance * (1.0 + 5.0 ** 0.5 * r + 5.0 / 3.0 * r * r) * torch.exp(-5.0 ** 0.5 * r)
+
+
+def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=False, q_sqrt=None, white=False,
+                                               eps=None, mean_function=None, jitter=1e-6, W=None, sample=True):
+    """Reference temp_workaround.py:12-98.  Xnew [S, N, D] (or [T, D]); f = q_mu [M, R]; q_sqrt [R, M, M].
+    Returns sample, mean [S, N, P], var [S, N, P] (full_cov=False) or [S, R, N, N] (full_cov=True, forward only)."""
+    if not white:
+        raise NotImplementedError('white=False (temp_workaround.py:63-65) is never taken by GPLayer (layers.py:42)')
+    if q_sqrt is None:
+        raise NotImplementedError('q_sqrt=None is the SGHMC branch (temp_workaround.py:174-184), outside the IW-ELBO path')
+    X = _t(Xnew)
+    lead = X.shape[:-1]
+    D = X.shape[-1]
+    X2 = X.reshape(-1, D)
+    T = X2.shape[0]
+    Z = _t(feat.feat.Z if hasattr(feat, 'feat') else feat.Z)
+    q_mu, q_sq = _t(f), _t(q_sqrt)
+    if q_sq.dim() != 3:
+        raise NotImplementedError('diagonal q_sqrt [M, R] (temp_workaround.py:72-73) is not used by GPLayer (layers.py:21-25)')
+    M, R = q_mu.shape
+    ls, variance = _t(kern.lengthscales), _t(kern.variance)
+    ls_vec = ls.expand(D) if ls.dim() == 0 or ls.numel() == 1 else ls
+    Wt = _t(W)
+    mf_kind = mean_function.kind if mean_function is not None else 'Zero'
+    mfA = _t(mean_function.A) if mf_kind == 'Linear' else None
+    mfb = _t(mean_function.b) if mf_kind == 'Linear' else None
+    P = Wt.shape[0] if Wt is not None else R
+    if sample and not full_cov:
+        e = torch.randn(T, R, dtype=F64, device=X.device) if eps is None else _t(eps).reshape(T, R)
+    else:
+        e = None
+    meta = dict(kern=kern.kind, mf=mf_kind, jitter=float(jitter))
+    smp, mean, var, _ = _GPConditional.apply(X2, Z, ls_vec, variance, q_mu, q_sq, Wt, mfA, mfb, e, meta)
+    mean_o = mean.reshape(*lead, P)
+    if not full_cov:
+        return (smp.reshape(*lead, P) if e is not None else None), mean_o, var.reshape(*lead, P)
+    # ---- full covariance over the inner axis (forward only; library GEMMs on the saved panels) ----
+    if Wt is not None:
+        raise NotImplementedError('the Mok branch forces full_cov=False (temp_workaround.py:125-129)')
+    with torch.no_grad():
+        save, Lm, aux, d = meta['_save']
+        S_ = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
+        N = lead[-1]
+        Tp = (T + 127) // 128 * 128
+        NB = capi.gp_mp(M) // 64
+        stride = (Tp // 64) * NB * 64 * 68
+        A = _unblock(save, 0, Tp, NB)[:T].reshape(S_, N, NB * 64)
+        Knn = _torch_K(kern.kind, X.reshape(S_, N, D), X.reshape(S_, N, D), ls_vec, variance)
+        base = Knn - A @ A.transpose(1, 2)                                     # [S, N, N]
+        cov = []
+        for r in range(R):
+            U = _unblock(save, (1 + r) * stride, Tp, NB)[:T].reshape(S_, N, NB * 64)
+            cov.append(base + U @ U.transpose(1, 2))
+        cov = torch.stack(cov, 1)                                              # [S, R, N, N]
+        smp_o = None
+        if sample:
+            # the joint draw the reference intends at :92-96 (its own version has a shape bug and never executes)
+            z = torch.randn(S_, R, N, 1, dtype=F64, device=X.device) if eps is None else _t(eps).reshape(S_, R, N, 1)
+            Lc = torch.linalg.cholesky(cov)
+            smp_o = (mean.reshape(S_, N, R).transpose(1, 2)[..., None] + Lc @ z)[..., 0].transpose(1, 2).reshape(*lead, R)
+    if len(lead) == 1:
+        cov = cov[0]
+    return smp_o, mean_o, cov
+
+
+def multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=False, full_output_cov=False, q_sqrt=None,
+                                   white=False, eps=None, mean_function=None, jitter=1e-6, sample=True):
+    """Reference temp_workaround.py:118-161.  SharedMixedMok + MixedKernelSharedMof: the latent GPs are evaluated with
+    full_cov forced to False (:125-129) and mixed by W (mean, sample: @ W^T; variance: @ (W^2)^T, :142-145) -- fused in
+    the per-point kernel.  2-D inputs (the gpflow sample_conditional branch, :133-140,156-161) run the same kernel."""
+    if full_output_cov:
+        raise NotImplementedError('full_output_cov=True is not used on the IW-ELBO path')
+    mix, base = _kern_parts(kern)
+    if mix:
+        return independent_multisample_sample_conditional(
+            Xnew, feat, base, f, full_cov=False, q_sqrt=q_sqrt, white=white, eps=eps, mean_function=mean_function,
+            jitter=jitter, W=kern.W, sample=sample)
+    return independent_multisample_sample_conditional(
+        Xnew, feat, base, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white, eps=eps, mean_function=mean_function,
+        jitter=jitter, sample=sample)
+
+
+class _GaussKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_mu, q_sqrt):
+        LIB.load()
+        qm, qs = _c(q_mu), _c(q_sqrt)
+        M, R = qm.shape
+        kl = torch.zeros(1, dtype=F64, device=qm.device)
+        capi.gauss_kl_fwd(M, R, qm, qs, kl)
+        ctx.saved = (qm, qs)
+        return kl.reshape(())
+
+    @staticmethod
+    def backward(ctx, dkl):
+        qm, qs = ctx.saved
+        M, R = qm.shape
+        dqm, dqs = torch.zeros_like(qm), torch.zeros_like(qs)
+        capi.gauss_kl_bwd(M, R, qm, qs, dkl.detach().reshape(1).contiguous(), dqm, dqs)
+        return dqm, dqs
+
+
+def gauss_kl(q_mu, q_sqrt, K=None):
+    """Reference temp_workaround.py:167-188 with q_sqrt given: gpflow's whitened gauss_kl (K must be None, as at
+    layers.py:44)."""
+    if K is not None:
+        raise NotImplementedError('GPLayer uses the whitened KL (K=None, layers.py:44)')
+    if q_sqrt is None:
+        raise NotImplementedError('q_sqrt=None is the SGHMC branch (temp_workaround.py:174-184)')
+    return _GaussKL.apply(_t(q_mu), _t(q_sqrt))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LatentVariableLayer / Encoder
+# ------------------------------------------------------------------------------------------------------------------
+class _LVPropagate(torch.autograd.Function):
+    """iwvi_lv_fwd / iwvi_lv_bwd.  F [T, Df], enc_in [T, Dxy] or None (prior branch), params packed W0,b0,W1,b1,..."""
+
+    @staticmethod
+    def forward(ctx, F, enc_in, params, eps, meta):
+        LIB.load()
+        dev = eps.device
+        T, Lw = eps.shape
+        Df = 0 if F is None else F.shape[1]
+        prior = enc_in is None
+        d = capi.lv_desc(T, 1, Df, 0 if prior else enc_in.shape[1], Lw, None if prior else meta['dims'],
+                         sampled=meta['sampled'], f_bcast=False, prior=prior, prior_mu=meta.get('prior_mu', 0.0),
+                         prior_sigma=meta.get('prior_sigma', 1.0))
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        samples, kl, mu, sigma = z(T, Df + Lw), z(T, Lw), z(T, Lw), z(T, Lw)
+        Fc, Ec, Pc, ec = _c(F), _c(enc_in), _c(params), _c(eps)
+        capi.lv_fwd(d, Fc, Ec, Pc, ec, samples, kl, mu, sigma)
+        ctx.d = d
+        ctx.saved = (Fc, Ec, Pc, ec, mu, sigma)
+        return samples, kl, mu, sigma
+
+    @staticmethod
+    def backward(ctx, d_samples, d_kl, d_mu, d_sigma):
+        Fc, Ec, Pc, ec, mu, sigma = ctx.saved
+        d = ctx.d
+        dev = ec.device
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        dF = z(*Fc.shape) if Fc is not None else None
+        if d.prior:
+            capi.lv_bwd(d, Fc, None, None, ec, None, None, _c(d_samples), _c(d_kl), None, None, None, dF, None)
+            return dF, None, None, None, None
+        dP = z(Pc.numel())
+        ws = z(capi.lv_bwd_ws_doubles(d))
+        capi.lv_bwd(d, Fc, Ec, Pc, ec, mu, sigma, _c(d_samples), _c(d_kl), _c(d_mu), _c(d_sigma), dP, dF, ws)
+        return dF, None, dP, None, None
+
+
+def _packed_encoder_params(enc):
+    return torch.cat([_t(p).reshape(-1) for pair in zip(enc.Ws, enc.bs) for p in pair])
+
+
+def encoder_forward(enc, Z):
+    """Encoder.__call__ (reference layers.py:137-152): Z [..., input_dim] -> (q_mu, q_sqrt) [..., latent_dim]."""
+    Zt = _t(Z)
+    lead = Zt.shape[:-1]
+    Z2 = Zt.reshape(-1, Zt.shape[-1])
+    eps0 = torch.zeros(Z2.shape[0], enc.latent_dim, dtype=F64, device=Z2.device)
+    meta = dict(dims=enc.layer_dims, sampled=False)
+    _, _, mu, sigma = _LVPropagate.apply(None, Z2, _packed_encoder_params(enc), eps0, meta)
+    return mu.reshape(*lead, enc.latent_dim), sigma.reshape(*lead, enc.latent_dim)
+
+
+def latent_variable_propagate(layer, F, inference_amorization_inputs=None, is_sampled_local_regularizer=False, eps=None):
+    """LatentVariableLayer.propagate (reference layers.py:72-105) -> (samples, mean, cov, kl):
+    samples = [F, W], mean = [F, q_mu], cov = [0, q_sqrt^2], kl [..., latent_dim] = log q(W) - log p(W) per sample
+    (is_sampled_local_regularizer) or the closed-form KL[q||N(0,1)]."""
+    Ft = _t(F)
+    lead = Ft.shape[:-1]
+    Df, Lw = Ft.shape[-1], layer.latent_dim
+    F2 = Ft.reshape(-1, Df)
+    T = F2.shape[0]
+    e = torch.randn(T, Lw, dtype=F64, device=F2.device) if eps is None else _t(eps).reshape(T, Lw)
+    meta = dict(sampled=bool(is_sampled_local_regularizer), prior_mu=layer.prior_mu, prior_sigma=layer.prior_sigma)
+    if inference_amorization_inputs is None:
+        samples, kl, mu, sigma = _LVPropagate.apply(F2, None, None, e, meta)
+    else:
+        XY = _t(inference_amorization_inputs)
+        meta['dims'] = layer.encoder.layer_dims
+        samples, kl, mu, sigma = _LVPropagate.apply(F2, XY.reshape(T, XY.shape[-1]),
+                                                    _packed_encoder_params(layer.encoder), e, meta)
+    mean = torch.cat([F2, mu], 1)
+    cov = torch.cat([torch.zeros_like(F2), sigma * sigma], 1)
+    r = lambda a, c: a.reshape(*lead, c)
+    return r(samples, Df + Lw), r(mean, Df + Lw), r(cov, Df + Lw), r(kl, Lw)
+
+
+def full_cov_conditional(layer, X):
+    """Single-GPLayer _build_predict(X, full_cov=True) (reference models.py:89-91 via GPModel.predict_f_full_cov, pinned
+    by tests/test_gp_layer.py:53-54): mean [N, R], cov [R, N, N]."""
+    _, mean, cov = multisample_sample_conditional(
+        X, layer.feature, layer.kern, layer.q_mu, full_cov=True, q_sqrt=layer.q_sqrt, white=True,
+        mean_function=layer.mean_function, jitter=layer.jitter, sample=False)
+    return mean, cov

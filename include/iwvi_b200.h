@@ -141,6 +141,15 @@ int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* 
                          double* dZ, double* dls, double* dvariance, double* dq_mu, double* dq_sqrt,
                          double* ws, void* stream);
 
+/*
+ * Whitened KL[q(u)||p(u)] on its own, for callers of the operator-level gauss_kl(q_mu, q_sqrt) (temp_workaround.py:167-188
+ * with K=None -> gpflow gauss_kl): kl = 0.5 (sum q_mu^2 - M R - sum log diag(Lq)^2 + sum Lq^2), Lq = tril(q_sqrt).
+ * iwvi_gp_prologue_fwd returns the same number as a by-product.  dkl [1] device scalar cotangent; outputs overwritten.
+ */
+int iwvi_gauss_kl_fwd(int32_t M, int32_t R, const double* q_mu, const double* q_sqrt, double* kl, void* stream);
+int iwvi_gauss_kl_bwd(int32_t M, int32_t R, const double* q_mu, const double* q_sqrt, const double* dkl,
+                      double* dq_mu, double* dq_sqrt, void* stream);
+
 /* ---- LatentVariableLayer + Encoder (layers.py:72-105, :137-152) ---- */
 typedef struct iwvi_lv_desc {
   int32_t Be;        /* distinct encoder rows                                              */
