@@ -47,10 +47,17 @@ __host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   w.npairs = al.NB * (al.NB + 1) / 2;
   const int nchunks = w.Tp / IWVI_BLK;
   const int items = (d.R + 1) * w.npairs;
-  int S = (3 * nsm + items - 1) / items;
-  if (S > nchunks) S = nchunks;
-  if (S < 1) S = 1;
-  w.chunks_per_split = (nchunks + S - 1) / S;
+  // split the points into S ranges so that items * S CTAs fill whole waves of the nsm SMs (one CTA per SM): minimise
+  // rounds * chunks-per-split, with a small charge per extra partial the finalize kernel has to sum
+  int bestS = 1;
+  double best = 1e300;
+  for (int S = 1; S <= 16 && S <= nchunks; S++) {
+    const int cps = (nchunks + S - 1) / S;
+    const int rounds = (items * S + nsm - 1) / nsm;
+    const double cost = (double)rounds * cps + 0.5 * S;
+    if (cost < best) { best = cost; bestS = S; }
+  }
+  w.chunks_per_split = (nchunks + bestS - 1) / bestS;
   w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
   int64_t o = 0;
@@ -180,16 +187,27 @@ __global__ void __launch_bounds__(EPI_PTS) gp_epi_bwd_kernel(const BwdParams p) 
 // 2. tile kernel
 // ------------------------------------------------------------------------------------------------
 struct BwdSeq {
-  int NB, R, npairs, ldz;
-  const double *Zt, *Lmb, *Lqb;
+  int NB, R, npairs, ldz, tp_bytes;
+  const double *Zt, *Lmb, *Lqb, *A_T, *U_T;
+  int64_t u_stride;
+  int64_t tile_off;   // offset of this tile's rows inside block 0 of its 64-point chunk (block-major saved arrays)
   int ph, r, i, j;
-  __device__ __forceinline__ void init() { ph = 0; r = 0; i = 0; j = 0; }
+  __device__ __forceinline__ void init(int n0) {
+    ph = -1; r = 0; i = 0; j = 0;
+    tile_off = (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
+  }
   __device__ __forceinline__ bool done() const { return ph == 3; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
     b.bytes = IWVI_STAGE_DOUBLES * 8;
-    if (ph == 0) {           // tril(q_sqrt_r) block (row block i, col block j), i >= j
-      b.src = Lqb + ((size_t)r * npairs + iwvi_pair(i, j)) * IWVI_STAGE_DOUBLES;
+    if (ph == -1) {          // saved A, m-block i, rows of this tile (contiguous)
+      b.src = A_T + tile_off + (int64_t)i * IWVI_STAGE_DOUBLES; b.bytes = (uint32_t)tp_bytes;
+    } else if (ph == 0) {
+      if (i < j) {           // saved U_r, m-block j, rows of this tile
+        b.src = U_T + (int64_t)r * u_stride + tile_off + (int64_t)j * IWVI_STAGE_DOUBLES; b.bytes = (uint32_t)tp_bytes;
+      } else {               // tril(q_sqrt_r) block (row block i, col block j), i >= j
+        b.src = Lqb + ((size_t)r * npairs + iwvi_pair(i, j)) * IWVI_STAGE_DOUBLES;
+      }
     } else if (ph == 1) {    // Lm block (row block j, col block i), j > i; j == NB: inverted diagonal block i
       b.src = Lmb + (size_t)(j < NB ? iwvi_pair(j, i) : iwvi_pair(i, i)) * IWVI_STAGE_DOUBLES;
     } else {                 // scaled inducing inputs, block i
@@ -198,8 +216,10 @@ struct BwdSeq {
     return b;
   }
   __device__ __forceinline__ void advance() {
-    if (ph == 0) {
-      if (++i == NB) { ++j; i = j; if (j == NB) { ++r; j = 0; i = 0; if (r == R) { ph = 1; i = NB - 1; j = NB; } } }
+    if (ph == -1) {
+      if (++i == NB) { ph = 0; r = 0; j = 0; i = -1; }
+    } else if (ph == 0) {
+      if (++i == NB) { ++j; i = j - 1; if (j == NB) { ++r; j = 0; i = -1; if (r == R) { ph = 1; i = NB - 1; j = NB; } } }
     } else if (ph == 1) {
       if (j < NB) ++j;
       else { --i; j = i + 1; if (i < 0) { ph = 2; i = 0; } }
@@ -260,8 +280,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     BwdSeq seq;
     seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
     seq.Zt = aux + al.off_zt; seq.Lmb = aux + al.off_lmb; seq.Lqb = aux + al.off_lqb;
+    const SaveLayout svp = iwvi_save_layout(T, M, R);
+    seq.A_T = p.save + svp.off_a; seq.U_T = p.save + svp.off_u; seq.u_stride = svp.u_stride;
+    seq.tp_bytes = TP * IWVI_LDS * 8;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      seq.init();
+      seq.init(tile * TP);
       while (!seq.done()) { pipe.produce(seq.get(), lane); seq.advance(); }
     }
     return;
@@ -317,27 +340,43 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     }
     named_bar_sync(BAR_ALL, 256);
 
-    // ---- Abar, part 1: q_mu gmean_bar^T - 2 A gsum   (A read from the saved point-major array, coalesced)
-    for (int idx = tid; idx < TP * Mp; idx += 256) {
-      const int n = idx / Mp, m = idx - n * Mp;
-      double v = -2.0 * A_T[iwvi_blk_off(n0 + n, m, NB)] * gsum_s[n];
-      const double* q = qmu + (size_t)m * IWVI_MAX_R;
-      for (int r = 0; r < R; r++) v += q[r] * gmb_s[r * TP + n];
-      panel[n * ldA + m] = v;
+    // ---- Abar, part 1: q_mu gmean_bar^T - 2 A gsum.  The saved A arrives block by block through the ring (the
+    //      producer warp prefetches it while the previous tile finishes), never through synchronous global loads.
+    {
+      const int mm = tid & 63;          // this thread's inducing index inside every block; its points: tid/64 + 4*q
+      for (int mb = 0; mb < NB; mb++) {
+        const double* q = qmu + (size_t)(mb * IWVI_BLK + mm) * IWVI_MAX_R;
+        double qr[IWVI_MAX_R];
+#pragma unroll
+        for (int r = 0; r < IWVI_MAX_R; r++) qr[r] = q[r];
+        const double* st = pipe.wait();
+        for (int n = tid >> 6; n < TP; n += 4) {
+          double v = -2.0 * st[n * IWVI_LDS + mm] * gsum_s[n];
+#pragma unroll
+          for (int r = 0; r < IWVI_MAX_R; r++) v += qr[r] * gmb_s[r * TP + n];
+          panel[n * ldA + mb * IWVI_BLK + mm] = v;
+        }
+        pipe.release(lane);
+      }
     }
     named_bar_sync(BAR_ALL, 256);
 
     // ---- Abar, part 2: += 2 tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register B-fragments per k-block j
+    //      (the saved U_r block comes through the ring too, ahead of the tril(q_sqrt) blocks that multiply it)
     for (int r = 0; r < R; r++) {
       for (int j = 0; j < NB; j++) {
         double vb[16][2];
+        {
+          const double* su = pipe.wait();
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
-          const int n = wn0 + b * 8 + g;
-          const double sc = gvb_s[r * TP + n];
-          const double* up = U_T + r * sv.u_stride + iwvi_blk_off(n0 + n, j * IWVI_BLK, NB) + t;
+          for (int b = 0; b < 2; b++) {
+            const int n = wn0 + b * 8 + g;
+            const double sc = gvb_s[r * TP + n];
+            const double* up = su + n * IWVI_LDS + t;
 #pragma unroll
-          for (int ks = 0; ks < 16; ks++) vb[ks][b] = up[ks * 4] * sc;
+            for (int ks = 0; ks < 16; ks++) vb[ks][b] = up[ks * 4] * sc;
+          }
+          pipe.release(lane);
         }
         for (int i = j; i < NB; i++) {
           const double* st = pipe.wait();
@@ -593,6 +632,51 @@ struct RedSeq {
   __device__ __forceinline__ void advance() { if (which == 0) which = 1; else { which = 0; ++c; } }
 };
 
+struct ReduceLoopArgs { const double *gvb, *gmb; int q; bool is_lm; int c0, c1, wm0, wn0, lane; };
+
+template <bool QMU>
+__device__ __forceinline__ void reduce_loop(RingT<4>& pipe, const ReduceLoopArgs& la, double (&acc)[4][2][2],
+                                            double (&accq)[4][2]) {
+  const int g = la.lane >> 2, t = la.lane & 3;
+  // per-point scale factors of this lane's k indices (k = 4*ks + t), prefetched one chunk ahead so that their
+  // global-memory latency hides behind the previous chunk's DMMAs
+  double sc[16], scn[16];
+  auto load_scales = [&](int c, double (&s_)[16]) {
+    const size_t pt0 = (size_t)c * IWVI_BLK + t;
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) s_[ks] = la.is_lm ? -1.0 : 2.0 * __ldg(la.gvb + (pt0 + 4 * ks) * IWVI_MAX_R + la.q);
+  };
+  load_scales(la.c0, sc);
+  for (int c = la.c0; c < la.c1; c++) {
+    if (c + 1 < la.c1) load_scales(c + 1, scn);
+    const double* sa = pipe.wait(0);   // [k = point][m]  -> A operand, k-major
+    const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major
+    const double* ap = sa + t * IWVI_LDS + la.wm0 + g;
+    const double* bp = sb + t * IWVI_LDS + la.wn0 + g;
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) {
+      const int k0 = 4 * ks;
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
+#pragma unroll
+      for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * sc[ks];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[j]);
+      if (QMU) {
+        const double bq = __ldg(la.gmb + ((size_t)c * IWVI_BLK + t + k0) * IWVI_MAX_R + g);
+#pragma unroll
+        for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
+      }
+    }
+    pipe.release(la.lane, 2);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) sc[ks] = scn[ks];
+  }
+}
+
 #define RED_NST 4
 #define RED_THREADS 288   // 8 consumer warps + 1 producer warp
 __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const BwdParams p) {
@@ -645,45 +729,12 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
 #pragma unroll
   for (int a = 0; a < 4; a++) { accq[a][0] = 0.0; accq[a][1] = 0.0; }
 
-  // per-point scale factors of this lane's k indices (k = 4*ks + t), prefetched one chunk ahead so that their
-  // global-memory latency hides behind the previous chunk's DMMAs
-  double sc[16], scn[16];
-  auto load_scales = [&](int c, double (&s_)[16]) {
-    const size_t pt0 = (size_t)c * IWVI_BLK + t;
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++) {
-      s_[ks] = is_lm ? -1.0 : 2.0 * __ldg(gvb + (pt0 + 4 * ks) * IWVI_MAX_R + q);
-    }
-  };
-  load_scales(c0, sc);
-  for (int c = c0; c < c1; c++) {
-    if (c + 1 < c1) load_scales(c + 1, scn);
-    const double* sa = pipe.wait(0);   // [k = point][m]  -> A operand, k-major
-    const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major
-    const double* ap = sa + t * IWVI_LDS + wm0 + g;
-    const double* bp = sb + t * IWVI_LDS + wn0 + g;
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++) {
-      const int k0 = 4 * ks;
-      double a[4], b[2];
-#pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
-#pragma unroll
-      for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * sc[ks];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[j]);
-      if (do_qmu && wn0 == 0) {   // few CTAs: dq_mu = A gmean_bar rides along
-        const double bq = __ldg(gmb + ((size_t)c * IWVI_BLK + t + k0) * IWVI_MAX_R + g);
-#pragma unroll
-        for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
-      }
-    }
-    pipe.release(lane, 2);
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++) sc[ks] = scn[ks];
-  }
+  // The two warps of the few CTAs that also form dq_mu = A gmean_bar take a separate copy of the loop: a DMMA that is
+  // merely predicated off still occupies the FP64 pipe for its full 16 cycles (measured: 24 instead of 16 cycles per
+  // useful DMMA when the ride-along sat under a predicate in the common loop).
+  const ReduceLoopArgs la = {gvb, gmb, q, is_lm, c0, c1, wm0, wn0, lane};
+  if (do_qmu && wn0 == 0) reduce_loop<true>(pipe, la, acc, accq);
+  else reduce_loop<false>(pipe, la, acc, accq);
 
   double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;
 #pragma unroll

@@ -215,25 +215,27 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     }
     named_bar_sync(BAR_ALL, 256);
 
-    // ---- S: fvar0 and latent means; optional save of A (contiguous tile of the point-major array)
-    for (int n = warp; n < TP; n += C::NW) {
-      double s[IWVI_MAX_R + 1];
-#pragma unroll
-      for (int r = 0; r <= IWVI_MAX_R; r++) s[r] = 0.0;
-      for (int m = lane; m < Mp; m += 32) {
-        const double a = panel[n * ldA + m];
-        s[IWVI_MAX_R] += a * a;
-        const double* q = qmu + (size_t)m * IWVI_MAX_R;
-#pragma unroll
-        for (int r = 0; r < IWVI_MAX_R; r++) s[r] += a * q[r];
+    // ---- S: fvar0 = sum_m A^2 and the latent means gmean = A^T q_mu, as one skinny DMMA product per 8 points
+    //      (A fragments from the panel, q_mu [Mp, 8] fragments straight from L1/L2); two accumulators break the
+    //      dependency chain.  The squares ride along on the A fragments.
+    for (int mt = warp; mt < TP / 8; mt += C::NW) {
+      const double* ap = panel + (mt * 8 + g) * ldA + t;
+      const double* bp = qmu + (size_t)t * IWVI_MAX_R + g;
+      double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0}, sq0 = 0.0, sq1 = 0.0;
+#pragma unroll 4
+      for (int k0 = 0; k0 < Mp; k0 += 8) {
+        const double a0 = ap[k0], a1 = ap[k0 + 4];
+        const double b0 = __ldg(bp + (size_t)k0 * IWVI_MAX_R), b1 = __ldg(bp + (size_t)(k0 + 4) * IWVI_MAX_R);
+        dmma884(c0, a0, b0);
+        dmma884(c1, a1, b1);
+        sq0 += a0 * a0; sq1 += a1 * a1;
       }
-#pragma unroll
-      for (int r = 0; r <= IWVI_MAX_R; r++) s[r] = warp_sum(s[r]);
-      if (lane == 0) {
-        fv0[n] = s[IWVI_MAX_R];
-#pragma unroll
-        for (int r = 0; r < IWVI_MAX_R; r++) gms[r * TP + n] = s[r];
-      }
+      double sq = sq0 + sq1;
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      if (t == 0) fv0[mt * 8 + g] = sq;
+      gms[(2 * t) * TP + mt * 8 + g] = c0[0] + c1[0];
+      gms[(2 * t + 1) * TP + mt * 8 + g] = c0[1] + c1[1];
     }
     if (do_save) {
       const int nvalid = min(TP, T - n0);       // real points of this tile
@@ -286,42 +288,45 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     }
     named_bar_sync(BAR_ALL, 256);
 
-    // ---- E: per-point epilogue
-    if (tid < TP && n0 + tid < T) {
-      const int n = tid;
-      const size_t pt = (size_t)(n0 + n);
-      double gm[IWVI_MAX_R], gv[IWVI_MAX_R], gs[IWVI_MAX_R];
-      for (int r = 0; r < R; r++) {
-        gm[r] = gms[r * TP + n];
-        double us = 0.0;
+    // ---- E: per-point epilogue, 256/TP threads per point sharing its output columns
+    {
+      constexpr int QT = 256 / TP;
+      const int n = tid / QT, q0 = tid % QT;
+      if (n0 + n < T) {
+        const size_t pt = (size_t)(n0 + n);
+        double gm[IWVI_MAX_R], gv[IWVI_MAX_R], gs[IWVI_MAX_R];
+        for (int r = 0; r < R; r++) {
+          gm[r] = gms[r * TP + n];
+          double us = 0.0;
 #pragma unroll
-        for (int wg = 0; wg < C::WMG; wg++) us += usq[(r * C::WMG + wg) * TP + n];
-        gv[r] = variance - fv0[n] + us;
-        gs[r] = do_sample ? gm[r] + p.eps[pt * R + r] * sqrt(gv[r]) : 0.0;
-        if (do_save) {
-          p.save[sv.off_gvar + pt * R + r] = gv[r];
-          p.save[sv.off_gmean + pt * R + r] = gm[r];
-        }
-      }
-      const int P = d.P;
-      for (int q = 0; q < P; q++) {
-        double mf = 0.0;
-        if (d.mf == IWVI_MF_IDENTITY) mf = p.X[pt * D + q];
-        else if (d.mf == IWVI_MF_LINEAR) {
-          mf = p.mfb[q];
-          for (int k = 0; k < D; k++) mf += p.X[pt * D + k] * p.mfA[k * P + q];
-        }
-        double om, ov, os;
-        if (d.mix) {
-          om = 0.0; ov = 0.0; os = 0.0;
-          for (int r = 0; r < R; r++) {
-            const double w = p.W[q * R + r];
-            om += gm[r] * w; ov += gv[r] * w * w; os += gs[r] * w;
+          for (int wg = 0; wg < C::WMG; wg++) us += usq[(r * C::WMG + wg) * TP + n];
+          gv[r] = variance - fv0[n] + us;
+          gs[r] = do_sample ? gm[r] + p.eps[pt * R + r] * sqrt(gv[r]) : 0.0;
+          if (do_save && q0 == 0) {
+            p.save[sv.off_gvar + pt * R + r] = gv[r];
+            p.save[sv.off_gmean + pt * R + r] = gm[r];
           }
-        } else { om = gm[q]; ov = gv[q]; os = gs[q]; }
-        p.mean[pt * P + q] = om + mf;
-        p.var[pt * P + q] = ov;
-        if (do_sample) p.sample[pt * P + q] = os + mf;
+        }
+        const int P = d.P;
+        for (int q = q0; q < P; q += QT) {
+          double mf = 0.0;
+          if (d.mf == IWVI_MF_IDENTITY) mf = p.X[pt * D + q];
+          else if (d.mf == IWVI_MF_LINEAR) {
+            mf = p.mfb[q];
+            for (int k = 0; k < D; k++) mf += p.X[pt * D + k] * p.mfA[k * P + q];
+          }
+          double om, ov, os;
+          if (d.mix) {
+            om = 0.0; ov = 0.0; os = 0.0;
+            for (int r = 0; r < R; r++) {
+              const double w = p.W[q * R + r];
+              om += gm[r] * w; ov += gv[r] * w * w; os += gs[r] * w;
+            }
+          } else { om = gm[q]; ov = gv[q]; os = gs[q]; }
+          p.mean[pt * P + q] = om + mf;
+          p.var[pt * P + q] = ov;
+          if (do_sample) p.sample[pt * P + q] = os + mf;
+        }
       }
     }
   }
