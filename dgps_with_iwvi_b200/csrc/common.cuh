@@ -145,6 +145,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// 1-D bulk copy shared -> global (asynchronous TMA store, tracked by bulk async-groups of the issuing thread)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's bulk stores have finished READING shared memory (their source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (before a barrier + bulk store)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // A 2-deep (NST) ring of 64-row blocks filled by warp 0 with bulk TMA; arrival through mbarriers,
 // release through the block-wide barrier that the algorithms need anyway between dependent steps.
 #define IWVI_NST 2
@@ -336,6 +347,12 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     for (int i = 0; i < nw; i++) s += red[i];
   }
   return s;
+}
+
+// Fire-and-forget add to global memory (no return value, so the issuing thread does not wait for L2).  Used only where
+// ONE thread owns the address for the whole kernel, so the additions happen in program order: still deterministic.
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 int iwvi_check_gp_desc(const iwvi_gp_desc* d);

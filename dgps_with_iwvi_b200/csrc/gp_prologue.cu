@@ -167,54 +167,105 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             for (int c = 0; c < 2; c++) acc[a][b][c] -= upd[a][b][c];
       }
       if (i == k) {
-        // ---- diagonal block: factorise in shared memory (column-major copy), then invert
+        // ---- diagonal block: factorise with the trailing matrix held in REGISTERS (thread (row, cg) owns the
+        //      entries (row, cg + 4q), q < 16, of the lower triangle), one block barrier per column; then invert by
+        //      recursive doubling (8 -> 16 -> 32 -> 64) with DMMA tile products.
+        __syncthreads();
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
           for (int b = 0; b < 2; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              St[(wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wm0 + a * 8 + g] = acc[a][b][c];
+              S[(wm0 + a * 8 + g) * IWVI_LDS + wn0 + b * 8 + 2 * t + c] = acc[a][b][c];
         __syncthreads();
-        const int row = tid & 63, cg = tid >> 6;
-        for (int j = 0; j < IWVI_BLK; j++) {
-          __syncthreads();   // trailing update of column j-1 is visible
-          const double djj = St[j * IWVI_LDS + j];
-          if (tid == 0 && !(djj > 0.0) && s_info == 0) s_info = k * IWVI_BLK + j + 1;
-          const double piv = sqrt(djj);
-          __syncthreads();
-          if (tid < IWVI_BLK) {
-            if (tid == j) St[j * IWVI_LDS + j] = piv;
-            else if (tid > j) St[j * IWVI_LDS + tid] /= piv;
-          }
-          __syncthreads();
-          const double lij = St[j * IWVI_LDS + row];
-          for (int c = j + 1 + cg; c <= row; c += 4) St[c * IWVI_LDS + row] -= lij * St[j * IWVI_LDS + c];
-        }
-        __syncthreads();
-        // L(k,k) to global (upper part zero) and row-major copy in S
-        for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
-          const int r = idx >> 6, c = idx & 63;
-          const double v = (c <= r) ? St[c * IWVI_LDS + r] : 0.0;
-          S[r * IWVI_LDS + c] = v;
-          Lm[(size_t)(k * IWVI_BLK + r) * Mp + k * IWVI_BLK + c] = v;
-        }
-        __syncthreads();
-        // inverse by forward substitution, one column per thread: Dv[i][c] = (L^-1)[i][c]
-        if (tid < IWVI_BLK) {
-          const int c = tid;
-          for (int i2 = 0; i2 < IWVI_BLK; i2++) {
-            double s0 = 0.0, s1 = 0.0;
-            int j = 0;
-            for (; j + 1 < i2; j += 2) {
-              s0 += S[i2 * IWVI_LDS + j] * Dv[j * IWVI_LDS + c];
-              s1 += S[i2 * IWVI_LDS + j + 1] * Dv[(j + 1) * IWVI_LDS + c];
+        {
+          const int row = tid & 63, cg = tid >> 6;
+          double e[16];
+#pragma unroll
+          for (int q = 0; q < 16; q++) e[q] = S[row * IWVI_LDS + cg + 4 * q];
+          double* colb = St;   // [2][64] column exchange buffer (double buffered: one barrier per step)
+          for (int j = 0; j < IWVI_BLK; j++) {
+            double* col = colb + (j & 1) * IWVI_BLK;
+            const int qj = j >> 2;
+            const bool owner = (cg == (j & 3)) && row >= j;
+            if (owner) {
+              double v = 0.0;
+#pragma unroll
+              for (int q = 0; q < 16; q++) if (q == qj) v = e[q];
+              col[row] = v;
             }
-            if (j < i2) s0 += S[i2 * IWVI_LDS + j] * Dv[j * IWVI_LDS + c];
-            Dv[i2 * IWVI_LDS + c] = (i2 < c) ? 0.0 : ((i2 == c ? 1.0 : 0.0) - (s0 + s1)) / S[i2 * IWVI_LDS + i2];
+            __syncthreads();
+            const double djj = col[j];
+            if (tid == 0 && !(djj > 0.0) && s_info == 0) s_info = k * IWVI_BLK + j + 1;
+            const double inv_d = 1.0 / djj;
+            const double lr = col[row] * inv_d;
+            if (row > j) {
+#pragma unroll
+              for (int q = 0; q < 16; q++) {
+                const int c = cg + 4 * q;
+                if (c > j && c <= row) e[q] -= lr * col[c];
+              }
+            }
+            if (owner) {
+              const double rs = 1.0 / sqrt(djj);
+#pragma unroll
+              for (int q = 0; q < 16; q++) if (q == qj) e[q] *= rs;
+            }
           }
+          __syncthreads();
+          // L(k,k): row-major copy in S (upper part zero) and to global; Dv := 0
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const int c = cg + 4 * q;
+            const double v = (c <= row) ? e[q] : 0.0;
+            S[row * IWVI_LDS + c] = v;
+            Lm[(size_t)(k * IWVI_BLK + row) * Mp + k * IWVI_BLK + c] = v;
+          }
+          for (int idx = tid; idx < IWVI_STAGE_DOUBLES; idx += 256) Dv[idx] = 0.0;
         }
         __syncthreads();
+        // level 0: the eight 8x8 diagonal sub-blocks, one thread per (sub-block, column)
+        if (tid < IWVI_BLK) {
+          const int b0 = (tid >> 3) * 8, c = tid & 7;
+          double x[8];
+#pragma unroll
+          for (int i2 = 0; i2 < 8; i2++) {
+            double s_ = (i2 == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (j < i2) s_ -= S[(b0 + i2) * IWVI_LDS + b0 + j] * x[j];
+            x[i2] = (i2 < c) ? 0.0 : s_ / S[(b0 + i2) * IWVI_LDS + b0 + i2];
+          }
+#pragma unroll
+          for (int i2 = 0; i2 < 8; i2++) Dv[(b0 + i2) * IWVI_LDS + b0 + c] = x[i2];
+        }
+        __syncthreads();
+        // levels 1..3: inv([L11 0; L21 L22]) = [inv11 0; -inv22 L21 inv11, inv22]
+        for (int sz = 8; sz < IWVI_BLK; sz *= 2) {
+          const int tpp = (sz / 8) * (sz / 8);            // 8x8 output tiles per pair
+          const int ntile = (IWVI_BLK / (2 * sz)) * tpp;
+          for (int pass = 0; pass < 2; pass++) {
+            // pass 0: bufA(lower-left) = L21 inv11 ; pass 1: Dv(lower-left) = -inv22 bufA(lower-left)
+            for (int tl = warp; tl < ntile; tl += 8) {
+              const int pr = tl / tpp, rem = tl - pr * tpp;
+              const int ti = rem / (sz / 8), tj = rem - ti * (sz / 8);
+              const int r0 = pr * 2 * sz;
+              const int orow = r0 + sz + ti * 8, ocol = r0 + tj * 8;
+              const double* Am = pass == 0 ? S : Dv;       // rows orow.., k-columns: pass 0: r0.., pass 1: r0+sz..
+              const double* Bm = pass == 0 ? Dv : bufA;    // k-rows: pass 0: r0.., pass 1: r0+sz.. ; columns ocol..
+              const int ak0 = pass == 0 ? r0 : r0 + sz;
+              double c2[2] = {0.0, 0.0};
+              for (int k0 = 0; k0 < sz; k0 += 4)
+                dmma884(c2, Am[(orow + g) * IWVI_LDS + ak0 + k0 + t], Bm[(ak0 + k0 + t) * IWVI_LDS + ocol + g]);
+              double* Cm = pass == 0 ? bufA : Dv;
+              const double sg = pass == 0 ? 1.0 : -1.0;
+              Cm[(orow + g) * IWVI_LDS + ocol + 2 * t] = sg * c2[0];
+              Cm[(orow + g) * IWVI_LDS + ocol + 2 * t + 1] = sg * c2[1];
+            }
+            __syncthreads();
+          }
+        }
         for (int idx = tid; idx < IWVI_STAGE_DOUBLES; idx += 256) {
           const int c = idx % IWVI_LDS;
           Lmb[(size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES + idx] = (c < IWVI_BLK) ? Dv[idx] : 0.0;

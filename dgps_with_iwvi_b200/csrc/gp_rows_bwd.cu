@@ -61,7 +61,7 @@ __host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
   int64_t o = 0;
-  w.off_bbar = o; o += sv.u_stride;            // Bbar, block-major like the saved A
+  w.off_bbar = o; o += sv.u_stride;            // Bbar / 2, block-major like the saved A
   w.off_gmb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_gvb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_epi = o;  o += (int64_t)w.n_epi * EPI_STRIDE;
@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     }
     named_bar_sync(BAR_ALL, 256);
 
-    // ---- Abar, part 1: q_mu gmean_bar^T - 2 A gsum.  The saved A arrives block by block through the ring (the
+    // ---- Abar / 2, part 1: (q_mu gmean_bar^T) / 2 - A gsum.  (The factor 2 of part 2 is exact in binary floating
+    //      point, so the panel carries Abar / 2 until the back substitution writes 2 x its result.)  The saved A arrives block by block through the ring (the
     //      producer warp prefetches it while the previous tile finishes), never through synchronous global loads.
     {
       const int mm = tid & 63;          // this thread's inducing index inside every block; its points: tid/64 + 4*q
@@ -351,10 +352,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         for (int r = 0; r < IWVI_MAX_R; r++) qr[r] = q[r];
         const double* st = pipe.wait();
         for (int n = tid >> 6; n < TP; n += 4) {
-          double v = -2.0 * st[n * IWVI_LDS + mm] * gsum_s[n];
+          double v = 0.0;
 #pragma unroll
           for (int r = 0; r < IWVI_MAX_R; r++) v += qr[r] * gmb_s[r * TP + n];
-          panel[n * ldA + mb * IWVI_BLK + mm] = v;
+          panel[n * ldA + mb * IWVI_BLK + mm] = 0.5 * v - st[n * IWVI_LDS + mm] * gsum_s[n];   // Abar / 2
         }
         pipe.release(lane);
       }
@@ -379,9 +380,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           pipe.release(lane);
         }
         for (int i = j; i < NB; i++) {
-          const double* st = pipe.wait();
+          // the accumulators start from this thread's own panel entries (exclusive owner): no read-modify-write pass
           double acc[C::TM][2][2];
-          acc_zero<C::TM, 2>(acc);
+#pragma unroll
+          for (int a_ = 0; a_ < C::TM; a_++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+              for (int c = 0; c < 2; c++)
+                acc[a_][b][c] = panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a_ * 8 + g];
+          const double* st = pipe.wait();
           const double* ap = st + (wm0 + g) * IWVI_LDS + t;
 #pragma unroll
           for (int ks = 0; ks < 16; ks++) {
@@ -403,33 +411,38 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
               for (int c = 0; c < 2; c++) {
                 const int m = i * IWVI_BLK + wm0 + a_ * 8 + g;
                 const int n = wn0 + b * 8 + 2 * t + c;
-                panel[n * ldA + m] += 2.0 * acc[a_][b][c];
+                panel[n * ldA + m] = acc[a_][b][c];
               }
         }
       }
     }
     named_bar_sync(BAR_ALL, 256);
 
-    // ---- Bbar = Lm^-T Abar, blocked back substitution in place
+    // ---- Bbar / 2 = Lm^-T (Abar / 2), blocked back substitution in place.  The factor 2 is restored where Bbar is
+    //      consumed: the gram adjoint below and the reduce kernel's dLm scale.
     for (int i = NB - 1; i >= 0; i--) {
       double acc[C::TM][C::TN][2];
-      acc_zero<C::TM, C::TN>(acc);
-      for (int j = i + 1; j < NB; j++) {
-        const double* st = pipe.wait();
-        warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
-        pipe.release(lane);
-      }
       if (i < NB - 1) {
+        // acc = -(rhs_i) + sum_{j>i} L(j,i)^T Bbar_j, then rhs_i := -acc
 #pragma unroll
         for (int a = 0; a < C::TM; a++)
 #pragma unroll
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-              const int m = i * IWVI_BLK + wm0 + a * 8 + g;
-              const int n = wn0 + b * 8 + 2 * t + c;
-              panel[n * ldA + m] -= acc[a][b][c];
-            }
+            for (int c = 0; c < 2; c++)
+              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g];
+        for (int j = i + 1; j < NB; j++) {
+          const double* st = pipe.wait();
+          warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+          pipe.release(lane);
+        }
+#pragma unroll
+        for (int a = 0; a < C::TM; a++)
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = -acc[a][b][c];
         named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = pipe.wait();   // inverted diagonal block i, used transposed
@@ -442,19 +455,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
 #pragma unroll
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int m = i * IWVI_BLK + wm0 + a * 8 + g;
-            const int n = wn0 + b * 8 + 2 * t + c;
-            panel[n * ldA + m] = acc[a][b][c];
-          }
+          for (int c = 0; c < 2; c++)
+            panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = acc[a][b][c];
       named_bar_sync(colbar, C::WMG * 32);
     }
 
-    // ---- store Bbar (needed by the reduce kernel for dLm); rows of invalid points are zero by construction
+    // ---- store Bbar / 2 (needed by the reduce kernel for dLm) with asynchronous TMA stores straight from the panel, one
+    //      512-byte run per (point, m-block); rows of invalid points are zero by construction
+    fence_async_smem();
     named_bar_sync(BAR_ALL, 256);
-    for (int idx = tid; idx < TP * Mp; idx += 256) {
-      const int n = idx / Mp, m = idx - n * Mp;
-      bbar_T[iwvi_blk_off(n0 + n, m, NB)] = panel[n * ldA + m];
+    if (warp == 0) {
+      double* dst = bbar_T + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
+      for (int idx = lane; idx < TP * NB; idx += 32) {
+        const int n = idx / NB, mb = idx - n * NB;
+        bulk_s2g(dst + (int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS, panel + n * ldA + mb * IWVI_BLK, IWVI_BLK * 8);
+      }
+      bulk_commit();
+      bulk_wait_read();   // the gram adjoint below overwrites the panel in place
     }
     named_bar_sync(BAR_ALL, 256);
 
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             double K, dK;
             kern_k_dk(d.kern, r2, variance, K, dK);
             const bool valid = (mg < M) && (n0 + n < T);
-            const double bb = panel[n * ldA + mg];
+            const double bb = 2.0 * panel[n * ldA + mg];
             const double G = valid ? bb * dK : 0.0;
             if (valid) dvar_acc += bb * K;
             panel[n * ldA + mg] = G;
@@ -571,7 +588,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             const int dcol = b * 8 + 2 * t + c;
             if (b < nd8 && dcol < D && mg < M) {
               const double zv = st[ml * ldz + dcol];
-              mypart[(size_t)mg * ldz + dcol] += -2.0 * consts[IWVI_C_INVLS + dcol] * (accz[b][c] - zv * grv);
+              red_add(&mypart[(size_t)mg * ldz + dcol], -2.0 * consts[IWVI_C_INVLS + dcol] * (accz[b][c] - zv * grv));
             }
           }
       }
@@ -592,7 +609,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           for (int c = 0; c < 2; c++) {
             const int dcol = b * 8 + 2 * t + c;
             if (b < nd8 && dcol < D)
-              p.dX[pt * D + dcol] += 2.0 * consts[IWVI_C_INVLS + dcol] * (xs[n * ldz + dcol] * gsv - accx[b][c]);
+              red_add(&p.dX[pt * D + dcol], 2.0 * consts[IWVI_C_INVLS + dcol] * (xs[n * ldz + dcol] * gsv - accx[b][c]));
           }
       }
     }
@@ -644,7 +661,7 @@ __device__ __forceinline__ void reduce_loop(RingT<4>& pipe, const ReduceLoopArgs
   auto load_scales = [&](int c, double (&s_)[16]) {
     const size_t pt0 = (size_t)c * IWVI_BLK + t;
 #pragma unroll
-    for (int ks = 0; ks < 16; ks++) s_[ks] = la.is_lm ? -1.0 : 2.0 * __ldg(la.gvb + (pt0 + 4 * ks) * IWVI_MAX_R + la.q);
+    for (int ks = 0; ks < 16; ks++) s_[ks] = la.is_lm ? -2.0 : 2.0 * __ldg(la.gvb + (pt0 + 4 * ks) * IWVI_MAX_R + la.q);
   };
   load_scales(la.c0, sc);
   for (int c = la.c0; c < la.c1; c++) {

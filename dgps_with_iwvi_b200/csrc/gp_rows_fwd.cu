@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
-    named_bar_sync(BAR_ALL, 256);  // previous tile fully done with every shared buffer
+    if (warp == 0) bulk_wait_read();   // the previous tile's bulk stores no longer read the panel
+    named_bar_sync(BAR_ALL, 256);      // previous tile fully done with every shared buffer
 
     // ---- x tile: xs[n][k] = X[n0+n][k] / ls[k] (zero padded), xn[n] = |xs[n]|^2
     for (int idx = tid; idx < TP * ldz; idx += 256) {
@@ -176,7 +177,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     for (int i = 0; i < NB; i++) {
       double acc[C::TM][C::TN][2];
       if (i > 0) {
-        acc_zero<C::TM, C::TN>(acc);
+        // acc = -(Kuf_i) + sum_{j<i} Lm(i,j) A_j, then rhs_i := -acc (each thread owns its entries: no read-modify-write)
+#pragma unroll
+        for (int a = 0; a < C::TM; a++)
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g];
         for (int j = 0; j < i; j++) {
           const double* st = ring.wait();
           warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA,
@@ -188,11 +196,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
 #pragma unroll
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-              const int m = i * IWVI_BLK + wm0 + a * 8 + g;
-              const int n = wn0 + b * 8 + 2 * t + c;
-              panel[n * ldA + m] -= acc[a][b][c];
-            }
+            for (int c = 0; c < 2; c++)
+              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = -acc[a][b][c];
         named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = ring.wait();   // inverted diagonal block
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
           }
       named_bar_sync(colbar, C::WMG * 32);
     }
+    fence_async_smem();   // the panel (A) is read by bulk stores below
     named_bar_sync(BAR_ALL, 256);
 
     // ---- S: fvar0 = sum_m A^2 and the latent means gmean = A^T q_mu, as one skinny DMMA product per 8 points
@@ -238,16 +244,35 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
       gms[(2 * t + 1) * TP + mt * 8 + g] = c0[1] + c1[1];
     }
     if (do_save) {
-      const int nvalid = min(TP, T - n0);       // real points of this tile
-      const int nrows = min(TP, sv.Tp - n0);    // points of the padded array this tile owns (pad points := 0)
-      double* dst = p.save + sv.off_a;
-      for (int idx = tid; idx < nrows * Mp; idx += 256) {
-        const int n = idx / Mp, m = idx - n * Mp;
-        dst[iwvi_blk_off(n0 + n, m, NB)] = (n < nvalid) ? panel[n * ldA + m] : 0.0;
+      const int nvalid = min(TP, T - n0);       // real points of this tile (pad points are saved as zeros)
+      double* dst = p.save + sv.off_a + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
+      if (nvalid == TP) {
+        // asynchronous TMA stores straight from the panel: one 512-byte run per (point, m-block)
+        if (warp == 0) {
+          for (int idx = lane; idx < TP * NB; idx += 32) {
+            const int n = idx / NB, mb = idx - n * NB;
+            bulk_s2g(dst + (int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS, panel + n * ldA + mb * IWVI_BLK, IWVI_BLK * 8);
+          }
+          bulk_commit();
+        }
+      } else {
+        const int mm = tid & 63;
+        for (int mb = 0; mb < NB; mb++)
+          for (int n = tid >> 6; n < TP; n += 4)
+            dst[(int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS + mm] = (n < nvalid) ? panel[n * ldA + mb * IWVI_BLK + mm] : 0.0;
       }
     }
 
     // ---- U: triangular products with tril(q_sqrt_r)^T, column sums of squares (no inter-warp data flow)
+    // this thread's corner of every saved U block of the tile (block-major [point][68]); pad points are saved as zeros
+    double* ubase = p.save + sv.off_u + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES +
+                    (int64_t)((n0 & 63) + wn0 + 2 * t) * IWVI_LDS + wm0 + g;
+    unsigned pad_mask = 0;
+#pragma unroll
+    for (int b = 0; b < C::TN; b++)
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+        if (n0 + wn0 + b * 8 + 2 * t + c >= T) pad_mask |= 1u << (b * 2 + c);
     for (int r = 0; r < R; r++) {
       double csq[C::TN][2];
 #pragma unroll
@@ -255,6 +280,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
       for (int i = 0; i < NB; i++) {
         double acc[C::TM][C::TN][2];
         acc_zero<C::TM, C::TN>(acc);
+        double* ub = ubase + (int64_t)r * sv.u_stride + (int64_t)i * IWVI_STAGE_DOUBLES;
         for (int j = i; j < NB; j++) {
           const double* st = ring.wait();
           warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
@@ -268,11 +294,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
             for (int c = 0; c < 2; c++) {
               const double u = acc[a][b][c];
               csq[b][c] += u * u;
-              if (do_save) {
-                const int m = i * IWVI_BLK + wm0 + a * 8 + g;
-                const int n = wn0 + b * 8 + 2 * t + c;
-                if (n0 + n < sv.Tp) p.save[sv.off_u + r * sv.u_stride + iwvi_blk_off(n0 + n, m, NB)] = (n0 + n < T) ? u : 0.0;
-              }
+              if (do_save) ub[(b * 8 + c) * IWVI_LDS + a * 8] = ((pad_mask >> (b * 2 + c)) & 1u) ? 0.0 : u;
             }
       }
 #pragma unroll
@@ -330,6 +352,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
       }
     }
   }
+  if (warp == 0) bulk_wait_read();   // shared memory must outlive the last tile's bulk stores
 }
 
 template <int TP>
