@@ -82,11 +82,12 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// acc[TM][TN][2] += A(m,k) * B(k,n),  m in [0, 8*TM), n in [0, 8*TN), k in [0, KC), KC % 4 == 0.
+// acc[TM][TN][2] += A(m,k) * B(k,n),  n in [0, 8*TN), k in [0, KC), KC % 4 == 0; the warp's TM row tiles of 8 rows are
+// MS tiles apart: tile i covers rows 8*MS*i .. 8*MS*i + 7 relative to As (MS == 1: TM*8 consecutive rows).
 //   ALAY == 0: A(m,k) = As[m*lda + k]      ALAY == 1: A(m,k) = As[k*lda + m]
 //   BLAY == 0: B(k,n) = Bs[n*ldb + k]      BLAY == 1: B(k,n) = Bs[k*ldb + n]
-// accumulator element acc[i][j][c] is C(8*i + lane/4, 8*j + 2*(lane%4) + c).
-template <int TM, int TN, int ALAY, int BLAY>
+// accumulator element acc[i][j][c] is C(8*MS*i + lane/4, 8*j + 2*(lane%4) + c).
+template <int TM, int TN, int ALAY, int BLAY, int MS = 1>
 __device__ __forceinline__ void warp_gemm(double (&acc)[TM][TN][2], const double* __restrict__ As, int lda,
                                           const double* __restrict__ Bs, int ldb, int KC, int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -96,13 +97,47 @@ __device__ __forceinline__ void warp_gemm(double (&acc)[TM][TN][2], const double
   for (int k0 = 0; k0 < KC; k0 += 4) {
     double a[TM], b[TN];
 #pragma unroll
-    for (int i = 0; i < TM; i++) a[i] = ALAY == 0 ? ap[i * 8 * lda + k0] : ap[k0 * lda + i * 8];
+    for (int i = 0; i < TM; i++) a[i] = ALAY == 0 ? ap[i * 8 * MS * lda + k0] : ap[k0 * lda + i * 8 * MS];
 #pragma unroll
     for (int j = 0; j < TN; j++) b[j] = BLAY == 0 ? bp[j * 8 * ldb + k0] : bp[k0 * ldb + j * 8];
 #pragma unroll
     for (int i = 0; i < TM; i++)
 #pragma unroll
       for (int j = 0; j < TN; j++) dmma884(acc[i][j], a[i], b[j]);
+  }
+}
+
+// The same product for a TRIANGULAR 64x64 A block whose structural zeros are skipped at the granularity of the 8x8x4
+// DMMA: Ablk is the block's (0,0) corner, the warp's row tiles are mt0, mt0 + MS, ... (units of 8 rows).  The k range
+// is cut into segments inside which the set of active row tiles is a compile-time constant, so no DMMA is ever issued
+// under a predicate (a predicated-off DMMA still occupies the FP64 pipe).
+//   LOWER == 1: A(m,k) != 0 only for k <= m  -> row tile ti needs k in [0, 8*(ti+1))
+//   LOWER == 0: A(m,k) != 0 only for k >= m  -> row tile ti needs k in [8*ti, 64)
+template <int TM, int TN, int ALAY, int BLAY, int MS, int LOWER>
+__device__ __forceinline__ void warp_gemm_tri(double (&acc)[TM][TN][2], const double* __restrict__ Ablk, int lda,
+                                              const double* __restrict__ Bs, int ldb, int mt0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const double* ap = ALAY == 0 ? Ablk + (mt0 * 8 + g) * lda + t : Ablk + t * lda + mt0 * 8 + g;
+  const double* bp = BLAY == 0 ? Bs + g * ldb + t : Bs + t * ldb + g;
+#pragma unroll
+  for (int s = 0; s < TM; s++) {
+    const int k_lo = LOWER ? (s == 0 ? 0 : 8 * (mt0 + MS * (s - 1) + 1)) : 8 * (mt0 + MS * s);
+    const int k_hi = LOWER ? 8 * (mt0 + MS * s + 1) : (s == TM - 1 ? IWVI_BLK : 8 * (mt0 + MS * (s + 1)));
+#pragma unroll 2
+    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
+      double a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+        if (LOWER ? i >= s : i <= s) a[i] = ALAY == 0 ? ap[i * 8 * MS * lda + k0] : ap[k0 * lda + i * 8 * MS];
+#pragma unroll
+      for (int j = 0; j < TN; j++) b[j] = BLAY == 0 ? bp[j * 8 * ldb + k0] : bp[k0 * ldb + j * 8];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+        if (LOWER ? i >= s : i <= s) {
+#pragma unroll
+          for (int j = 0; j < TN; j++) dmma884(acc[i][j], a[i], b[j]);
+        }
+    }
   }
 }
 

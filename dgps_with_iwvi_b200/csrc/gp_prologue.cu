@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
 #pragma unroll
           for (int q = 0; q < 16; q++) e[q] = S[row * IWVI_LDS + cg + 4 * q];
           double* colb = St;   // [2][64] column exchange buffer (double buffered: one barrier per step)
-          for (int j = 0; j < IWVI_BLK; j++) {
+#pragma unroll
+          for (int j = 0; j < IWVI_BLK; j++) {   // fully unrolled: the owner's register index j >> 2 is a constant
             double* col = colb + (j & 1) * IWVI_BLK;
             const int qj = j >> 2;
             const bool owner = (cg == (j & 3)) && row >= j;
@@ -198,8 +199,8 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             __syncthreads();
             const double djj = col[j];
             if (tid == 0 && !(djj > 0.0) && s_info == 0) s_info = k * IWVI_BLK + j + 1;
-            const double inv_d = 1.0 / djj;
-            const double lr = col[row] * inv_d;
+            const double rs = rsqrt(djj);          // one reciprocal square root serves the update and the scaling
+            const double lr = col[row] * (rs * rs);
             if (row > j) {
 #pragma unroll
               for (int q = 0; q < 16; q++) {
@@ -208,7 +209,6 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
               }
             }
             if (owner) {
-              const double rs = 1.0 / sqrt(djj);
 #pragma unroll
               for (int q = 0; q < 16; q++) if (q == qj) e[q] *= rs;
             }
@@ -524,39 +524,45 @@ __global__ void __launch_bounds__(256) pbwd_gram_kernel(const PbwdParams p) {
       }
     }
   }
-  // KL adjoint
+}
+
+// KL adjoint (whitened gauss_kl): dq_mu = dkl q_mu, dLq = dkl (Lq - diag(1/diag Lq)) on the lower triangle
+__global__ void __launch_bounds__(256) pbwd_kl_kernel(const PbwdParams p) {
+  const int M = p.d.M, R = p.d.R;
   const double dkl = p.dkl[0];
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = gtid; e < (int64_t)R * M * M; e += gsz) {
-    const int64_t rem = e % ((int64_t)M * M);
-    const int a = (int)(rem / M), b = (int)(rem - (int64_t)a * M);
-    double v = 0.0;
-    if (b <= a) {
-      const double q = p.q_sqrt[e];
-      v = dkl * (a == b ? q - 1.0 / q : q);
+  const int n_sq = R * M * M, n_all = n_sq + M * R;      // R M^2 <= 8 * 512^2 fits an int
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < n_all; e += gridDim.x * 256) {
+    if (e < n_sq) {
+      const int rem = e % (M * M);
+      const int a = rem / M, b = rem - a * M;
+      double v = 0.0;
+      if (b <= a) {
+        const double q = p.q_sqrt[e];
+        v = dkl * (a == b ? q - 1.0 / q : q);
+      }
+      if (p.accumulate) p.dq_sqrt[e] += v; else p.dq_sqrt[e] = v;
+    } else {
+      const int e2 = e - n_sq;
+      const double v = dkl * p.q_mu[e2];
+      if (p.accumulate) p.dq_mu[e2] += v; else p.dq_mu[e2] = v;
     }
-    if (p.accumulate) p.dq_sqrt[e] += v; else p.dq_sqrt[e] = v;
-  }
-  for (int64_t e = gtid; e < (int64_t)M * R; e += gsz) {
-    const double v = dkl * p.q_mu[e];
-    if (p.accumulate) p.dq_mu[e] += v; else p.dq_mu[e] = v;
   }
 }
 
-__global__ void pbwd_final_kernel(const PbwdParams p) {
+// fixed-order sums of the per-row partials of dls and dvariance, one warp per output
+__global__ void __launch_bounds__(32) pbwd_final_kernel(const PbwdParams p) {
   const AuxLayout al = iwvi_aux_layout(p.d.M, p.d.D, p.d.R);
   const PbwdWs wl = pbwd_ws_layout(al.Mp);
-  const int k = threadIdx.x;
+  const int k = blockIdx.x, lane = threadIdx.x;
+  double s = 0.0;
   if (k < p.d.D) {
-    double s = 0.0;
-    for (int i = 0; i < p.d.M; i++) s += p.ws[wl.off_dls + (size_t)i * 32 + k];
-    if (p.accumulate) p.dls[k] += s; else p.dls[k] = s;
-  } else if (k == 32) {
-    double s = 0.0;
-    for (int i = 0; i < p.d.M; i++) s += p.ws[wl.off_dvar + i];
-    s /= p.aux[al.off_consts + IWVI_C_VARIANCE];
-    if (p.accumulate) p.dvariance[0] += s; else p.dvariance[0] = s;
+    for (int i = lane; i < p.d.M; i += 32) s += p.ws[wl.off_dls + (size_t)i * 32 + k];
+    s = warp_sum(s);
+    if (lane == 0) { if (p.accumulate) p.dls[k] += s; else p.dls[k] = s; }
+  } else {
+    for (int i = lane; i < p.d.M; i += 32) s += p.ws[wl.off_dvar + i];
+    s = warp_sum(s) / p.aux[al.off_consts + IWVI_C_VARIANCE];
+    if (lane == 0) { if (p.accumulate) p.dvariance[0] += s; else p.dvariance[0] = s; }
   }
 }
 
@@ -665,7 +671,14 @@ extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, con
   IWVI_CHECK_LAUNCH();
   pbwd_gram_kernel<<<(al.Mp + 7) / 8, 256, 0, st>>>(p);
   IWVI_CHECK_LAUNCH();
-  pbwd_final_kernel<<<1, 64, 0, st>>>(p);
+  {
+    const int n_all = d->R * d->M * d->M + d->M * d->R;
+    int grid = (n_all + 1023) / 1024;
+    if (grid > 592) grid = 592;
+    pbwd_kl_kernel<<<grid, 256, 0, st>>>(p);
+    IWVI_CHECK_LAUNCH();
+  }
+  pbwd_final_kernel<<<d->D + 1, 32, 0, st>>>(p);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }

@@ -27,7 +27,7 @@ template <int TP> struct TileCfg {
 };
 
 #define EPI_STRIDE 1344   // >= P*R + D*P + P + 1 at the maxima (32*8 + 32*32 + 32 + 1 = 1313)
-#define EPI_PTS 256
+#define EPI_PTS 32
 #define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
 #define TILE_THREADS 288    // 8 consumer warps + 1 producer warp
 #define BAR_ALL 1
@@ -83,7 +83,11 @@ struct BwdParams {
 // ------------------------------------------------------------------------------------------------
 // 1. per-point epilogue adjoint
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EPI_PTS) gp_epi_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
+  // One CTA per EPI_PTS = 32 points.  The cotangent tiles are loaded coalesced into shared memory; thread (point, r)
+  // un-mixes them, thread (point, k) forms the mean-function part of dX, and (only for trainable W / mean function)
+  // each thread sums one entry of dW / dmfA / dmfb over the CTA's points.
+  __shared__ double ds[EPI_PTS][IWVI_MAX_P + 1], dm[EPI_PTS][IWVI_MAX_P + 1], dv[EPI_PTS][IWVI_MAX_P + 1];
   __shared__ double red[32];
   const iwvi_gp_desc& d = p.d;
   const int T = d.T, R = d.R, P = d.P, D = d.D;
@@ -93,91 +97,80 @@ __global__ void __launch_bounds__(EPI_PTS) gp_epi_bwd_kernel(const BwdParams p) 
   const double* gmean = p.save + sv.off_gmean;
   double* gmb = p.ws + p.wl.off_gmb;
   double* gvb = p.ws + p.wl.off_gvb;
+  const int tid = threadIdx.x;
   const int p0 = blockIdx.x * EPI_PTS;
-  const int pt = p0 + threadIdx.x;
+  const int npts = max(0, min(EPI_PTS, T - p0));     // real points of this CTA (the rest are zero padding)
+  for (int idx = tid; idx < EPI_PTS * P; idx += 256) {
+    const int n = idx / P, q = idx - n * P;
+    const bool ok = n < npts;
+    const size_t g_ = (size_t)p0 * P + idx;
+    ds[n][q] = (ok && p.d_sample) ? p.d_sample[g_] : 0.0;
+    dm[n][q] = (ok && p.d_mean) ? p.d_mean[g_] : 0.0;
+    dv[n][q] = (ok && p.d_var) ? p.d_var[g_] : 0.0;
+  }
+  __syncthreads();
   double gv_sum = 0.0;
-  if (pt < p.wl.Tp) {
-    double om[IWVI_MAX_R], ov[IWVI_MAX_R];
-#pragma unroll
-    for (int r = 0; r < IWVI_MAX_R; r++) { om[r] = 0.0; ov[r] = 0.0; }
-    if (pt < T) {
-      for (int r = 0; r < R; r++) {
-        double gsb = 0.0, gm_ = 0.0, gv_ = 0.0;
-        if (d.mix) {
-          for (int q = 0; q < P; q++) {
-            const double w = p.W[q * R + r];
-            const double s_ = p.d_sample ? p.d_sample[(size_t)pt * P + q] : 0.0;
-            const double m_ = p.d_mean ? p.d_mean[(size_t)pt * P + q] : 0.0;
-            const double v_ = p.d_var ? p.d_var[(size_t)pt * P + q] : 0.0;
-            gsb += s_ * w; gm_ += m_ * w; gv_ += v_ * w * w;
-          }
-        } else {
-          gsb = p.d_sample ? p.d_sample[(size_t)pt * P + r] : 0.0;
-          gm_ = p.d_mean ? p.d_mean[(size_t)pt * P + r] : 0.0;
-          gv_ = p.d_var ? p.d_var[(size_t)pt * P + r] : 0.0;
+  {
+    const int n = tid >> 3, r = tid & 7;
+    const size_t pt = (size_t)p0 + n;
+    double gm_ = 0.0, gv_ = 0.0;
+    if (n < npts && r < R) {
+      double gsb = 0.0;
+      if (d.mix) {
+        for (int q = 0; q < P; q++) {
+          const double w = p.W[q * R + r];
+          gsb += ds[n][q] * w; gm_ += dm[n][q] * w; gv_ += dv[n][q] * w * w;
         }
-        gm_ += gsb;
-        if (sampled) gv_ += gsb * p.eps[(size_t)pt * R + r] / (2.0 * sqrt(gvar[(size_t)pt * R + r]));
-        om[r] = gm_; ov[r] = gv_; gv_sum += gv_;
+      } else {
+        gsb = ds[n][r]; gm_ = dm[n][r]; gv_ = dv[n][r];
       }
-      // mean-function part of dX (the gram part is added by the tile kernel)
-      for (int k = 0; k < D; k++) {
-        double v = 0.0;
-        if (d.mf == IWVI_MF_IDENTITY) {
-          v = (p.d_sample ? p.d_sample[(size_t)pt * P + k] : 0.0) + (p.d_mean ? p.d_mean[(size_t)pt * P + k] : 0.0);
-        } else if (d.mf == IWVI_MF_LINEAR) {
-          for (int q = 0; q < P; q++) {
-            const double dmf = (p.d_sample ? p.d_sample[(size_t)pt * P + q] : 0.0) +
-                               (p.d_mean ? p.d_mean[(size_t)pt * P + q] : 0.0);
-            v += dmf * p.mfA[k * P + q];
-          }
-        }
-        p.dX[(size_t)pt * D + k] = v;
-      }
+      gm_ += gsb;
+      if (sampled) gv_ += gsb * p.eps[pt * R + r] / (2.0 * sqrt(gvar[pt * R + r]));
+      gv_sum = gv_;
     }
-#pragma unroll
-    for (int r = 0; r < IWVI_MAX_R; r++) {
-      gmb[(size_t)pt * IWVI_MAX_R + r] = om[r];
-      gvb[(size_t)pt * IWVI_MAX_R + r] = ov[r];
+    if (pt < (size_t)p.wl.Tp) {
+      gmb[pt * IWVI_MAX_R + r] = gm_;
+      gvb[pt * IWVI_MAX_R + r] = gv_;
     }
+  }
+  // mean-function part of dX (the gram part is added by the tile kernel)
+  for (int idx = tid; idx < npts * D; idx += 256) {
+    const int n = idx / D, k = idx - n * D;
+    double v = 0.0;
+    if (d.mf == IWVI_MF_IDENTITY) v = ds[n][k] + dm[n][k];
+    else if (d.mf == IWVI_MF_LINEAR)
+      for (int q = 0; q < P; q++) v += (ds[n][q] + dm[n][q]) * p.mfA[k * P + q];
+    p.dX[(size_t)p0 * D + idx] = v;
   }
   double* part = p.ws + p.wl.off_epi + (size_t)blockIdx.x * EPI_STRIDE;
   const double tot = block_sum(gv_sum, red);
-  if (threadIdx.x == 0) part[P * R + D * P + P] = tot;
-  // partial sums over this block's points of dW, dmfA, dmfb
-  const int p1 = min(p0 + EPI_PTS, T);
+  if (tid == 0) part[P * R + D * P + P] = tot;
+  // partial sums over this CTA's points of dW, dmfA, dmfb
   const int nW = (d.mix && p.dW) ? P * R : 0;
   const int nA = (d.mf == IWVI_MF_LINEAR && p.dmfA) ? D * P : 0;
   const int nb = (d.mf == IWVI_MF_LINEAR && p.dmfb) ? P : 0;
-  for (int e = threadIdx.x; e < P * R + D * P + P; e += blockDim.x) {
+  for (int e = tid; e < P * R + D * P + P; e += 256) {
     double s = 0.0;
     if (e < P * R) {
       if (nW) {
         const int q = e / R, r = e - q * R;
         const double w = p.W[q * R + r];
-        for (int n = p0; n < p1; n++) {
-          const double gvv = gvar[(size_t)n * R + r], gmm = gmean[(size_t)n * R + r];
-          const double s_ = p.d_sample ? p.d_sample[(size_t)n * P + q] : 0.0;
-          const double m_ = p.d_mean ? p.d_mean[(size_t)n * P + q] : 0.0;
-          const double v_ = p.d_var ? p.d_var[(size_t)n * P + q] : 0.0;
-          const double gss = sampled ? gmm + p.eps[(size_t)n * R + r] * sqrt(gvv) : 0.0;
-          s += s_ * gss + m_ * gmm + 2.0 * v_ * w * gvv;
+        for (int n = 0; n < npts; n++) {
+          const size_t pt = (size_t)p0 + n;
+          const double gvv = gvar[pt * R + r], gmm = gmean[pt * R + r];
+          const double gss = sampled ? gmm + p.eps[pt * R + r] * sqrt(gvv) : 0.0;
+          s += ds[n][q] * gss + dm[n][q] * gmm + 2.0 * dv[n][q] * w * gvv;
         }
       }
     } else if (e < P * R + D * P) {
       if (nA) {
         const int e2 = e - P * R;
         const int k = e2 / P, q = e2 - k * P;
-        for (int n = p0; n < p1; n++) {
-          const double dmf = (p.d_sample ? p.d_sample[(size_t)n * P + q] : 0.0) +
-                             (p.d_mean ? p.d_mean[(size_t)n * P + q] : 0.0);
-          s += p.X[(size_t)n * D + k] * dmf;
-        }
+        for (int n = 0; n < npts; n++) s += p.X[((size_t)p0 + n) * D + k] * (ds[n][q] + dm[n][q]);
       }
     } else if (nb) {
       const int q = e - P * R - D * P;
-      for (int n = p0; n < p1; n++)
-        s += (p.d_sample ? p.d_sample[(size_t)n * P + q] : 0.0) + (p.d_mean ? p.d_mean[(size_t)n * P + q] : 0.0);
+      for (int n = 0; n < npts; n++) s += ds[n][q] + dm[n][q];
     }
     part[e] = s;
   }
@@ -228,6 +221,27 @@ struct BwdSeq {
     }
   }
 };
+
+// acc += Lq_block * V for one streamed 64x64 block of tril(q_sqrt_r) (row-major, A operand) and the register-resident
+// V fragments of this warp's 16 points.  DIAG: the block is lower triangular; row tile ti = WMI + WMG * a only needs
+// k < 8 (ti + 1), and because WMI is a template parameter the skipped DMMAs vanish at compile time.
+template <int TM, int WMG, int WMI, bool DIAG>
+__device__ __forceinline__ void lq_v_product(double (&acc)[TM][2][2], const double* __restrict__ ap,
+                                             const double (&vb)[16][2]) {
+#pragma unroll
+  for (int ks = 0; ks < 16; ks++) {
+    double a[TM];
+#pragma unroll
+    for (int a_ = 0; a_ < TM; a_++)
+      if (!DIAG || ks < 2 * (WMI + WMG * a_ + 1)) a[a_] = ap[a_ * 8 * WMG * IWVI_LDS + ks * 4];
+#pragma unroll
+    for (int a_ = 0; a_ < TM; a_++)
+      if (!DIAG || ks < 2 * (WMI + WMG * a_ + 1)) {
+        dmma884(acc[a_][0], a[a_], vb[ks][0]);
+        dmma884(acc[a_][1], a[a_], vb[ks][1]);
+      }
+  }
+}
 
 struct TileSmem { int panel, stages, xs, xn, gmb, gvb, gsum, gs, gr, dls, red, bars, total_doubles; };
 __host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
@@ -291,7 +305,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   }
 
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp % C::WMG) * C::WM;
+  // row tiles of a 64-row block dealt round-robin to the warps of a column group, order flipped in warps 4-7 (see
+  // gp_rows_fwd.cu): balances the work skipped in triangular diagonal blocks across warps and SM sub-partitions
+  const int wmi = ((warp >> 2) & 1) ? (C::WMG - 1 - warp % C::WMG) : (warp % C::WMG);
+  const int wr0 = wmi * 8;
+  constexpr int MR = 8 * C::WMG;
   const int wn0 = (warp / C::WMG) * C::WN;
   const int colbar = BAR_COL + warp / C::WMG;
 
@@ -388,19 +406,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             for (int b = 0; b < 2; b++)
 #pragma unroll
               for (int c = 0; c < 2; c++)
-                acc[a_][b][c] = panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a_ * 8 + g];
+                acc[a_][b][c] = panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a_ * MR + g];
           const double* st = pipe.wait();
-          const double* ap = st + (wm0 + g) * IWVI_LDS + t;
-#pragma unroll
-          for (int ks = 0; ks < 16; ks++) {
-            double a[C::TM];
-#pragma unroll
-            for (int a_ = 0; a_ < C::TM; a_++) a[a_] = ap[a_ * 8 * IWVI_LDS + ks * 4];
-#pragma unroll
-            for (int a_ = 0; a_ < C::TM; a_++) {
-              dmma884(acc[a_][0], a[a_], vb[ks][0]);
-              dmma884(acc[a_][1], a[a_], vb[ks][1]);
+          const double* ap = st + (wr0 + g) * IWVI_LDS + t;
+          if (i == j) {   // diagonal block of tril(q_sqrt_r): the structural zeros are skipped (compile-time pattern per wmi)
+            if (C::WMG == 2) {
+              if (wmi == 0) lq_v_product<C::TM, C::WMG, 0, true>(acc, ap, vb);
+              else lq_v_product<C::TM, C::WMG, 1, true>(acc, ap, vb);
+            } else {
+              if (wmi == 0) lq_v_product<C::TM, C::WMG, 0, true>(acc, ap, vb);
+              else if (wmi == 1) lq_v_product<C::TM, C::WMG, 1, true>(acc, ap, vb);
+              else if (wmi == 2) lq_v_product<C::TM, C::WMG, 2, true>(acc, ap, vb);
+              else lq_v_product<C::TM, C::WMG, 3, true>(acc, ap, vb);
             }
+          } else {
+            lq_v_product<C::TM, C::WMG, 0, false>(acc, ap, vb);
           }
           pipe.release(lane);
 #pragma unroll
@@ -409,7 +429,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             for (int b = 0; b < 2; b++)
 #pragma unroll
               for (int c = 0; c < 2; c++) {
-                const int m = i * IWVI_BLK + wm0 + a_ * 8 + g;
+                const int m = i * IWVI_BLK + wr0 + a_ * MR + g;
                 const int n = wn0 + b * 8 + 2 * t + c;
                 panel[n * ldA + m] = acc[a_][b][c];
               }
@@ -430,10 +450,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g];
+              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g];
         for (int j = i + 1; j < NB; j++) {
           const double* st = pipe.wait();
-          warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+          warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
           pipe.release(lane);
         }
 #pragma unroll
@@ -442,12 +462,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = -acc[a][b][c];
+              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g] = -acc[a][b][c];
         named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = pipe.wait();   // inverted diagonal block i, used transposed
       acc_zero<C::TM, C::TN>(acc);
-      warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, IWVI_BLK, lane);
+      warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, wmi, lane);
       pipe.release(lane);
       named_bar_sync(colbar, C::WMG * 32);   // every warp of the column group has read the right-hand side
 #pragma unroll
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++)
-            panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = acc[a][b][c];
+            panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g] = acc[a][b][c];
       named_bar_sync(colbar, C::WMG * 32);
     }
 
@@ -483,7 +503,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
       const double* st = pipe.wait();   // scaled inducing inputs of block i: st[m*ldz + k]
       double acc[C::TM][C::TN][2];
       acc_zero<C::TM, C::TN>(acc);
-      warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
+      warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
       double cs[C::TN][2];
 #pragma unroll
       for (int b = 0; b < C::TN; b++) { cs[b][0] = 0.0; cs[b][1] = 0.0; }
@@ -494,7 +514,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++) {
-            const int ml = wm0 + a * 8 + g;
+            const int ml = wr0 + a * MR + g;
             const int mg = i * IWVI_BLK + ml;
             const int n = wn0 + b * 8 + 2 * t + c;
             const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
@@ -511,7 +531,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           }
         rs += __shfl_xor_sync(0xffffffffu, rs, 1);
         rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-        if (t == 0) gr_s[((i & 1) * C::WNG + warp / C::WMG) * IWVI_BLK + wm0 + a * 8 + g] = rs;
+        if (t == 0) gr_s[((i & 1) * C::WNG + warp / C::WMG) * IWVI_BLK + wr0 + a * MR + g] = rs;
       }
 #pragma unroll
       for (int b = 0; b < C::TN; b++)
@@ -528,7 +548,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         double s = 0.0;
 #pragma unroll
         for (int a = 0; a < C::TM; a++) {
-          const double zv = st[(wm0 + a * 8 + g) * ldz + dd];
+          const double zv = st[(wr0 + a * MR + g) * ldz + dd];
 #pragma unroll
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
@@ -773,72 +793,110 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
 // ------------------------------------------------------------------------------------------------
 // 4. fixed-order sums of the partials
 // ------------------------------------------------------------------------------------------------
-__global__ void gp_finalize_bwd_kernel(const BwdParams p) {
+// fixed-order sum of `count` partials `src[i * stride]` by one warp: lane l adds partials l, l+32, ... in order, then a
+// fixed shuffle tree combines the lanes
+__device__ __forceinline__ double warp_partial_sum(const double* src, int count, size_t stride, int lane) {
+  double s = 0.0;
+  for (int i = lane; i < count; i += 32) s += src[(size_t)i * stride];
+  return warp_sum(s);
+}
+
+struct FinalLayout { int64_t n_blk, n_up, n_qmu, n_elem; int n_z, n_small, n_warp_out; int grid_elem, grid_warp; };
+__host__ __device__ inline FinalLayout final_layout(const iwvi_gp_desc& d, const BwdWs& wl) {
+  FinalLayout f;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  f.n_blk = (int64_t)(d.R + 1) * wl.npairs * IWVI_BLK * IWVI_BLK;                   // lower blocks of dLq_r, dLm
+  f.n_up = (int64_t)(d.R + 1) * (al.NB * (al.NB - 1) / 2) * IWVI_BLK * IWVI_BLK;    // blocks above the diagonal: zeros
+  f.n_qmu = (int64_t)d.M * d.R;
+  f.n_elem = f.n_blk + f.n_up + f.n_qmu;
+  f.n_z = d.M * d.D;
+  f.n_small = d.D + 1 + d.P * d.R + d.D * d.P + d.P;
+  f.n_warp_out = f.n_z + f.n_small;
+  f.grid_elem = (int)((f.n_elem + 255) / 256);
+  f.grid_warp = (f.n_warp_out + 7) / 8;
+  return f;
+}
+
+__global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p) {
   const iwvi_gp_desc& d = p.d;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const BwdWs& wl = p.wl;
   const int M = d.M, Mp = al.Mp, R = d.R, D = d.D, P = d.P, NB = al.NB, ldz = al.ldz;
-  const int64_t n_lq = (int64_t)R * M * M, n_lm = (int64_t)Mp * Mp, n_qmu = (int64_t)M * R, n_z = (int64_t)M * D;
-  const int64_t n_small = D + 1 + P * R + D * P + P;
-  const int64_t total = n_lq + n_lm + n_qmu + n_z + n_small;
+  const FinalLayout f = final_layout(d, wl);
   const double* red = p.ws + wl.off_red;
   const double* qred = p.ws + wl.off_qred;
   const double* tile = p.ws + wl.off_tile;
   const double* epi = p.ws + wl.off_epi;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t k = e;
-    if (k < n_lq + n_lm) {
-      int q, a, b;
-      double* dst;
-      if (k < n_lq) { q = (int)(k / ((int64_t)M * M)); const int64_t rem = k - (int64_t)q * M * M; a = (int)(rem / M); b = (int)(rem - (int64_t)a * M); dst = p.dq_sqrt + k; }
-      else { k -= n_lq; q = R; a = (int)(k / Mp); b = (int)(k - (int64_t)a * Mp); dst = p.dLm + k; }
+  const int BB = IWVI_BLK * IWVI_BLK;
+  if ((int)blockIdx.x < f.grid_elem) {
+    // ---- one thread per output element: split-K partials of the reduce kernel
+    int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e < f.n_blk) {
+      const int off = (int)(e % BB);
+      const int64_t e2 = e / BB;
+      const int pair = (int)(e2 % wl.npairs), q = (int)(e2 / wl.npairs);
+      int bi = 0;
+      while ((bi + 1) * (bi + 2) / 2 <= pair) bi++;
+      const int bj = pair - bi * (bi + 1) / 2;
+      const int a = bi * IWVI_BLK + (off >> 6), b = bj * IWVI_BLK + (off & 63);
       double s = 0.0;
-      if (a >= b) {
-        const int bi = a / IWVI_BLK, bj = b / IWVI_BLK;
-        const int pair = bi * (bi + 1) / 2 + bj;
-        const int off = (a - bi * IWVI_BLK) * IWVI_BLK + (b - bj * IWVI_BLK);
-        for (int s_ = 0; s_ < wl.S; s_++)
-          s += red[(((size_t)q * wl.S + s_) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK + off];
-      }
-      *dst = s;
-      continue;
+      if (a >= b)
+        for (int s_ = 0; s_ < wl.S; s_++) s += red[(((size_t)q * wl.S + s_) * wl.npairs + pair) * BB + off];
+      if (q < R) { if (a < M && b < M) p.dq_sqrt[((size_t)q * M + a) * M + b] = s; }
+      else p.dLm[(size_t)a * Mp + b] = s;
+      return;
     }
-    k -= n_lq + n_lm;
-    if (k < n_qmu) {
-      const int m = (int)(k / R), r = (int)(k - (int64_t)m * R);
+    e -= f.n_blk;
+    if (e < f.n_up) {
+      const int off = (int)(e % BB);
+      const int64_t e2 = e / BB;
+      const int nup = NB * (NB - 1) / 2;
+      const int up = (int)(e2 % nup), q = (int)(e2 / nup);
+      int bj = 1;                                  // block column bj > block row bi; enumerate (bi, bj) with bi < bj
+      while (bj * (bj + 1) / 2 <= up) bj++;
+      const int bi = up - bj * (bj - 1) / 2;
+      const int a = bi * IWVI_BLK + (off >> 6), b = bj * IWVI_BLK + (off & 63);
+      if (q < R) { if (a < M && b < M) p.dq_sqrt[((size_t)q * M + a) * M + b] = 0.0; }
+      else p.dLm[(size_t)a * Mp + b] = 0.0;
+      return;
+    }
+    e -= f.n_up;
+    if (e < f.n_qmu) {
+      const int m = (int)(e / R), r = (int)(e - (int64_t)m * R);
       const int bi = m / IWVI_BLK;
       double s = 0.0;
       for (int s_ = 0; s_ < wl.S; s_++)
         s += qred[((size_t)s_ * NB + bi) * IWVI_BLK * IWVI_MAX_R + (m - bi * IWVI_BLK) * IWVI_MAX_R + r];
-      p.dq_mu[k] = s;
-      continue;
+      p.dq_mu[e] = s;
     }
-    k -= n_qmu;
-    if (k < n_z) {
-      const int m = (int)(k / D), dd = (int)(k - (int64_t)m * D);
-      double s = 0.0;
-      for (int g_ = 0; g_ < p.grid_tile; g_++) s += tile[(size_t)g_ * wl.tile_stride + (size_t)m * ldz + dd];
-      p.dZ[k] = s;
-      continue;
-    }
-    k -= n_z;
-    if (k < D) {
-      double s = 0.0;
-      for (int g_ = 0; g_ < p.grid_tile; g_++) s += tile[(size_t)g_ * wl.tile_stride + (size_t)Mp * ldz + k];
-      p.dls[k] = s;
-    } else if (k == D) {
-      double s = 0.0;
-      for (int g_ = 0; g_ < p.grid_tile; g_++) s += tile[(size_t)g_ * wl.tile_stride + (size_t)Mp * ldz + 32];
-      for (int e_ = 0; e_ < wl.n_epi; e_++) s += epi[(size_t)e_ * EPI_STRIDE + P * R + D * P + P];
-      p.dvariance[0] = s;
-    } else {
-      const int64_t j = k - D - 1;   // index into [dW | dmfA | dmfb]
-      double s = 0.0;
-      for (int e_ = 0; e_ < wl.n_epi; e_++) s += epi[(size_t)e_ * EPI_STRIDE + j];
-      if (j < P * R) { if (p.dW) p.dW[j] = s; }
-      else if (j < P * R + D * P) { if (p.dmfA) p.dmfA[j - P * R] = s; }
-      else { if (p.dmfb) p.dmfb[j - P * R - D * P] = s; }
-    }
+    return;
+  }
+  // ---- one warp per output: per-CTA partials of the tile kernel and of the epilogue kernel
+  const int lane = threadIdx.x & 31;
+  const int o = ((int)blockIdx.x - f.grid_elem) * 8 + (threadIdx.x >> 5);
+  if (o >= f.n_warp_out) return;
+  if (o < f.n_z) {
+    const int m = o / D, dd = o - m * D;
+    const double s = warp_partial_sum(tile + (size_t)m * ldz + dd, p.grid_tile, wl.tile_stride, lane);
+    if (lane == 0) p.dZ[o] = s;
+    return;
+  }
+  const int k = o - f.n_z;
+  if (k < D) {
+    const double s = warp_partial_sum(tile + (size_t)Mp * ldz + k, p.grid_tile, wl.tile_stride, lane);
+    if (lane == 0) p.dls[k] = s;
+  } else if (k == D) {
+    const double s = warp_partial_sum(tile + (size_t)Mp * ldz + 32, p.grid_tile, wl.tile_stride, lane) +
+                     warp_partial_sum(epi + P * R + D * P + P, wl.n_epi, EPI_STRIDE, lane);
+    if (lane == 0) p.dvariance[0] = s;
+  } else {
+    const int j = k - D - 1;   // index into [dW | dmfA | dmfb]
+    double* dst = j < P * R ? (p.dW ? p.dW + j : nullptr)
+                : j < P * R + D * P ? (p.dmfA ? p.dmfA + (j - P * R) : nullptr)
+                                    : (p.dmfb ? p.dmfb + (j - P * R - D * P) : nullptr);
+    if (!dst) return;          // frozen parameter: its partials were not formed
+    const double s = warp_partial_sum(epi + j, wl.n_epi, EPI_STRIDE, lane);
+    if (lane == 0) *dst = s;
   }
 }
 
@@ -901,7 +959,7 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   const int only = d->flags & IWVI_FLAG_ONLY_MASK;
 
   if (!only || (only & IWVI_FLAG_ONLY_EPI)) {
-    gp_epi_bwd_kernel<<<p.wl.n_epi, EPI_PTS, 0, st>>>(p);
+    gp_epi_bwd_kernel<<<p.wl.n_epi, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
 
@@ -926,7 +984,8 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
     IWVI_CHECK_LAUNCH();
   }
   if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {
-    gp_finalize_bwd_kernel<<<2 * nsm, 256, 0, st>>>(p);
+    const FinalLayout fl = final_layout(*d, p.wl);
+    gp_finalize_bwd_kernel<<<fl.grid_elem + fl.grid_warp, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
   return IWVI_OK;

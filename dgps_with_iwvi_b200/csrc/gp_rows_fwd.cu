@@ -121,7 +121,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
   }
 
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp % C::WMG) * C::WM;   // first block-row of this warp
+  // Row tiles (8 rows) of a 64-row block are dealt round-robin to the WMG warps of a column group: warp `wmi` owns
+  // tiles wmi, wmi + WMG, ...  With the triangular diagonal blocks this balances the skipped work, and flipping the
+  // order in warps 4-7 balances it across the four SM sub-partitions too (warps w and w + 4 share one).
+  const int wmi = ((warp >> 2) & 1) ? (C::WMG - 1 - warp % C::WMG) : (warp % C::WMG);
+  const int wr0 = wmi * 8;                   // first row of this warp's first tile; tile a starts at wr0 + a * MR
+  constexpr int MR = 8 * C::WMG;             // row distance between consecutive tiles of one warp
   const int wn0 = (warp / C::WMG) * C::WN;   // first point of this warp
   const int colbar = BAR_COL + warp / C::WMG;
   const double* zn = aux + al.off_zn;
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
       const double* st = ring.wait();
       double acc[C::TM][C::TN][2];
       acc_zero<C::TM, C::TN>(acc);
-      warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
+      warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
       ring.release(lane);
 #pragma unroll
       for (int a = 0; a < C::TM; a++)
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++) {
-            const int mg = i * IWVI_BLK + wm0 + a * 8 + g;
+            const int mg = i * IWVI_BLK + wr0 + a * MR + g;
             const int n = wn0 + b * 8 + 2 * t + c;
             const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
             panel[n * ldA + mg] = (mg < d.M) ? kern_k(d.kern, r2, variance) : 0.0;
@@ -184,11 +189,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g];
+              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g];
         for (int j = 0; j < i; j++) {
           const double* st = ring.wait();
-          warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA,
-                                        IWVI_BLK, lane);
+          warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK,
+                                                ldA, IWVI_BLK, lane);
           ring.release(lane);
         }
 #pragma unroll
@@ -197,13 +202,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wm0 + a * 8 + g] = -acc[a][b][c];
+              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g] = -acc[a][b][c];
         named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = ring.wait();   // inverted diagonal block
       acc_zero<C::TM, C::TN>(acc);
-      warp_gemm<C::TM, C::TN, 0, 0>(acc, st + wm0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA,
-                                    IWVI_BLK, lane);
+      warp_gemm_tri<C::TM, C::TN, 0, 0, C::WMG, 1>(acc, st, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, wmi, lane);
       ring.release(lane);
       named_bar_sync(colbar, C::WMG * 32);   // every warp of the group has read the right-hand side
 #pragma unroll
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++) {
-            const int m = i * IWVI_BLK + wm0 + a * 8 + g;
+            const int m = i * IWVI_BLK + wr0 + a * MR + g;
             const int n = wn0 + b * 8 + 2 * t + c;
             panel[n * ldA + m] = acc[a][b][c];
           }
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     // ---- U: triangular products with tril(q_sqrt_r)^T, column sums of squares (no inter-warp data flow)
     // this thread's corner of every saved U block of the tile (block-major [point][68]); pad points are saved as zeros
     double* ubase = p.save + sv.off_u + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES +
-                    (int64_t)((n0 & 63) + wn0 + 2 * t) * IWVI_LDS + wm0 + g;
+                    (int64_t)((n0 & 63) + wn0 + 2 * t) * IWVI_LDS + wr0 + g;
     unsigned pad_mask = 0;
 #pragma unroll
     for (int b = 0; b < C::TN; b++)
@@ -283,7 +287,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
         double* ub = ubase + (int64_t)r * sv.u_stride + (int64_t)i * IWVI_STAGE_DOUBLES;
         for (int j = i; j < NB; j++) {
           const double* st = ring.wait();
-          warp_gemm<C::TM, C::TN, 1, 0>(acc, st + wm0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+          if (j == i)   // diagonal block of tril(q_sqrt_r), used transposed: upper triangular in (m, k)
+            warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, wmi, lane);
+          else
+            warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
           ring.release(lane);
         }
 #pragma unroll
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
             for (int c = 0; c < 2; c++) {
               const double u = acc[a][b][c];
               csq[b][c] += u * u;
-              if (do_save) ub[(b * 8 + c) * IWVI_LDS + a * 8] = ((pad_mask >> (b * 2 + c)) & 1u) ? 0.0 : u;
+              if (do_save) ub[(b * 8 + c) * IWVI_LDS + a * MR] = ((pad_mask >> (b * 2 + c)) & 1u) ? 0.0 : u;
             }
       }
 #pragma unroll
