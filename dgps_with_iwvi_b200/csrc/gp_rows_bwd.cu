@@ -37,7 +37,37 @@ struct BwdWs {   // workspace layout (doubles)
   int64_t off_bbar, off_gmb, off_gvb, off_epi, off_tile, off_red, off_qred, total;
   int Tp, n_epi, grid_tile, S, npairs, chunks_per_split, tile_stride;
 };
-__host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
+// host-side list-scheduling model behind the choice of S (see bwd_ws_layout); the last answer is cached per thread
+// because the entry points recompute the layout on every call
+inline int pick_reduce_split(int items, int npairs, int nchunks, int nsm) {
+  static thread_local int key[4] = {-1, -1, -1, -1}, cached = 1;
+  if (key[0] == items && key[1] == npairs && key[2] == nchunks && key[3] == nsm) return cached;
+  int bestS = 1;
+  double best = 1e300;
+  const int ns = nsm < 256 ? (nsm > 0 ? nsm : 1) : 256;
+  for (int S = 1; S <= 16 && S <= nchunks; S++) {
+    const int cps = (nchunks + S - 1) / S;
+    double freeat[256];
+    for (int k = 0; k < ns; k++) freeat[k] = 0.0;
+    double makespan = 0.0;
+    for (int it = 0; it < items * S; it++) {
+      const int pair = it % npairs;
+      int bi = 0;
+      while ((bi + 1) * (bi + 2) / 2 <= pair) bi++;
+      const bool diag = (pair - bi * (bi + 1) / 2) == bi;
+      int k = 0;
+      for (int k2 = 1; k2 < ns; k2++) if (freeat[k2] < freeat[k]) k = k2;
+      freeat[k] += cps * (diag ? 0.6 : 1.0);
+      if (freeat[k] > makespan) makespan = freeat[k];
+    }
+    const double cost = makespan + 0.5 * S;
+    if (cost < best) { best = cost; bestS = S; }
+  }
+  key[0] = items; key[1] = npairs; key[2] = nchunks; key[3] = nsm; cached = bestS;
+  return bestS;
+}
+
+inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   BwdWs w;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
@@ -47,16 +77,10 @@ __host__ __device__ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   w.npairs = al.NB * (al.NB + 1) / 2;
   const int nchunks = w.Tp / IWVI_BLK;
   const int items = (d.R + 1) * w.npairs;
-  // split the points into S ranges so that items * S CTAs fill whole waves of the nsm SMs (one CTA per SM): minimise
-  // rounds * chunks-per-split, with a small charge per extra partial the finalize kernel has to sum
-  int bestS = 1;
-  double best = 1e300;
-  for (int S = 1; S <= 16 && S <= nchunks; S++) {
-    const int cps = (nchunks + S - 1) / S;
-    const int rounds = (items * S + nsm - 1) / nsm;
-    const double cost = (double)rounds * cps + 0.5 * S;
-    if (cost < best) { best = cost; bestS = S; }
-  }
+  // Split the points into S ranges.  CTAs are dispatched in blockIdx order to whichever SM frees up first; a diagonal
+  // pair costs ~0.6 of an off-diagonal one (reduce_diag).  Pick the S whose simulated makespan is smallest, with a
+  // small charge per extra partial the finalize kernel has to sum.
+  const int bestS = pick_reduce_split(items, w.npairs, nchunks, nsm);
   w.chunks_per_split = (nchunks + bestS - 1) / bestS;
   w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
@@ -329,6 +353,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   for (int idx = tid; idx < p.wl.tile_stride; idx += 256) mypart[idx] = 0.0;
   dls_s[tid] = 0.0;
   double dvar_acc = 0.0;
+  // lengthscale adjoint: sum_mn G_mn (x~_nd - z~_md)^2 = sum_n colsum_n x~_nd^2 + sum_m z~_md (rowsum_m z~_md - 2 (G x~)_md),
+  // assembled from quantities the dX / dZ sections hold anyway (the same expanded form GPflow uses for r^2 itself);
+  // this thread's slots are the input columns d = 8 b + 2 t + c
+  double dl_acc[4][2];
+#pragma unroll
+  for (int b = 0; b < 4; b++) { dl_acc[b][0] = 0.0; dl_acc[b][1] = 0.0; }
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
@@ -543,23 +573,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           v += __shfl_xor_sync(0xffffffffu, v, 16);
           if (g == 0) gs_s[(warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c] += v;
         }
-      // lengthscale adjoint, accumulated directly (no cancellation): sum G (x~_d - z~_d)^2
-      for (int dd = 0; dd < D; dd++) {
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < C::TM; a++) {
-          const double zv = st[(wr0 + a * MR + g) * ldz + dd];
-#pragma unroll
-          for (int b = 0; b < C::TN; b++)
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-              const double df = xs[(wn0 + b * 8 + 2 * t + c) * ldz + dd] - zv;
-              s += acc[a][b][c] * df * df;
-            }
-        }
-        s = warp_sum(s);
-        if (lane == 0) dls_s[warp * 32 + dd] += s;
-      }
       named_bar_sync(BAR_ALL, 256);   // G_i visible in the panel, gr_s complete
 
       // dX partial: accx[n][d] += sum_{m in block} G[m][n] z~[m][d]   (warp w owns points 8w..8w+7)
@@ -609,6 +622,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             if (b < nd8 && dcol < D && mg < M) {
               const double zv = st[ml * ldz + dcol];
               red_add(&mypart[(size_t)mg * ldz + dcol], -2.0 * consts[IWVI_C_INVLS + dcol] * (accz[b][c] - zv * grv));
+              dl_acc[b][c] += zv * (grv * zv - 2.0 * accz[b][c]);   // z part of sum G (x~ - z~)^2, see dl_acc
             }
           }
       }
@@ -628,8 +642,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
 #pragma unroll
           for (int c = 0; c < 2; c++) {
             const int dcol = b * 8 + 2 * t + c;
-            if (b < nd8 && dcol < D)
-              red_add(&p.dX[pt * D + dcol], 2.0 * consts[IWVI_C_INVLS + dcol] * (xs[n * ldz + dcol] * gsv - accx[b][c]));
+            if (b < nd8 && dcol < D) {
+              const double xv = xs[n * ldz + dcol];
+              red_add(&p.dX[pt * D + dcol], 2.0 * consts[IWVI_C_INVLS + dcol] * (xv * gsv - accx[b][c]));
+              dl_acc[b][c] += gsv * xv * xv;                        // x part of sum G (x~ - z~)^2
+            }
           }
       }
     }
@@ -646,6 +663,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
       mypart[(size_t)Mp * ldz + 32] = tot / variance;
     }
   }
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      double v = dl_acc[b][c];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (g == 0) dls_s[warp * 32 + b * 8 + 2 * t + c] = v;
+    }
+  named_bar_sync(BAR_ALL, 256);
   if (tid < 32) {
     double s = 0.0;
     for (int w = 0; w < C::NW; w++) s += dls_s[w * 32 + tid];
@@ -714,6 +742,86 @@ __device__ __forceinline__ void reduce_loop(RingT<4>& pipe, const ReduceLoopArgs
   }
 }
 
+// Diagonal output blocks (bi == bj): only the lower triangle of the 64x64 block is needed (dLq_r and dLm are tril'd),
+// i.e. 36 of the 64 8x8 tiles.  Warp w (and w + 4) owns row tiles {w, 7 - w} of the tile grid = 9 tiles, and the two
+// warps split every 64-point chunk in halves (k split) whose partial sums are combined through shared memory at the
+// end: 72 instead of 128 DMMAs per warp per chunk, evenly spread over the four SM sub-partitions.  The per-point scale
+// multiplies the two A fragments (2 DMULs per k-step) instead of the up-to-8 B fragments.
+template <int WQ, bool QMU>
+__device__ __forceinline__ void reduce_diag(RingT<4>& pipe, const ReduceLoopArgs& la, int warp, double* scratch,
+                                            double* out, double* oq) {
+  const int g = la.lane >> 2, t = la.lane & 3;
+  const int half = warp >> 2;
+  constexpr int R1 = WQ, R2 = 7 - WQ, N1 = WQ + 1, N2 = 8 - WQ;
+  double acc1[N1][2], acc2[N2][2], accq[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+  for (int j = 0; j < N1; j++) { acc1[j][0] = 0.0; acc1[j][1] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < N2; j++) { acc2[j][0] = 0.0; acc2[j][1] = 0.0; }
+  double sc[8], scn[8];
+  auto load_scales = [&](int c, double (&s_)[8]) {
+    const size_t pt0 = (size_t)c * IWVI_BLK + 32 * half + t;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) s_[ks] = la.is_lm ? -2.0 : 2.0 * __ldg(la.gvb + (pt0 + 4 * ks) * IWVI_MAX_R + la.q);
+  };
+  load_scales(la.c0, sc);
+  for (int c = la.c0; c < la.c1; c++) {
+    if (c + 1 < la.c1) load_scales(c + 1, scn);
+    const double* sa = pipe.wait(0);
+    const double* sb = pipe.wait(1);
+    const double* ap = sa + (32 * half + t) * IWVI_LDS + g;
+    const double* bp = sb + (32 * half + t) * IWVI_LDS + g;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      const int k0 = 4 * ks;
+      const double a1u = ap[k0 * IWVI_LDS + R1 * 8], a2u = ap[k0 * IWVI_LDS + R2 * 8];
+      const double a1 = a1u * sc[ks], a2 = a2u * sc[ks];
+#pragma unroll
+      for (int j = 0; j < N2; j++) {
+        const double b = bp[k0 * IWVI_LDS + j * 8];
+        if (j < N1) dmma884(acc1[j], a1, b);
+        dmma884(acc2[j], a2, b);
+      }
+      if (QMU) {   // compile-time: a DMMA under a runtime predicate would occupy the pipe even when off
+        const double bq = __ldg(la.gmb + ((size_t)c * IWVI_BLK + 32 * half + t + k0) * IWVI_MAX_R + g);
+        dmma884(accq[0], a1u, bq);
+        dmma884(accq[1], a2u, bq);
+      }
+    }
+    pipe.release(la.lane, 2);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) sc[ks] = scn[ks];
+  }
+  // combine the two k halves through the ring memory, once EVERY consumer warp has finished reading its last stages
+  named_bar_sync(1, 256);
+  double* scr = scratch + (size_t)((warp & 3) * 32 + la.lane) * 24;
+  if (half == 1) {
+#pragma unroll
+    for (int j = 0; j < N1; j++) { scr[2 * j] = acc1[j][0]; scr[2 * j + 1] = acc1[j][1]; }
+#pragma unroll
+    for (int j = 0; j < N2; j++) { scr[2 * (N1 + j)] = acc2[j][0]; scr[2 * (N1 + j) + 1] = acc2[j][1]; }
+    scr[18] = accq[0][0]; scr[19] = accq[0][1]; scr[20] = accq[1][0]; scr[21] = accq[1][1];
+  }
+  named_bar_sync(1, 256);
+  if (half == 0) {
+#pragma unroll
+    for (int j = 0; j < N1; j++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) out[(R1 * 8 + g) * IWVI_BLK + j * 8 + 2 * t + c] = acc1[j][c] + scr[2 * j + c];
+#pragma unroll
+    for (int j = 0; j < N2; j++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) out[(R2 * 8 + g) * IWVI_BLK + j * 8 + 2 * t + c] = acc2[j][c] + scr[2 * (N1 + j) + c];
+    if (QMU) {
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        oq[(R1 * 8 + g) * IWVI_MAX_R + 2 * t + c] = accq[0][c] + scr[18 + c];
+        oq[(R2 * 8 + g) * IWVI_MAX_R + 2 * t + c] = accq[1][c] + scr[20 + c];
+      }
+    }
+  }
+}
+
 #define RED_NST 4
 #define RED_THREADS 288   // 8 consumer warps + 1 producer warp
 __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const BwdParams p) {
@@ -757,6 +865,27 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
     while (!seq.done()) { pipe.produce(seq.get(), lane); seq.advance(); }
     return;
   }
+  double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;
+  double* oq = p.ws + wl.off_qred + ((size_t)s * NB + bi) * IWVI_BLK * IWVI_MAX_R;
+  if (bi == bj) {
+    const ReduceLoopArgs la = {gvb, gmb, q, is_lm, c0, c1, 0, 0, lane};
+    if (do_qmu) {
+      switch (warp & 3) {
+        case 0: reduce_diag<0, true>(pipe, la, warp, stages, out, oq); break;
+        case 1: reduce_diag<1, true>(pipe, la, warp, stages, out, oq); break;
+        case 2: reduce_diag<2, true>(pipe, la, warp, stages, out, oq); break;
+        default: reduce_diag<3, true>(pipe, la, warp, stages, out, oq); break;
+      }
+    } else {
+      switch (warp & 3) {
+        case 0: reduce_diag<0, false>(pipe, la, warp, stages, out, oq); break;
+        case 1: reduce_diag<1, false>(pipe, la, warp, stages, out, oq); break;
+        case 2: reduce_diag<2, false>(pipe, la, warp, stages, out, oq); break;
+        default: reduce_diag<3, false>(pipe, la, warp, stages, out, oq); break;
+      }
+    }
+    return;
+  }
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;     // warp tile 32 x 16 of the 64 x 64 output block
 
@@ -773,7 +902,6 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
   if (do_qmu && wn0 == 0) reduce_loop<true>(pipe, la, acc, accq);
   else reduce_loop<false>(pipe, la, acc, accq);
 
-  double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -782,7 +910,6 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
       for (int c = 0; c < 2; c++)
         out[(wm0 + i * 8 + g) * IWVI_BLK + wn0 + j * 8 + 2 * t + c] = acc[i][j][c];
   if (do_qmu && wn0 == 0) {
-    double* oq = p.ws + wl.off_qred + ((size_t)s * NB + bi) * IWVI_BLK * IWVI_MAX_R;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll

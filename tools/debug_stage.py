@@ -13,6 +13,7 @@ def close(name, got, want, rtol=1e-8):
     bad = np.argwhere(~(np.abs(got - want) <= rtol * np.abs(want).max()))
     print('%-12s err %.3e  nbad %d of %d  first bad %s' % (name, err, len(bad), got.size, bad[:6].tolist()))
 TS.close = close
-for i in [int(a) for a in sys.argv[1:]] or [1]:
-    print('shape', TS.SHAPES[i])
-    TS.test_gp_layer_stages(TS.SHAPES[i])
+for a in sys.argv[1:] or ['1']:
+    shape = TS.SHAPES[int(a)] if a.isdigit() else eval(a)
+    print('shape', shape)
+    TS.test_gp_layer_stages(shape)
