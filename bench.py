@@ -30,6 +30,15 @@ CONFIGS = {
 FP64_DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200 (profiles/FP64_PEAK_r01.md); MEASURED_PEAKS.json has no fp64 entry
 
 
+_STDOUT = None
+
+
+def emit(obj):
+    f = _STDOUT or sys.stdout
+    f.write(json.dumps(obj) + '\n')
+    f.flush()
+
+
 def make_data(N, D, seed=0):
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((N, D))
@@ -74,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '25'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -171,7 +180,7 @@ def run_reference(args):
                                    'reference needs TF1/GPflow1 which cannot be installed here' % (Bs, cfg['B'], cfg['K'])},
         'e2e': {'value': value, 'unit': 'KxN samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(name, cfg, gpus):
@@ -187,12 +196,18 @@ def workload_config(name, cfg, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--config', default='c3', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that chat on stdout (NCCL prints its version there) are sent to
+    # stderr for the duration of the run, and the line is written to the saved descriptor
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -314,7 +329,8 @@ def main():
         'step_tflops_per_gpu': flops / sec / 1e12,
         'step_frac_of_fp64_dmma_peak': flops / sec / 1e12 / FP64_DMMA_PEAK_TFLOPS,
         'roofline': {'bound': 'tensor', 'kernel': dom['kernel'], 'achieved': dom['tflops'], 'peak': FP64_DMMA_PEAK_TFLOPS,
-                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / FP64_DMMA_PEAK_TFLOPS, 'traffic': None,
+                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / FP64_DMMA_PEAK_TFLOPS,
+                     'traffic': ncu_traffic(args.config, dom['kernel']),
                      'peak_source': 'FP64 DMMA issue-rate probe measured on this pool (profiles/FP64_PEAK_r01.md); '
                                     'MEASURED_PEAKS.json carries only bf16 and HBM'},
         'kernels': kern,
@@ -330,16 +346,29 @@ def main():
                                'sample': 'oracle (torch-CPU fp64 restatement of the reference, KxK final layer) '
                                          'forward+autograd on %d of %d minibatch rows x K=%d, 3 evals after 1 warm-up, no '
                                          'optimiser step' % (Bs, B, K)}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(config, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this config (profiles/ncu_<config>_summary.json, written by tools/ncu_to_profiles.py); None if not captured."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_%s_summary.json' % config)
+    try:
+        with open(path) as f:
+            return json.load(f)['kernels'][kernel]['dram_bytes_per_launch']
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def kernel_timings(eng, capi, LIB, torch, reps=5):
     """Times gp_rows_fwd_kernel, gp_tile_bwd_kernel and gp_reduce_bwd_kernel of the widest inner GP layer alone, on the
     buffers the last step left behind.  Algorithmic flops per launch:
       rows_fwd : T[(1+R)M^2 + 2M(D+2R+1)]           tile_bwd : T[(1+R)M^2 + 2M(3D+R+1)]
-      reduce   : T(1+R)M^2 (1 + 1/NB)  (lower-triangular block pairs only) + 2TMR"""
+      reduce   : T(1+R)M^2 + 2TMR   (lower triangles only)
+    All three use SURVEY.md 8(d)'s triangular-aware count; the blocked algorithms execute more (diagonal blocks are
+    only skipped at 8x8x4 granularity), so 1.0 is not reachable."""
     gps = [r for r in eng.recs if r['type'] == 'gp']
     r = max(gps, key=lambda q: q['R'] * q['M'] * q['M'])
     n_like = len(gps)
@@ -374,7 +403,7 @@ def kernel_timings(eng, capi, LIB, torch, reps=5):
         ('gp_rows_fwd_kernel', fwd, T * ((1 + R) * M * M + 2 * M * (D + 2 * R + 1))),
         ('gp_tile_bwd_kernel', lambda: bwd(LIB.FLAG_ONLY_TILE if hasattr(LIB, 'FLAG_ONLY_TILE') else 32),
          T * ((1 + R) * M * M + 2 * M * (3 * D + R + 1))),
-        ('gp_reduce_bwd_kernel', lambda: bwd(64), T * (1 + R) * M * M * (1 + 1.0 / NB) + 2 * T * M * R),
+        ('gp_reduce_bwd_kernel', lambda: bwd(64), T * (1 + R) * M * M + 2 * T * M * R),
     ]
     out = []
     for name, fn, fl in cases:

@@ -138,3 +138,17 @@ def test_full_size_properties_c2():
     b = mv.compute_log_likelihood(Xb, Yb, [None if e is None else e.reshape(B, -1) for e in eps])
     engi, engv = m.engine(B, K), mv.engine(B, 1)
     assert np.isfinite(a) and np.isfinite(b) and abs(a - b) < 0.05 * abs(a)
+
+
+def test_data_parallel_two_gpus_matches_single():
+    """2 ranks over NCCL (row shards + one all-reduce of the flat bucket) == one rank on the whole minibatch."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(here, 'dp_check.py')],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
