@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libiwvi_b200.so')
+LIB_PATH = os.environ.get('IWVI_B200_LIB') or os.path.join(HERE, 'lib', 'libiwvi_b200.so')
 
 MAX_ENC_LAYERS = 8
 

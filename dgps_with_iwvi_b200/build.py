@@ -35,9 +35,11 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, timing=False):
+    """timing=True: a second library, lib/libiwvi_b200_timing.so, compiled with -DIWVI_PHASE_TIMING (per-phase clock64()
+    totals, tools/phase_timing.py); select it with the environment variable IWVI_B200_LIB."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, 'obj')
+    objdir = os.path.join(LIBDIR, 'obj_timing' if timing else 'obj')
     os.makedirs(objdir, exist_ok=True)
     srcs = sources()
     hdrs = _deps()
@@ -47,7 +49,8 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, os.path.basename(s)[:-3] + '.o')
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o])
+            jobs.append([NVCC] + FLAGS + (['-DIWVI_PHASE_TIMING', '-rdc=true'] if timing else []) +
+                        (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -59,10 +62,11 @@ def build(force=False, verbose=False):
         for out in ex.map(run, jobs):
             if verbose and out:
                 print(out)
-    if jobs or force or _stale(LIB, objs):
-        run([NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
-    return LIB
+    lib = LIB.replace('.so', '_timing.so') if timing else LIB
+    if jobs or force or _stale(lib, objs):
+        run([NVCC, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, timing='--timing' in sys.argv))

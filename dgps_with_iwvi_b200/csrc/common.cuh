@@ -326,35 +326,141 @@ struct RingT {
 // ---------------------------------------------------------------------------------------------
 // stationary kernels (GPflow 1.x formulas): K(r2) and dK/dr2
 // ---------------------------------------------------------------------------------------------
+// Branch-free exp(x) for the kernel functions (x <= ~700; in practice x <= 0).  libdevice's exp() carries a rarely
+// taken slow-path branch, which splits the sixteen independent evaluations each thread makes per 64x64 gram block into
+// separate basic blocks that the scheduler cannot interleave: measured ~450 cycles per element.  Straight-line code
+// overlaps them.  Method: x = k ln2 + r, |r| <= ln2/2 (Cody-Waite, two-part ln2); exp(r) = (exp(r/8))^8 with a
+// degree-8 Taylor polynomial on |r/8| <= 0.0434 (truncation 3e-17 relative) and three squarings; scale by 2^k through
+// the exponent field.  Relative error a few ulp (<= ~2e-15 against numpy over [-700, 1]); the Lm / Kuf stage parity
+// tests (rtol 1e-8) exercise it for every kernel family.
+// Arguments below -708 are clamped (result 3.3e-308 instead of a denormal or 0); NaN propagates.
+__device__ __forceinline__ double exp_bf(double x) {
+  x = (x < -708.0) ? -708.0 : x;
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer, kept in the low word
+  const double t = fma(x, 1.4426950408889634074, MAGIC);
+  const int k = __double2loint(t);
+  const double kd = t - MAGIC;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  const double s = 0.125 * r;
+  double p = 2.48015873015873015873e-05;             // 1/8!
+  p = fma(p, s, 1.98412698412698412698e-04);         // 1/7!
+  p = fma(p, s, 1.38888888888888888889e-03);         // 1/6!
+  p = fma(p, s, 8.33333333333333333333e-03);         // 1/5!
+  p = fma(p, s, 4.16666666666666666667e-02);         // 1/4!
+  p = fma(p, s, 1.66666666666666666667e-01);         // 1/3!
+  p = fma(p, s, 0.5);
+  p = fma(p, s, 1.0);
+  double e = fma(p, s, 1.0);                         // exp(r/8)
+  e *= e; e *= e; e *= e;                            // exp(r)
+  return e * __hiloint2double((k + 1023) << 20, 0);  // * 2^k  (k >= -1022 thanks to the clamp)
+}
+
+// N independent evaluations in lock step (x -> exp(x) in place).  Written statement by statement over the N values
+// because ptxas otherwise emits the N serial dependency chains one after the other (observed in the SASS), which
+// leaves the FP64 pipe idle for most of each chain's latency.
+template <int N>
+__device__ __forceinline__ void exp_bf_n(double (&x)[N]) {
+  const double MAGIC = 6755399441055744.0;
+  double t[N], r[N], p[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = (x[i] < -708.0) ? -708.0 : x[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) t[i] = fma(x[i], 1.4426950408889634074, MAGIC);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = t[i] - MAGIC;
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = fma(r[i], -6.93147180369123816490e-01, x[i]);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = 0.125 * fma(r[i], -1.90821492927058770002e-10, x[i]);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(2.48015873015873015873e-05, r[i], 1.98412698412698412698e-04);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.38888888888888888889e-03);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 8.33333333333333333333e-03);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 4.16666666666666666667e-02);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.66666666666666666667e-01);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 0.5);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] *= p[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] *= p[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] *= p[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = p[i] * __hiloint2double((__double2loint(t[i]) + 1023) << 20, 0);
+}
+
+// K(r2) for N squared distances at once (in place: r2 -> K); optionally dK/dr2 as well
+template <int KIND, int N, bool WITH_DK>
+__device__ __forceinline__ void kern_n(double (&v)[N], double (&dk)[N], double variance) {
+  if (KIND == IWVI_KERN_RBF) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] *= -0.5;
+    exp_bf_n<N>(v);
+#pragma unroll
+    for (int i = 0; i < N; i++) { v[i] *= variance; if (WITH_DK) dk[i] = -0.5 * v[i]; }
+    return;
+  }
+  const double c = KIND == IWVI_KERN_MATERN52 ? 2.23606797749978969641 : KIND == IWVI_KERN_MATERN32 ? 1.73205080756887729353 : 1.0;
+  double r[N], e[N];
+  bool clamped[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { clamped[i] = v[i] < 1e-40; r[i] = sqrt(fmax(v[i], 1e-40)); e[i] = -c * r[i]; }
+  exp_bf_n<N>(e);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (KIND == IWVI_KERN_MATERN52) {
+      v[i] = variance * (1.0 + c * r[i] + (5.0 / 3.0) * r[i] * r[i]) * e[i];
+      if (WITH_DK) dk[i] = -(5.0 / 6.0) * variance * (1.0 + c * r[i]) * e[i];
+    } else if (KIND == IWVI_KERN_MATERN32) {
+      v[i] = variance * (1.0 + c * r[i]) * e[i];
+      if (WITH_DK) dk[i] = -1.5 * variance * e[i];
+    } else {
+      v[i] = variance * e[i];
+      if (WITH_DK) dk[i] = -variance * e[i] / (2.0 * r[i]);
+    }
+    if (WITH_DK && clamped[i]) dk[i] = 0.0;
+  }
+}
+
 __device__ __forceinline__ double kern_k(int kind, double r2, double variance) {
-  if (kind == IWVI_KERN_RBF) return variance * exp(-0.5 * r2);
+  if (kind == IWVI_KERN_RBF) return variance * exp_bf(-0.5 * r2);
   const double r = sqrt(fmax(r2, 1e-40));
   if (kind == IWVI_KERN_MATERN52) {
     const double s5 = 2.23606797749978969641;
-    return variance * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * exp(-s5 * r);
+    return variance * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * exp_bf(-s5 * r);
   }
   if (kind == IWVI_KERN_MATERN32) {
     const double s3 = 1.73205080756887729353;
-    return variance * (1.0 + s3 * r) * exp(-s3 * r);
+    return variance * (1.0 + s3 * r) * exp_bf(-s3 * r);
   }
-  return variance * exp(-r);
+  return variance * exp_bf(-r);
 }
 __device__ __forceinline__ void kern_k_dk(int kind, double r2, double variance, double& K, double& dK) {
-  if (kind == IWVI_KERN_RBF) { K = variance * exp(-0.5 * r2); dK = -0.5 * K; return; }
+  if (kind == IWVI_KERN_RBF) { K = variance * exp_bf(-0.5 * r2); dK = -0.5 * K; return; }
   const bool clamped = r2 < 1e-40;
   const double r = sqrt(fmax(r2, 1e-40));
   if (kind == IWVI_KERN_MATERN52) {
     const double s5 = 2.23606797749978969641;
-    const double e = exp(-s5 * r);
+    const double e = exp_bf(-s5 * r);
     K = variance * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
     dK = -(5.0 / 6.0) * variance * (1.0 + s5 * r) * e;
   } else if (kind == IWVI_KERN_MATERN32) {
     const double s3 = 1.73205080756887729353;
-    const double e = exp(-s3 * r);
+    const double e = exp_bf(-s3 * r);
     K = variance * (1.0 + s3 * r) * e;
     dK = -1.5 * variance * e;
   } else {
-    const double e = exp(-r);
+    const double e = exp_bf(-r);
     K = variance * e;
     dK = -variance * e / (2.0 * r);
   }
@@ -391,5 +497,18 @@ __device__ __forceinline__ void red_add(double* p, double v) {
 }
 
 int iwvi_check_gp_desc(const iwvi_gp_desc* d);
+
+// Optional phase timing (tools/phase_timing.py builds a second library with -DIWVI_PHASE_TIMING): thread 0 of every CTA
+// accumulates clock64() deltas per phase; the totals land in a device array read back through iwvi_debug_phase_cycles.
+#ifdef IWVI_PHASE_TIMING
+extern __device__ unsigned long long iwvi_phase_cycles[2][16];
+#define PHASE_DECL long long ph_t_ = clock64(); long long ph_acc_[16] = {0}
+#define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); ph_acc_[k] += now_ - ph_t_; ph_t_ = now_; } } while (0)
+#define PHASE_FLUSH(kern) do { if (threadIdx.x == 0) for (int k_ = 0; k_ < 16; k_++) atomicAdd(&iwvi_phase_cycles[kern][k_], (unsigned long long)ph_acc_[k_]); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE_MARK(k)
+#define PHASE_FLUSH(kern)
+#endif
 
 #define IWVI_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return IWVI_ERR_LAUNCH; } while (0)

@@ -95,6 +95,7 @@ __device__ __forceinline__ void load_block(double* dst, const double* src, int l
   }
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             const int ng = k * IWVI_BLK + wn0 + b * 8 + 2 * t + c;
             double v;
             if (mg < M && ng < M) {
-              v = kern_k(d.kern, zn[mg] + zn[ng] - 2.0 * acc[a][b][c], variance);
+              v = kern_k(KIND, zn[mg] + zn[ng] - 2.0 * acc[a][b][c], variance);
               if (mg == ng) v += jitter;
             } else {
               v = (mg == ng) ? 1.0 : 0.0;
@@ -598,6 +599,15 @@ __global__ void gauss_kl_bwd_kernel(int M, int R, const double* q_mu, const doub
   for (int64_t e = gtid; e < (int64_t)M * R; e += gsz) dq_mu[e] = g * q_mu[e];
 }
 
+template <int KIND>
+int launch_chol(const ProParams& p, int smem_bytes, cudaStream_t st) {
+  if (cudaFuncSetAttribute(gp_chol_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  gp_chol_kernel<KIND><<<1, 256, smem_bytes, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -632,11 +642,12 @@ extern "C" int iwvi_gp_prologue_fwd(const iwvi_gp_desc* d, const double* Z, cons
   gp_pack_kernel<<<IWVI_PACK_GRID, 256, 0, st>>>(p);
   IWVI_CHECK_LAUNCH();
   const int smem_bytes = (5 * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK * 36) * 8;
-  if (cudaFuncSetAttribute(gp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-    return IWVI_ERR_LAUNCH;
-  gp_chol_kernel<<<1, 256, smem_bytes, st>>>(p);
-  IWVI_CHECK_LAUNCH();
-  return IWVI_OK;
+  switch (d->kern) {
+    case IWVI_KERN_RBF: return launch_chol<IWVI_KERN_RBF>(p, smem_bytes, st);
+    case IWVI_KERN_MATERN12: return launch_chol<IWVI_KERN_MATERN12>(p, smem_bytes, st);
+    case IWVI_KERN_MATERN32: return launch_chol<IWVI_KERN_MATERN32>(p, smem_bytes, st);
+    default: return launch_chol<IWVI_KERN_MATERN52>(p, smem_bytes, st);
+  }
 }
 
 extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* Z,

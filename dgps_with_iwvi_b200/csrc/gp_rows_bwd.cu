@@ -267,18 +267,37 @@ __device__ __forceinline__ void lq_v_product(double (&acc)[TM][2][2], const doub
   }
 }
 
+// acc[b] += sum_k a(k) * B(k, 8 b + g) for b < NB8: one 8-row A tile (this lane's element of k-step k0 is ap[k0 * a_stride])
+// against NB8 column tiles of a [k][ld] operand (bp already points at row t, column g); columns >= ncols read as 0.
+template <int NB8>
+__device__ __forceinline__ void skinny_gemm(double (&acc)[4][2], const double* __restrict__ ap, int a_stride,
+                                            const double* __restrict__ bp, int ld, int K, int g, int ncols) {
+#pragma unroll 4
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const double a = ap[k0 * a_stride];
+#pragma unroll
+    for (int b = 0; b < NB8; b++) {
+      const double bv = (b * 8 + g < ncols) ? bp[k0 * ld + b * 8] : 0.0;
+      dmma884(acc[b], a, bv);
+    }
+  }
+}
+
 struct TileSmem { int panel, stages, xs, xn, gmb, gvb, gsum, gs, gr, dls, red, bars, total_doubles; };
 __host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
   TileSmem s; int o = 0;
-  s.panel = o;  o += TP * (Mp + 4);
+  s.panel = o;  o += (Mp / IWVI_BLK) * TP * IWVI_LDS;   // block-major [m-block][point][68], see gp_rows_fwd.cu
   s.stages = o; o += IWVI_NST * IWVI_STAGE_DOUBLES;
   s.xs = o;     o += TP * ldx;
   s.xn = o;     o += TP;
   s.gmb = o;    o += IWVI_MAX_R * TP;
   s.gvb = o;    o += IWVI_MAX_R * TP;
   s.gsum = o;   o += TP;
-  s.gs = o;     o += 4 * TP;               // [WMG][TP] column sums of G per warp row group
-  s.gr = o;     o += 2 * 4 * IWVI_BLK;     // [2][WNG][64] row sums of G per warp column group, double buffered
+  // gs [WMG][TP] column sums of G per warp row group, gr [2][WNG][64] row sums per warp column group (double buffered):
+  // only alive in the gram adjoint, when the per-point cotangents gmb / gvb are dead -> share their memory if they fit
+  const int n_gs = 4 * TP, n_gr = 2 * 4 * IWVI_BLK;
+  if (n_gs + n_gr <= 2 * IWVI_MAX_R * TP) { s.gs = s.gmb; s.gr = s.gmb + n_gs; }
+  else { s.gs = o; o += n_gs; s.gr = o; o += n_gr; }
   s.dls = o;    o += 8 * 32;               // [warp][32]
   s.red = o;    o += 32;
   s.bars = o;   o += 2 * IWVI_NST;
@@ -286,14 +305,15 @@ __host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
   return s;
 }
 
-template <int TP>
+template <int TP, int KIND>   // KIND: compile-time kernel family, see gp_rows_fwd.cu
 __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdParams p) {
   using C = TileCfg<TP>;
   static_assert(C::TN == 2, "register-resident V fragments assume two n-tiles per warp");
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
-  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, ldA = Mp + 4, R = d.R, D = d.D, T = d.T, M = d.M;
+  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, R = d.R, D = d.D, T = d.T, M = d.M;
+  constexpr int PSTR = TP * IWVI_LDS;   // element (point n, m) of m-block b: panel[b * PSTR + n * IWVI_LDS + m]
   const int Dk = iwvi_round_up(D, 4);
   const int nd8 = (D + 7) / 8;
   const TileSmem sl = tile_smem_layout(TP, Mp, ldz);
@@ -311,6 +331,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* aux = p.aux;
 
+  // the 4 pad columns of every panel row travel with the bulk stores: keep them zero (nothing else writes them)
+  for (int idx = threadIdx.x; idx < NB * TP * 4; idx += TILE_THREADS) panel[(idx >> 2) * IWVI_LDS + IWVI_BLK + (idx & 3)] = 0.0;
   RingT<IWVI_NST> pipe;
   pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages, C::NW);
   if (warp == C::NW) {
@@ -360,9 +382,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
 #pragma unroll
   for (int b = 0; b < 4; b++) { dl_acc[b][0] = 0.0; dl_acc[b][1] = 0.0; }
 
+  PHASE_DECL;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
     named_bar_sync(BAR_ALL, 256);
+    PHASE_MARK(7);
 
     // ---- per-point cotangents of this tile, x tile
     for (int idx = tid; idx < IWVI_MAX_R * TP; idx += 256) {
@@ -376,7 +400,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
       if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
       xs[idx] = v;
     }
-    for (int idx = tid; idx < 4 * TP; idx += 256) gs_s[idx] = 0.0;
     named_bar_sync(BAR_ALL, 256);
     if (tid < TP) {
       double s = 0.0;
@@ -387,6 +410,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
       gsum_s[tid] = gsum;
     }
     named_bar_sync(BAR_ALL, 256);
+    PHASE_MARK(0);
 
     // ---- Abar / 2, part 1: (q_mu gmean_bar^T) / 2 - A gsum.  (The factor 2 of part 2 is exact in binary floating
     //      point, so the panel carries Abar / 2 until the back substitution writes 2 x its result.)  The saved A arrives block by block through the ring (the
@@ -403,12 +427,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           double v = 0.0;
 #pragma unroll
           for (int r = 0; r < IWVI_MAX_R; r++) v += qr[r] * gmb_s[r * TP + n];
-          panel[n * ldA + mb * IWVI_BLK + mm] = 0.5 * v - st[n * IWVI_LDS + mm] * gsum_s[n];   // Abar / 2
+          panel[mb * PSTR + n * IWVI_LDS + mm] = 0.5 * v - st[n * IWVI_LDS + mm] * gsum_s[n];   // Abar / 2
         }
         pipe.release(lane);
       }
     }
     named_bar_sync(BAR_ALL, 256);
+    PHASE_MARK(1);
 
     // ---- Abar, part 2: += 2 tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register B-fragments per k-block j
     //      (the saved U_r block comes through the ring too, ahead of the tril(q_sqrt) blocks that multiply it)
@@ -436,7 +461,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             for (int b = 0; b < 2; b++)
 #pragma unroll
               for (int c = 0; c < 2; c++)
-                acc[a_][b][c] = panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a_ * MR + g];
+                acc[a_][b][c] = panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a_ * MR + g];
           const double* st = pipe.wait();
           const double* ap = st + (wr0 + g) * IWVI_LDS + t;
           if (i == j) {   // diagonal block of tril(q_sqrt_r): the structural zeros are skipped (compile-time pattern per wmi)
@@ -459,14 +484,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
             for (int b = 0; b < 2; b++)
 #pragma unroll
               for (int c = 0; c < 2; c++) {
-                const int m = i * IWVI_BLK + wr0 + a_ * MR + g;
                 const int n = wn0 + b * 8 + 2 * t + c;
-                panel[n * ldA + m] = acc[a_][b][c];
+                panel[i * PSTR + n * IWVI_LDS + wr0 + a_ * MR + g] = acc[a_][b][c];
               }
         }
       }
     }
     named_bar_sync(BAR_ALL, 256);
+    PHASE_MARK(2);
 
     // ---- Bbar / 2 = Lm^-T (Abar / 2), blocked back substitution in place.  The factor 2 is restored where Bbar is
     //      consumed: the gram adjoint below and the reduce kernel's dLm scale.
@@ -480,10 +505,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g];
+              acc[a][b][c] = -panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g];
         for (int j = i + 1; j < NB; j++) {
           const double* st = pipe.wait();
-          warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+          warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS, IWVI_LDS, IWVI_BLK, lane);
           pipe.release(lane);
         }
 #pragma unroll
@@ -492,12 +517,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g] = -acc[a][b][c];
+              panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g] = -acc[a][b][c];
         named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = pipe.wait();   // inverted diagonal block i, used transposed
       acc_zero<C::TM, C::TN>(acc);
-      warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, wmi, lane);
+      warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + i * PSTR + wn0 * IWVI_LDS, IWVI_LDS, wmi, lane);
       pipe.release(lane);
       named_bar_sync(colbar, C::WMG * 32);   // every warp of the column group has read the right-hand side
 #pragma unroll
@@ -506,55 +531,65 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++)
-            panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g] = acc[a][b][c];
+            panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g] = acc[a][b][c];
       named_bar_sync(colbar, C::WMG * 32);
     }
 
+    PHASE_MARK(3);
     // ---- store Bbar / 2 (needed by the reduce kernel for dLm) with asynchronous TMA stores straight from the panel, one
     //      512-byte run per (point, m-block); rows of invalid points are zero by construction
     fence_async_smem();
     named_bar_sync(BAR_ALL, 256);
     if (warp == 0) {
       double* dst = bbar_T + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
-      for (int idx = lane; idx < TP * NB; idx += 32) {
-        const int n = idx / NB, mb = idx - n * NB;
-        bulk_s2g(dst + (int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS, panel + n * ldA + mb * IWVI_BLK, IWVI_BLK * 8);
+      if (lane < NB) {   // one bulk operation per m-block (block-major panel == block-major destination)
+        bulk_s2g(dst + (int64_t)lane * IWVI_STAGE_DOUBLES, panel + lane * PSTR, TP * IWVI_LDS * 8);
+        bulk_commit();
+        bulk_wait_read();   // the gram adjoint below overwrites the panel in place
       }
-      bulk_commit();
-      bulk_wait_read();   // the gram adjoint below overwrites the panel in place
+      __syncwarp();
     }
     named_bar_sync(BAR_ALL, 256);
 
+    PHASE_MARK(4);
     // ---- gram adjoint, block row by block row
     double accx[4][2];
 #pragma unroll
     for (int b = 0; b < 4; b++) { accx[b][0] = 0.0; accx[b][1] = 0.0; }
     for (int i = 0; i < NB; i++) {
+      double znr[C::TM];                // |z|^2 of this thread's rows: fetched before the wait so the latency overlaps
+#pragma unroll
+      for (int a = 0; a < C::TM; a++) znr[a] = __ldg(zn + i * IWVI_BLK + wr0 + a * MR + g);
       const double* st = pipe.wait();   // scaled inducing inputs of block i: st[m*ldz + k]
       double acc[C::TM][C::TN][2];
       acc_zero<C::TM, C::TN>(acc);
       warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
+      PHASE_MARK(8);
       double cs[C::TN][2];
 #pragma unroll
       for (int b = 0; b < C::TN; b++) { cs[b][0] = 0.0; cs[b][1] = 0.0; }
 #pragma unroll
       for (int a = 0; a < C::TM; a++) {
         double rs = 0.0;
+        const int ml = wr0 + a * MR + g;
+        const int mg = i * IWVI_BLK + ml;
+        double kv[C::TN * 2], dkv[C::TN * 2];
+#pragma unroll
+        for (int b = 0; b < C::TN; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) kv[b * 2 + c] = znr[a] + xn[wn0 + b * 8 + 2 * t + c] - 2.0 * acc[a][b][c];
+        kern_n<KIND, C::TN * 2, true>(kv, dkv, variance);           // K and dK/dr2 of the row in lock step
 #pragma unroll
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++) {
-            const int ml = wr0 + a * MR + g;
-            const int mg = i * IWVI_BLK + ml;
             const int n = wn0 + b * 8 + 2 * t + c;
-            const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
-            double K, dK;
-            kern_k_dk(d.kern, r2, variance, K, dK);
             const bool valid = (mg < M) && (n0 + n < T);
-            const double bb = 2.0 * panel[n * ldA + mg];
-            const double G = valid ? bb * dK : 0.0;
-            if (valid) dvar_acc += bb * K;
-            panel[n * ldA + mg] = G;
+            double* pe = panel + i * PSTR + n * IWVI_LDS + ml;
+            const double bb = 2.0 * *pe;
+            const double G = valid ? bb * dkv[b * 2 + c] : 0.0;
+            if (valid) dvar_acc += bb * kv[b * 2 + c];
+            *pe = G;
             acc[a][b][c] = G;
             cs[b][c] += G;
             rs += G;
@@ -571,43 +606,37 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) gs_s[(warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c] += v;
+          if (g == 0) {   // one writer per slot: the first block row initialises, the others accumulate
+            double* gp = &gs_s[(warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c];
+            *gp = (i == 0 ? 0.0 : *gp) + v;
+          }
         }
+      PHASE_MARK(9);
       named_bar_sync(BAR_ALL, 256);   // G_i visible in the panel, gr_s complete
+      PHASE_MARK(10);
 
       // dX partial: accx[n][d] += sum_{m in block} G[m][n] z~[m][d]   (warp w owns points 8w..8w+7)
       if (warp < TP / 8) {
-        const double* ap = panel + (warp * 8 + g) * ldA + i * IWVI_BLK + t;
-#pragma unroll 4
-        for (int k0 = 0; k0 < IWVI_BLK; k0 += 4) {
-          const double a = ap[k0];
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (b < nd8) {
-              const int dcol = b * 8 + g;
-              const double bv = (dcol < ldz) ? st[(k0 + t) * ldz + dcol] : 0.0;
-              dmma884(accx[b], a, bv);
-            }
-          }
+        const double* ap = panel + i * PSTR + (warp * 8 + g) * IWVI_LDS + t;
+        switch (nd8) {   // compile-time column-tile count: no DMMA under a predicate
+          case 1: skinny_gemm<1>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
+          case 2: skinny_gemm<2>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
+          case 3: skinny_gemm<3>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
+          default: skinny_gemm<4>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
         }
       }
+      PHASE_MARK(11);
       // dZ partial of block row i: sum_n G[m][n] x~[n][d]   (warp w owns rows 8w..8w+7 of the block)
       {
         double accz[4][2];
 #pragma unroll
         for (int b = 0; b < 4; b++) { accz[b][0] = 0.0; accz[b][1] = 0.0; }
-        const double* ap = panel + t * ldA + i * IWVI_BLK + warp * 8 + g;
-#pragma unroll 4
-        for (int k0 = 0; k0 < TP; k0 += 4) {
-          const double a = ap[k0 * ldA];
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (b < nd8) {
-              const int dcol = b * 8 + g;
-              const double bv = (dcol < ldz) ? xs[(k0 + t) * ldz + dcol] : 0.0;
-              dmma884(accz[b], a, bv);
-            }
-          }
+        const double* ap = panel + i * PSTR + t * IWVI_LDS + warp * 8 + g;
+        switch (nd8) {
+          case 1: skinny_gemm<1>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
+          case 2: skinny_gemm<2>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
+          case 3: skinny_gemm<3>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
+          default: skinny_gemm<4>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
         }
         const int ml = warp * 8 + g;
         const int mg = i * IWVI_BLK + ml;
@@ -627,8 +656,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
           }
       }
       pipe.release(lane);
+      PHASE_MARK(12);
     }
 
+    PHASE_MARK(5);
     // ---- dX += 2/ls (x~ colsum(G) - G^T z~)
     if (warp < TP / 8) {
       const int n = warp * 8 + g;
@@ -652,6 +683,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     }
   }
 
+  PHASE_MARK(6);
+  PHASE_FLUSH(1);
   named_bar_sync(BAR_ALL, 256);
   {
     const double v = warp_sum(dvar_acc);
@@ -1027,6 +1060,24 @@ __global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p)
   }
 }
 
+template <int TP, int KIND>
+static int launch_tile_k(const BwdParams& p, int smem_bytes, cudaStream_t st) {
+  if (cudaFuncSetAttribute(gp_tile_bwd_kernel<TP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  gp_tile_bwd_kernel<TP, KIND><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+template <int TP>
+static int launch_tile(const BwdParams& p, int smem_bytes, cudaStream_t st) {
+  switch (p.d.kern) {
+    case IWVI_KERN_RBF: return launch_tile_k<TP, IWVI_KERN_RBF>(p, smem_bytes, st);
+    case IWVI_KERN_MATERN12: return launch_tile_k<TP, IWVI_KERN_MATERN12>(p, smem_bytes, st);
+    case IWVI_KERN_MATERN32: return launch_tile_k<TP, IWVI_KERN_MATERN32>(p, smem_bytes, st);
+    default: return launch_tile_k<TP, IWVI_KERN_MATERN52>(p, smem_bytes, st);
+  }
+}
+
 int pick_bwd_tp(int Mp, int ldz, int max_smem, int* smem_bytes) {
   const int cands[2] = {64, 32};
   for (int c = 0; c < 2; c++) {
@@ -1090,17 +1141,10 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
     IWVI_CHECK_LAUNCH();
   }
 
-  if (only && !(only & IWVI_FLAG_ONLY_TILE)) {
-  } else if (TP == 64) {
-    if (cudaFuncSetAttribute(gp_tile_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-      return IWVI_ERR_LAUNCH;
-    gp_tile_bwd_kernel<64><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);
-  } else {
-    if (cudaFuncSetAttribute(gp_tile_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-      return IWVI_ERR_LAUNCH;
-    gp_tile_bwd_kernel<32><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);
+  if (!only || (only & IWVI_FLAG_ONLY_TILE)) {
+    rc = TP == 64 ? launch_tile<64>(p, smem_bytes, st) : launch_tile<32>(p, smem_bytes, st);
+    if (rc != IWVI_OK) return rc;
   }
-  IWVI_CHECK_LAUNCH();
 
   if (!only || (only & IWVI_FLAG_ONLY_REDUCE)) {
     const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * RED_NST) * 8;

@@ -14,6 +14,7 @@
 //
 // Nothing of size M x T touches HBM unless IWVI_FLAG_SAVE asks for A and U (kept for the backward pass: on B200 an
 // HBM round trip costs less than recomputing them at the 37 TFLOP/s fp64 rate).
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -22,11 +23,13 @@ struct FwdSeq {  // order in which blocks are consumed by one tile
   int NB, R, npairs, ldz;
   const double *Zt, *Lmb, *Lqb;
   int ph, r, i, j;
-  __device__ __forceinline__ void init() { ph = 0; r = 0; i = 0; j = 0; }
+  // (the scaled inducing inputs are read straight from L1/L2 by the gram phase: streaming those small blocks through
+  //  the ring exposed one TMA latency per block and kept the first Lm blocks from being prefetched)
+  __device__ __forceinline__ void init() { ph = 1; r = 0; i = 0; j = 0; }
   __device__ __forceinline__ bool done() const { return ph == 3; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
-    if (ph == 0) {          // scaled inducing inputs of block i
+    if (ph == 0) {          // (unused) scaled inducing inputs of block i
       b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.bytes = (uint32_t)(IWVI_BLK * ldz * 8);
     } else if (ph == 1) {   // Lm(i,j), j < i; then the inverted diagonal block (slot (i,i))
       b.src = Lmb + (size_t)iwvi_pair(i, j) * IWVI_STAGE_DOUBLES; b.bytes = IWVI_STAGE_DOUBLES * 8;
@@ -49,7 +52,7 @@ struct FwdSeq {  // order in which blocks are consumed by one tile
 
 template <int TP> struct TileCfg {
   static constexpr int NW = 8;
-  static constexpr int WNG = TP >= 64 ? 4 : 2;  // warps along the point axis
+  static constexpr int WNG = TP >= 64 ? 4 : 2;  // warps along the point axis (TP is 64 or 32)
   static constexpr int WMG = NW / WNG;          // warps along the 64 rows of a block
   static constexpr int WM = IWVI_BLK / WMG;
   static constexpr int WN = TP / WNG;
@@ -70,12 +73,16 @@ struct FwdSmem {
 };
 __host__ __device__ inline FwdSmem fwd_smem_layout(int TP, int Mp, int ldx) {
   FwdSmem s; int o = 0;
-  s.panel = o;  o += TP * (Mp + 4);
+  // the panel is block-major like the saved arrays: [m-block][point][68], so that a whole m-block of the tile leaves
+  // for HBM as ONE bulk-TMA store (per-row 512-byte stores were bound by the TMA engine's per-operation cost)
+  s.panel = o;  o += (Mp / IWVI_BLK) * TP * IWVI_LDS;
   s.stages = o; o += IWVI_NST * IWVI_STAGE_DOUBLES;
-  s.xs = o;     o += TP * ldx;
+  const int n_xs = TP * ldx, n_usq = IWVI_MAX_R * TP * (TP >= 64 ? 2 : 4);   // usq: one slot per warp row group
+  s.xs = o;     o += n_xs;
+  if (n_usq <= n_xs) s.usq = s.xs;            // x tile is dead after the gram phase; usq lives from U to E
+  else { s.usq = o; o += n_usq; }
   s.xn = o;     o += TP;
   s.fv0 = o;    o += TP;
-  s.usq = o;    o += IWVI_MAX_R * TP * (TP >= 64 ? 2 : 4);   // one slot per warp row group: fixed-order sums
   s.gm = o;     o += IWVI_MAX_R * TP;
   s.bars = o;   o += 2 * IWVI_NST;
   s.total_doubles = o;
@@ -86,13 +93,17 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int TP, int Mp, int ldx) {
 #define BAR_ALL 1         // named barrier of the 256 consumer threads
 #define BAR_COL 2         // + column-group index: the WMG warps that share a set of points
 
-template <int TP>
+// KIND (the stationary kernel, IWVI_KERN_*) is a template parameter: with a run-time switch the sixteen inlined
+// copies of the kernel function per thread carried all four families and pushed the code past the instruction cache.
+template <int TP, int KIND>
 __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdParams p) {
   using C = TileCfg<TP>;
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
-  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, ldA = Mp + 4, R = d.R, D = d.D, T = d.T;
+  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, R = d.R, D = d.D, T = d.T;
+  constexpr int PSTR = TP * IWVI_LDS;        // doubles per m-block of the panel: element (point n, m) of block b is
+                                             // panel[b * PSTR + n * IWVI_LDS + m]
   const int Dk = iwvi_round_up(D, 4);
   const FwdSmem sl = fwd_smem_layout(TP, Mp, ldz);
   double* panel = smem + sl.panel;
@@ -105,6 +116,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* aux = p.aux;
 
+  // the 4 pad columns of every panel row travel with the bulk stores: keep them zero (nothing else writes them)
+  for (int idx = threadIdx.x; idx < NB * TP * 4; idx += FWD_THREADS) panel[(idx >> 2) * IWVI_LDS + IWVI_BLK + (idx & 3)] = 0.0;
   RingT<IWVI_NST> ring;
   ring.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages, C::NW);
 
@@ -137,6 +150,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
   const bool do_save = (d.flags & IWVI_FLAG_SAVE) != 0;
   const bool do_sample = (d.flags & IWVI_FLAG_SAMPLE) != 0;
 
+  PHASE_DECL;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
     if (warp == 0) bulk_wait_read();   // the previous tile's bulk stores no longer read the panel
@@ -157,27 +171,65 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     }
     named_bar_sync(BAR_ALL, 256);
 
-    // ---- G: gram blocks -> panel (Kuf)
-    for (int i = 0; i < NB; i++) {
-      const double* st = ring.wait();
-      double acc[C::TM][C::TN][2];
-      acc_zero<C::TM, C::TN>(acc);
-      warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
-      ring.release(lane);
+    PHASE_MARK(0);
+    // ---- G: gram blocks -> panel (Kuf).  A fragments (Z / ls, [Mp][ldz]) and |z|^2 come straight from L1/L2; they are
+    //      fetched for block i + 1 while block i's kernel function is evaluated.
+    //      The k range is the zero-padded row length of Z / ls (5 or 8 k-steps of 4, a compile-time constant per
+    //      branch): a run-time trip count would put the DMMAs under predicates, which occupy the pipe even when off.
+    auto gram_phase = [&](auto nk_c) {
+      constexpr int NK = decltype(nk_c)::value;
+      const double* ztw = aux + al.off_zt + (size_t)(wr0 + g) * ldz + t;
+      double za[C::TM][NK], znr[C::TM];
+      auto fetch = [&](int i) {
 #pragma unroll
-      for (int a = 0; a < C::TM; a++)
+        for (int a = 0; a < C::TM; a++) {
+          const double* zp = ztw + (size_t)(i * IWVI_BLK + a * MR) * ldz;
 #pragma unroll
-        for (int b = 0; b < C::TN; b++)
+          for (int ks = 0; ks < NK; ks++) za[a][ks] = __ldg(zp + 4 * ks);
+          znr[a] = __ldg(zn + i * IWVI_BLK + wr0 + a * MR + g);
+        }
+      };
+      fetch(0);
+      for (int i = 0; i < NB; i++) {
+        double acc[C::TM][C::TN][2];
+        acc_zero<C::TM, C::TN>(acc);
+        const double* bp = xs + (wn0 + g) * ldz + t;
 #pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int mg = i * IWVI_BLK + wr0 + a * MR + g;
-            const int n = wn0 + b * 8 + 2 * t + c;
-            const double r2 = zn[mg] + xn[n] - 2.0 * acc[a][b][c];
-            panel[n * ldA + mg] = (mg < d.M) ? kern_k(d.kern, r2, variance) : 0.0;
-          }
-    }
+        for (int ks = 0; ks < NK; ks++) {
+          double b[C::TN];
+#pragma unroll
+          for (int j = 0; j < C::TN; j++) b[j] = bp[j * 8 * ldz + 4 * ks];
+#pragma unroll
+          for (int a = 0; a < C::TM; a++)
+#pragma unroll
+            for (int j = 0; j < C::TN; j++) dmma884(acc[a][j], za[a][ks], b[j]);
+        }
+        double zc[C::TM];
+#pragma unroll
+        for (int a = 0; a < C::TM; a++) zc[a] = znr[a];
+        if (i + 1 < NB) fetch(i + 1);
+#pragma unroll
+        for (int a = 0; a < C::TM; a++) {
+          const int mg = i * IWVI_BLK + wr0 + a * MR + g;
+          double kv[C::TN * 2], unused[C::TN * 2];
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) kv[b * 2 + c] = zc[a] + xn[wn0 + b * 8 + 2 * t + c] - 2.0 * acc[a][b][c];
+          kern_n<KIND, C::TN * 2, false>(kv, unused, variance);     // the row's kernel values in lock step
+#pragma unroll
+          for (int b = 0; b < C::TN; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+              panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g] = (mg < d.M) ? kv[b * 2 + c] : 0.0;
+        }
+      }
+    };
+    if (ldz == 20) gram_phase(std::integral_constant<int, 5>());
+    else gram_phase(std::integral_constant<int, 8>());
     named_bar_sync(colbar, C::WMG * 32);
 
+    PHASE_MARK(1);
     // ---- T: blocked forward substitution, in place.  Data only flows between the WMG warps of a column group.
     for (int i = 0; i < NB; i++) {
       double acc[C::TM][C::TN][2];
@@ -189,11 +241,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              acc[a][b][c] = -panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g];
+              acc[a][b][c] = -panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g];
         for (int j = 0; j < i; j++) {
           const double* st = ring.wait();
-          warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * IWVI_LDS, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK,
-                                                ldA, IWVI_BLK, lane);
+          warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * IWVI_LDS, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS,
+                                                IWVI_LDS, IWVI_BLK, lane);
           ring.release(lane);
         }
 #pragma unroll
@@ -202,12 +254,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
           for (int b = 0; b < C::TN; b++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
-              panel[(wn0 + b * 8 + 2 * t + c) * ldA + i * IWVI_BLK + wr0 + a * MR + g] = -acc[a][b][c];
+              panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g] = -acc[a][b][c];
         named_bar_sync(colbar, C::WMG * 32);
       }
       const double* st = ring.wait();   // inverted diagonal block
       acc_zero<C::TM, C::TN>(acc);
-      warp_gemm_tri<C::TM, C::TN, 0, 0, C::WMG, 1>(acc, st, IWVI_LDS, panel + wn0 * ldA + i * IWVI_BLK, ldA, wmi, lane);
+      warp_gemm_tri<C::TM, C::TN, 0, 0, C::WMG, 1>(acc, st, IWVI_LDS, panel + i * PSTR + wn0 * IWVI_LDS, IWVI_LDS, wmi, lane);
       ring.release(lane);
       named_bar_sync(colbar, C::WMG * 32);   // every warp of the group has read the right-hand side
 #pragma unroll
@@ -216,29 +268,32 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
         for (int b = 0; b < C::TN; b++)
 #pragma unroll
           for (int c = 0; c < 2; c++) {
-            const int m = i * IWVI_BLK + wr0 + a * MR + g;
             const int n = wn0 + b * 8 + 2 * t + c;
-            panel[n * ldA + m] = acc[a][b][c];
+            panel[i * PSTR + n * IWVI_LDS + wr0 + a * MR + g] = acc[a][b][c];
           }
       named_bar_sync(colbar, C::WMG * 32);
     }
     fence_async_smem();   // the panel (A) is read by bulk stores below
     named_bar_sync(BAR_ALL, 256);
 
+    PHASE_MARK(2);
     // ---- S: fvar0 = sum_m A^2 and the latent means gmean = A^T q_mu, as one skinny DMMA product per 8 points
     //      (A fragments from the panel, q_mu [Mp, 8] fragments straight from L1/L2); two accumulators break the
     //      dependency chain.  The squares ride along on the A fragments.
     for (int mt = warp; mt < TP / 8; mt += C::NW) {
-      const double* ap = panel + (mt * 8 + g) * ldA + t;
+      const double* ap = panel + (mt * 8 + g) * IWVI_LDS + t;
       const double* bp = qmu + (size_t)t * IWVI_MAX_R + g;
       double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0}, sq0 = 0.0, sq1 = 0.0;
+      for (int mb = 0; mb < NB; mb++) {
 #pragma unroll 4
-      for (int k0 = 0; k0 < Mp; k0 += 8) {
-        const double a0 = ap[k0], a1 = ap[k0 + 4];
-        const double b0 = __ldg(bp + (size_t)k0 * IWVI_MAX_R), b1 = __ldg(bp + (size_t)(k0 + 4) * IWVI_MAX_R);
-        dmma884(c0, a0, b0);
-        dmma884(c1, a1, b1);
-        sq0 += a0 * a0; sq1 += a1 * a1;
+        for (int k0 = 0; k0 < IWVI_BLK; k0 += 8) {
+          const double a0 = ap[mb * PSTR + k0], a1 = ap[mb * PSTR + k0 + 4];
+          const double b0 = __ldg(bp + (size_t)(mb * IWVI_BLK + k0) * IWVI_MAX_R);
+          const double b1 = __ldg(bp + (size_t)(mb * IWVI_BLK + k0 + 4) * IWVI_MAX_R);
+          dmma884(c0, a0, b0);
+          dmma884(c1, a1, b1);
+          sq0 += a0 * a0; sq1 += a1 * a1;
+        }
       }
       double sq = sq0 + sq1;
       sq += __shfl_xor_sync(0xffffffffu, sq, 1);
@@ -251,19 +306,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
       const int nvalid = min(TP, T - n0);       // real points of this tile (pad points are saved as zeros)
       double* dst = p.save + sv.off_a + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
       if (nvalid == TP) {
-        // asynchronous TMA stores straight from the panel: one 512-byte run per (point, m-block)
-        if (warp == 0) {
-          for (int idx = lane; idx < TP * NB; idx += 32) {
-            const int n = idx / NB, mb = idx - n * NB;
-            bulk_s2g(dst + (int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS, panel + n * ldA + mb * IWVI_BLK, IWVI_BLK * 8);
-          }
+        // asynchronous TMA stores straight from the panel: one bulk operation per m-block and 64-point chunk
+        if (warp == 0 && lane < NB) {
+          bulk_s2g(dst + (int64_t)lane * IWVI_STAGE_DOUBLES, panel + lane * PSTR, TP * IWVI_LDS * 8);
           bulk_commit();
         }
       } else {
         const int mm = tid & 63;
         for (int mb = 0; mb < NB; mb++)
           for (int n = tid >> 6; n < TP; n += 4)
-            dst[(int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS + mm] = (n < nvalid) ? panel[n * ldA + mb * IWVI_BLK + mm] : 0.0;
+            dst[(int64_t)mb * IWVI_STAGE_DOUBLES + n * IWVI_LDS + mm] = (n < nvalid) ? panel[mb * PSTR + n * IWVI_LDS + mm] : 0.0;
       }
     }
 
@@ -288,9 +340,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
         for (int j = i; j < NB; j++) {
           const double* st = ring.wait();
           if (j == i)   // diagonal block of tril(q_sqrt_r), used transposed: upper triangular in (m, k)
-            warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, wmi, lane);
+            warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS, IWVI_LDS, wmi, lane);
           else
-            warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + wn0 * ldA + j * IWVI_BLK, ldA, IWVI_BLK, lane);
+            warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS, IWVI_LDS, IWVI_BLK, lane);
           ring.release(lane);
         }
 #pragma unroll
@@ -317,6 +369,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     }
     named_bar_sync(BAR_ALL, 256);
 
+    PHASE_MARK(4);
     // ---- E: per-point epilogue, 256/TP threads per point sharing its output columns
     {
       constexpr int QT = 256 / TP;
@@ -358,17 +411,29 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
         }
       }
     }
+    PHASE_MARK(5);
   }
+  PHASE_FLUSH(0);
   if (warp == 0) bulk_wait_read();   // shared memory must outlive the last tile's bulk stores
+}
+
+template <int TP, int KIND>
+int launch_fwd_k(const FwdParams& p, int smem_bytes, int grid, cudaStream_t stream) {
+  if (cudaFuncSetAttribute(gp_rows_fwd_kernel<TP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  gp_rows_fwd_kernel<TP, KIND><<<grid, FWD_THREADS, smem_bytes, stream>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
 }
 
 template <int TP>
 int launch_fwd(const FwdParams& p, int smem_bytes, int grid, cudaStream_t stream) {
-  if (cudaFuncSetAttribute(gp_rows_fwd_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-    return IWVI_ERR_LAUNCH;
-  gp_rows_fwd_kernel<TP><<<grid, FWD_THREADS, smem_bytes, stream>>>(p);
-  IWVI_CHECK_LAUNCH();
-  return IWVI_OK;
+  switch (p.d.kern) {
+    case IWVI_KERN_RBF: return launch_fwd_k<TP, IWVI_KERN_RBF>(p, smem_bytes, grid, stream);
+    case IWVI_KERN_MATERN12: return launch_fwd_k<TP, IWVI_KERN_MATERN12>(p, smem_bytes, grid, stream);
+    case IWVI_KERN_MATERN32: return launch_fwd_k<TP, IWVI_KERN_MATERN32>(p, smem_bytes, grid, stream);
+    default: return launch_fwd_k<TP, IWVI_KERN_MATERN52>(p, smem_bytes, grid, stream);
+  }
 }
 
 }  // namespace
@@ -385,9 +450,10 @@ int iwvi_check_gp_desc(const iwvi_gp_desc* d) {
 
 // pick the tile width: the largest TP whose panel fits and that still yields >= 2 tiles per SM, else smaller
 int iwvi_pick_tp(int T, int Mp, int ldz, int nsm, int max_smem, int* smem_bytes) {
-  const int cands[3] = {128, 64, 32};
+  // (a tile never straddles a 64-point chunk of the block-major saved arrays: TP divides 64)
+  const int cands[2] = {64, 32};
   int best = -1, best_bytes = 0;
-  for (int c = 0; c < 3; c++) {
+  for (int c = 0; c < 2; c++) {
     const int TP = cands[c];
     const int bytes = fwd_smem_layout(TP, Mp, ldz).total_doubles * 8;
     if (bytes > max_smem) continue;
@@ -426,7 +492,6 @@ extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const d
   p.ntiles = (d->flags & IWVI_FLAG_SAVE) ? iwvi_save_layout(d->T, d->M, d->R).Tp / TP : (d->T + TP - 1) / TP;
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
   cudaStream_t st = (cudaStream_t)stream;
-  if (TP == 128) return launch_fwd<128>(p, smem_bytes, grid, st);
   if (TP == 64) return launch_fwd<64>(p, smem_bytes, grid, st);
   return launch_fwd<32>(p, smem_bytes, grid, st);
 }

@@ -81,7 +81,7 @@ with open(os.path.join(ROOT, 'profiles', 'ncu_%s_summary.json' % config), 'w') a
     json.dump(out, f, indent=1, sort_keys=True)
 
 md = ['# ncu --set full, config %s, %s (%s)\n' % (config, rnd, os.path.basename(rep)),
-      '| kernel | us | DMMA pipe busy | tensor pipe active %% | DRAM read MB | DRAM write MB | regs | dyn smem | L2 hit %% |',
+      '| kernel | us | DMMA pipe busy | tensor pipe active % | DRAM read MB | DRAM write MB | regs | dyn smem KB | L2 hit % |',
       '|---|---|---|---|---|---|---|---|---|']
 for k, d in sorted(best.items()):
     f2 = lambda v, s=1.0: '-' if v is None else '%.1f' % (v * s)
