@@ -58,6 +58,8 @@ SIGNATURES = {
     'iwvi_iwelbo_fwd': (C.c_int, [C.POINTER(ElboDesc)] + [P] * 10),
     'iwvi_iwelbo_bwd': (C.c_int, [C.POINTER(ElboDesc)] + [P] * 12),
     'iwvi_normal_fill': (C.c_int, [P, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, P]),
+    'iwvi_normal_fill_counter': (C.c_int, [P, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int64, P, P]),
+    'iwvi_adam_step_counter': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, P, C.c_double, C.c_double, C.c_double, P, P]),
     'iwvi_positive_fwd': (C.c_int, [P, P, C.c_int64, P]),
     'iwvi_adam_step': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int64, P]),

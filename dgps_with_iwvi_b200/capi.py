@@ -23,8 +23,8 @@ def _ptr(t):
         return None
     if not t.is_cuda:
         raise RuntimeError('dgps_with_iwvi_b200 has no CPU path: tensor is on %s' % t.device)
-    if t.dtype not in (torch.float64, torch.int32):
-        raise TypeError('expected float64/int32, got %s' % t.dtype)
+    if t.dtype not in (torch.float64, torch.int32, torch.int64):
+        raise TypeError('expected float64/int32/int64, got %s' % t.dtype)
     if not t.is_contiguous():
         raise ValueError('tensor must be contiguous')
     return t.data_ptr()
@@ -167,6 +167,20 @@ def normal_fill(out, n_points, C_, first_point, seed):
     _count(1)
     L.check(L.load().iwvi_normal_fill(_ptr(out), int(n_points), int(C_), int(first_point),
                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()), 'iwvi_normal_fill')
+
+
+def normal_fill_counter(out, n_points, C_, first_point, seed_base, layer, step_add, state):
+    _count(1)
+    L.check(L.load().iwvi_normal_fill_counter(_ptr(out), int(n_points), int(C_), int(first_point),
+                                              int(seed_base) & 0xFFFFFFFFFFFFFFFF, int(layer), int(step_add), _ptr(state),
+                                              _stream()), 'iwvi_normal_fill_counter')
+
+
+def adam_step_counter(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr_dev, beta1, beta2, eps, state):
+    _count(2)
+    L.check(L.load().iwvi_adam_step_counter(_ptr(x), _ptr(grad_elbo), _ptr(m), _ptr(v), _ptr(mask), _ptr(theta_pos), int(n),
+                                            int(n_pos), _ptr(lr_dev), float(beta1), float(beta2), float(eps), _ptr(state),
+                                            _stream()), 'iwvi_adam_step_counter')
 
 
 def positive_fwd(x, theta, n):

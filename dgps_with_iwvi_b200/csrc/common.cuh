@@ -25,7 +25,7 @@ __host__ __device__ inline int iwvi_ldz(int D) { return D <= 20 ? 20 : 36; }
 // ---------------------------------------------------------------------------------------------
 struct AuxLayout {
   int Mp, NB, ldz, R, npairs;
-  int64_t off_lmb, off_lqb, off_zt, off_zn, off_qmu, off_consts, off_scratch, total;
+  int64_t off_lmb, off_lqb, off_zt, off_zn, off_qmu, off_consts, off_scratch, off_prog, total;
 };
 // index of the lower block (i, j), i >= j, in the block-major arrays
 __host__ __device__ inline int iwvi_pair(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -46,6 +46,7 @@ __host__ __device__ inline AuxLayout iwvi_aux_layout(int M, int D, int R) {
   a.off_qmu = o;    o += (int64_t)a.Mp * IWVI_MAX_R;            // q_mu padded to [Mp, 8]
   a.off_consts = o; o += 64;                                    // [0]=variance, 1/ls[d] at [8+d]
   a.off_scratch = o; o += IWVI_PACK_GRID;                       // per-CTA partial sums of the KL (fixed-order final sum)
+  a.off_prog = o;    o += 8;                                    // 16 ints: per block-row progress counters of the Cholesky
   a.total = o;
   return a;
 }
@@ -494,6 +495,17 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // ONE thread owns the address for the whole kernel, so the additions happen in program order: still deterministic.
 __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// inter-CTA hand-off through global memory (producer: data stores, __syncthreads, thread 0: st_release; consumer:
+// thread 0 spins on ld_acquire, __syncthreads, then everybody reads the data with L2-coherent loads)
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 int iwvi_check_gp_desc(const iwvi_gp_desc* d);

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
     else if (e >= IWVI_C_INVLS && e < IWVI_C_INVLS + D) v = 1.0 / p.ls[e - IWVI_C_INVLS];
     aux[al.off_consts + e] = v;
   }
+  if (gtid < 16) reinterpret_cast<int*>(aux + al.off_prog)[gtid] = 0;   // Cholesky hand-off counters
+  if (gtid == 0) p.info[0] = 0;
   const double tot = block_sum(klp, red);
   if (threadIdx.x == 0) aux[al.off_scratch + blockIdx.x] = tot;
 }
@@ -92,6 +94,13 @@ __device__ __forceinline__ void load_block(double* dst, const double* src, int l
   for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
     const int r = idx >> 6, c = idx & 63;
     dst[r * IWVI_LDS + c] = src[(size_t)r * ld + c];
+  }
+}
+// the same through L2 (data another CTA of the running grid has just published)
+__device__ __forceinline__ void load_block_cg(double* dst, const double* src, int ld, int tid) {
+  for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    dst[r * IWVI_LDS + c] = __ldcg(src + (size_t)r * ld + c);
   }
 }
 
@@ -109,7 +118,6 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   double* Dv = St + IWVI_STAGE_DOUBLES;             // [64][68] inverted diagonal block of the current column
   double* zi = Dv + IWVI_STAGE_DOUBLES;             // [64][ldz]
   double* zk = zi + IWVI_BLK * 36;                  // [64][ldz]
-  __shared__ int s_info;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -121,14 +129,22 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   const double jitter = d.jitter;
   double* Lm = p.Lm;
   double* Lmb = p.aux + al.off_lmb;   // block-major padded copies: L(i,k) for i > k, inverted diagonal blocks at (k,k)
-  if (tid == 0) s_info = 0;
-
-  for (int k = 0; k < NB; k++) {
+  // Dataflow schedule: CTA i owns block row i and forms its blocks (i,0) .. (i,i) left to right.  prog[r] counts the
+  // blocks row r has published; block (i,k) needs L(k,j), j < k (prog[k] >= j + 1) and, off the diagonal, the inverted
+  // diagonal block of row k (prog[k] >= k + 1).  All NB <= 8 CTAs are co-resident, and row i only ever waits for rows
+  // above it, so the waits cannot deadlock.  The critical path is the chain of diagonal blocks, not a serial sweep.
+  int* prog = reinterpret_cast<int*>(p.aux + al.off_prog);
+  const int i = blockIdx.x;
+  auto wait_row = [&](int row, int need) {
+    if (tid == 0) while (ld_acquire(prog + row) < need) {}
     __syncthreads();
-    for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zk[idx] = Zt[(size_t)k * IWVI_BLK * ldz + idx];
-    for (int i = k; i < NB; i++) {
+  };
+  for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zi[idx] = Zt[(size_t)i * IWVI_BLK * ldz + idx];
+
+  for (int k = 0; k <= i; k++) {
+    {
       __syncthreads();
-      for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zi[idx] = Zt[(size_t)i * IWVI_BLK * ldz + idx];
+      for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zk[idx] = Zt[(size_t)k * IWVI_BLK * ldz + idx];
       __syncthreads();
       // gram block (i,k) of Kuu + jitter I, identity on the padding
       double acc[4][2][2];
@@ -154,8 +170,9 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
       // left-looking update: -= sum_{j<k} L(i,j) L(k,j)^T
       for (int j = 0; j < k; j++) {
         __syncthreads();
+        if (k < i) wait_row(k, j + 1);      // L(k,j) is another row's block
         load_block(bufA, Lm + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
-        load_block(bufB, Lm + (size_t)(k * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
+        load_block_cg(bufB, Lm + (size_t)(k * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
         __syncthreads();
         double upd[4][2][2];
         acc_zero<4, 2>(upd);
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             }
             __syncthreads();
             const double djj = col[j];
-            if (tid == 0 && !(djj > 0.0) && s_info == 0) s_info = k * IWVI_BLK + j + 1;
+            if (tid == 0 && !(djj > 0.0)) atomicCAS(p.info, 0, k * IWVI_BLK + j + 1);
             const double rs = rsqrt(djj);          // one reciprocal square root serves the update and the scaling
             const double lr = col[row] * (rs * rs);
             if (row > j) {
@@ -278,7 +295,10 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             Lm[(size_t)(k * IWVI_BLK + r) * Mp + jb * IWVI_BLK + c] = 0.0;
           }
       } else {
-        // ---- L(i,k) = S(i,k) Dinv_k^T
+        // ---- L(i,k) = S(i,k) Dinv_k^T, with row k's inverted diagonal block fetched once it is published
+        wait_row(k, k + 1);
+        for (int idx = tid; idx < IWVI_STAGE_DOUBLES; idx += 256)
+          Dv[idx] = __ldcg(Lmb + (size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES + idx);
         __syncthreads();
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -303,13 +323,14 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             }
       }
     }
+    // publish block (i,k)
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release(prog + i, k + 1); }
   }
-  __syncthreads();
-  if (tid == 0) {
+  if (i == NB - 1 && tid == 0) {   // the last row depends on every other row: it finishes last
     double s = 0.0;
-    for (int i = 0; i < IWVI_PACK_GRID; i++) s += aux[al.off_scratch + i];
+    for (int q = 0; q < IWVI_PACK_GRID; q++) s += aux[al.off_scratch + q];
     p.kl[0] = 0.5 * (s - (double)M * (double)d.R);
-    p.info[0] = s_info;
   }
 }
 
@@ -603,7 +624,7 @@ template <int KIND>
 int launch_chol(const ProParams& p, int smem_bytes, cudaStream_t st) {
   if (cudaFuncSetAttribute(gp_chol_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
-  gp_chol_kernel<KIND><<<1, 256, smem_bytes, st>>>(p);
+  gp_chol_kernel<KIND><<<iwvi_round_up(p.d.M, IWVI_BLK) / IWVI_BLK, 256, smem_bytes, st>>>(p);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }

@@ -371,7 +371,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void normal_fill_kernel(double* out, int64_t f0, int64_t n, uint64_t seed) {
+// `state` (device, may be NULL): state[0] = optimiser steps completed so far.  With it the seed of the step being run is
+// derived on the device, seed = seed_base * C1 + (state[0] + 1 + step_add) * C2 + (layer + 1) * C3 (mod 2^64), the same
+// mix engine.layer_seed applies on the host -- so that a captured CUDA graph draws fresh noise on every replay.
+__global__ void normal_fill_kernel(double* out, int64_t f0, int64_t n, uint64_t seed, const int64_t* state, int64_t step_add,
+                                   int layer) {
+  if (state)
+    seed = seed * 0x9E3779B97F4A7C15ull + (uint64_t)(state[0] + 1 + step_add) * 0xBF58476D1CE4E5B9ull +
+           (uint64_t)(layer + 1) * 0x94D049BB133111EBull;
   const int64_t q0 = f0 >> 1, q1 = (f0 + n - 1) >> 1;
   for (int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= q1; q += (int64_t)gridDim.x * blockDim.x) {
     uint32_t r[4];
@@ -391,8 +398,15 @@ __global__ void normal_fill_kernel(double* out, int64_t f0, int64_t n, uint64_t 
 // ------------------------------------------------------------------------------------------------
 // Adam (+ positive transform)
 // ------------------------------------------------------------------------------------------------
+// `state` / `lr_dev` (device, may be NULL): step count and learning rate read on the device (CUDA-graph replay); then
+// lr_t is the plain learning rate and the bias correction is formed here from t = state[0] + 1.
 __global__ void adam_kernel(double* x, const double* g_elbo, double* m, double* v, const double* mask, double* theta_pos,
-                            int64_t n, int64_t n_pos, double lr_t, double b1, double b2, double eps) {
+                            int64_t n, int64_t n_pos, double lr_t, double b1, double b2, double eps, const int64_t* state,
+                            const double* lr_dev) {
+  if (state) {
+    const double t = (double)(state[0] + 1);
+    lr_t = lr_dev[0] * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double xi = x[i];
     double g = -g_elbo[i];                         // the optimiser minimises -ELBO
@@ -406,6 +420,7 @@ __global__ void adam_kernel(double* x, const double* g_elbo, double* m, double* 
     if (i < n_pos) theta_pos[i] = softplus_d(xi) + 1e-6;
   }
 }
+__global__ void step_counter_inc_kernel(int64_t* state) { state[0] += 1; }
 __global__ void positive_fwd_kernel(const double* x, double* theta, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     theta[i] = softplus_d(x[i]) + 1e-6;
@@ -523,7 +538,21 @@ extern "C" int iwvi_normal_fill(double* out, int64_t n_points, int32_t C, int64_
   const int64_t pairs = n / 2 + 2;
   int64_t nb = (pairs + 255) / 256;
   if (nb > 4 * 148) nb = 4 * 148;
-  normal_fill_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(out, first_point * C, n, seed);
+  normal_fill_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(out, first_point * C, n, seed, nullptr, 0, 0);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_normal_fill_counter(double* out, int64_t n_points, int32_t C, int64_t first_point, uint64_t seed_base,
+                                        int32_t layer, int64_t step_add, const int64_t* state, void* stream) {
+  if (!out || !state) return IWVI_ERR_NULL;
+  if (n_points < 0 || C < 1 || first_point < 0 || layer < 0) return IWVI_ERR_BAD_DESC;
+  const int64_t n = n_points * C;
+  if (n == 0) return IWVI_OK;
+  const int64_t pairs = n / 2 + 2;
+  int64_t nb = (pairs + 255) / 256;
+  if (nb > 4 * 148) nb = 4 * 148;
+  normal_fill_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(out, first_point * C, n, seed_base, state, step_add, layer);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }
@@ -546,7 +575,23 @@ extern "C" int iwvi_adam_step(double* x, const double* grad_elbo, double* m, dou
   int64_t nb = (n + 255) / 256;
   if (nb > 4 * 148) nb = 4 * 148;
   adam_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr_t, beta1,
-                                                        beta2, eps);
+                                                        beta2, eps, nullptr, nullptr);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_adam_step_counter(double* x, const double* grad_elbo, double* m, double* v, const double* mask,
+                                      double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1,
+                                      double beta2, double eps, int64_t* state, void* stream) {
+  if (!x || !grad_elbo || !m || !v || !lr || !state) return IWVI_ERR_NULL;
+  if (n_pos > 0 && !theta_pos) return IWVI_ERR_NULL;
+  if (n <= 0) return IWVI_ERR_BAD_DESC;
+  int64_t nb = (n + 255) / 256;
+  if (nb > 4 * 148) nb = 4 * 148;
+  adam_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, 0.0, beta1, beta2,
+                                                        eps, state, lr);
+  IWVI_CHECK_LAUNCH();
+  step_counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }

@@ -240,9 +240,11 @@ class Engine:
         else:                      # sample-major: point = s*B + n
             out.view(self.K, self.B, -1).copy_(A[None, :, :].expand(self.K, self.B, A.shape[1]))
 
-    def draw_noise(self, eps=None, seed=0, step=0, row0=0):
+    def draw_noise(self, eps=None, seed=0, step=0, row0=0, state=None):
         """eps: list with one entry per layer (None where no noise is consumed) of arrays shaped [*, C] in point
-        order, or None to draw counter-based noise keyed by (seed, step, layer) and the GLOBAL point index."""
+        order, or None to draw counter-based noise keyed by (seed, step, layer) and the GLOBAL point index.
+        state: optional int64 device tensor whose element 0 counts completed optimiser steps; the step is then read on
+        the device (step = state[0] + 1), which makes the call replayable inside a CUDA graph."""
         for r in self.recs:
             buf = r.get('eps')
             if buf is None:
@@ -250,11 +252,13 @@ class Engine:
             if eps is not None:
                 e = eps[r['idx']]
                 buf.copy_(torch.as_tensor(np.asarray(e), dtype=F64).reshape(buf.shape), non_blocking=True)
+                continue
+            first = int(row0) * self.K if self.mode == 'iw' else 0
+            step_add = 0 if self.mode == 'iw' else 7919 * int(row0)
+            if state is not None:
+                capi.normal_fill_counter(buf, self.T, buf.shape[1], first, seed, r['idx'], step_add, state)
             else:
-                if self.mode == 'iw':
-                    capi.normal_fill(buf, self.T, buf.shape[1], int(row0) * self.K, layer_seed(seed, step, r['idx']))
-                else:
-                    capi.normal_fill(buf, self.T, buf.shape[1], 0, layer_seed(seed, step + 7919 * int(row0), r['idx']))
+                capi.normal_fill(buf, self.T, buf.shape[1], first, layer_seed(seed, step + step_add, r['idx']))
 
     def forward(self):
         flat = self.flat

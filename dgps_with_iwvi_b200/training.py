@@ -24,8 +24,13 @@ def staircase_decay(base, step, decay_steps=1000, rate=0.98):
 
 
 class Trainer:
+    """use_graph=True (default): after two eager steps the whole step -- noise, forward, backward, optimiser -- is
+    captured ONCE as a CUDA graph and replayed; the step count and learning rate live in device memory
+    (iwvi_normal_fill_counter / iwvi_adam_step_counter) so every replay draws fresh noise and applies the right bias
+    correction.  With several ranks the NCCL all-reduce stays an eager call between two graphs."""
+
     def __init__(self, model, B_local, lr=5e-3, lr_decay=0.98, beta1=0.9, beta2=0.999, eps=1e-8, seed=0,
-                 process_group=None):
+                 process_group=None, use_graph=True):
         self.model = model
         self.pg = process_group
         self.distributed = dist.is_available() and dist.is_initialized()
@@ -41,20 +46,64 @@ class Trainer:
         self.betas, self.eps = (beta1, beta2), eps
         self.seed = seed
         self.t = 0
-        self.launches_per_step = None
+        dev = self.flat.device
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)          # [0] = optimiser steps completed
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float64, device=dev)
+        self._lr_host = float(lr)
+        self.use_graph = bool(use_graph)
+        self._graphs = None            # (graph_fwd_bwd, graph_update) once captured
+        self._graph_launches = 0
+        self._graph_row0 = None
+        self.eager_steps_before_capture = 2
+
+    # ---- the two halves of a step, written against device-side state only (capturable) ----
+    def _fwd_bwd(self, row0):
+        self.engine.draw_noise(None, seed=self.seed, row0=row0, state=self.state)
+        self.engine.forward()
+        self.engine.backward()
+
+    def _update(self):
+        f = self.flat
+        capi.adam_step_counter(f.x, f.g, self.m, self.v, f.mask, f.theta_pos, f.n, f.n_pos, self.lr_dev, self.betas[0],
+                               self.betas[1], self.eps, self.state)
+
+    def _capture(self, row0):
+        l0 = capi.LAUNCHES
+        torch.cuda.synchronize()
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            self._fwd_bwd(row0)
+        with torch.cuda.graph(gb, pool=ga.pool()):
+            self._update()
+        self._graphs = (ga, gb)
+        self._graph_launches = capi.LAUNCHES - l0
+        self._graph_row0 = row0
+        capi.LAUNCHES = l0             # capture launched nothing; replays are counted in step_device
 
     def step_device(self, X_local, Y_local, row0_global=None):
         """One training step on this rank's rows; returns the global ELBO as a 1-element device tensor (no sync)."""
         self.t += 1
         row0 = self.rank * self.B_local if row0_global is None else row0_global
-        self.engine.elbo_and_grads(X_local, Y_local, None, seed=self.seed, step=self.t, row0=row0)
+        lr = staircase_decay(self.lr, self.t - 1, 1000, self.lr_decay)
+        if lr != self._lr_host:
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
+        self.engine.set_batch(X_local, Y_local)
+        graph = self.use_graph and self.t > self.eager_steps_before_capture
+        if graph and (self._graphs is None or self._graph_row0 != row0):
+            self._capture(row0)
+        if graph:
+            self._graphs[0].replay()
+        else:
+            self._fwd_bwd(row0)
         if self.world_size > 1:
             dist.all_reduce(self.flat.g, op=dist.ReduceOp.SUM, group=self.pg)
-        f = self.flat
-        lr = staircase_decay(self.lr, self.t - 1, 1000, self.lr_decay)
-        capi.adam_step(f.x, f.g, self.m, self.v, f.mask, f.theta_pos, f.n, f.n_pos, lr, self.betas[0], self.betas[1],
-                       self.eps, self.t)
-        return f.loss_slot
+        if graph:
+            self._graphs[1].replay()
+            capi.LAUNCHES += self._graph_launches
+        else:
+            self._update()
+        return self.flat.loss_slot
 
     def step(self, X_host, Y_host):
         """End-to-end call: host (pinned) minibatch in, ELBO (python float) out."""

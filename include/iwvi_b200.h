@@ -206,6 +206,12 @@ int iwvi_iwelbo_bwd(const iwvi_elbo_desc* d, const double* fmean, const double* 
  * counter = ((first_point + p) * C + c) >> 1, lane (.. & 1) of a Box-Muller pair. */
 int iwvi_normal_fill(double* out, int64_t n_points, int32_t C, int64_t first_point, uint64_t seed, void* stream);
 
+/* The same with the step taken from DEVICE memory, so that a captured CUDA graph of the whole training step draws fresh
+ * noise on every replay: state[0] = optimiser steps completed so far (advanced by iwvi_adam_step_counter);
+ * seed = seed_base * 0x9E3779B97F4A7C15 + (state[0] + 1 + step_add) * 0xBF58476D1CE4E5B9 + (layer + 1) * 0x94D049BB133111EB. */
+int iwvi_normal_fill_counter(double* out, int64_t n_points, int32_t C, int64_t first_point, uint64_t seed_base,
+                             int32_t layer, int64_t step_add, const int64_t* state, void* stream);
+
 /* ---- optimiser step either side of the path (experiments/build_models.py:284-295) ----
  * gpflow.transforms.positive (Log1pe): theta = softplus(x) + 1e-6 for the first n entries. */
 int iwvi_positive_fwd(const double* x, double* theta, int64_t n, void* stream);
@@ -216,6 +222,12 @@ int iwvi_positive_fwd(const double* x, double* theta, int64_t n, void* stream);
 int iwvi_adam_step(double* x, const double* grad_elbo, double* m, double* v, const double* mask, double* theta_pos,
                    int64_t n, int64_t n_pos, double lr, double beta1, double beta2, double eps, int64_t t,
                    void* stream);
+
+/* iwvi_adam_step with the step count t = state[0] + 1 and the learning rate lr[0] read from DEVICE memory; increments
+ * state[0] afterwards (second, one-thread launch).  For CUDA-graph replay of the training step. */
+int iwvi_adam_step_counter(double* x, const double* grad_elbo, double* m, double* v, const double* mask,
+                           double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1, double beta2,
+                           double eps, int64_t* state, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
