@@ -91,17 +91,20 @@ __global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
 // ------------------------------------------------------------------------------------------------
 // copy a 64x64 block (row-major, leading dimension ld) from global into a padded shared stage
 __device__ __forceinline__ void load_block(double* dst, const double* src, int ld, int tid) {
-  for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    dst[r * IWVI_LDS + c] = src[(size_t)r * ld + c];
-  }
+  // all 16 loads of a thread are issued before the first store: one memory latency per block, not sixteen
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) v[q] = src[(size_t)((tid >> 6) + 4 * q) * ld + (tid & 63)];
+#pragma unroll
+  for (int q = 0; q < 16; q++) dst[((tid >> 6) + 4 * q) * IWVI_LDS + (tid & 63)] = v[q];
 }
 // the same through L2 (data another CTA of the running grid has just published)
 __device__ __forceinline__ void load_block_cg(double* dst, const double* src, int ld, int tid) {
-  for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    dst[r * IWVI_LDS + c] = __ldcg(src + (size_t)r * ld + c);
-  }
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) v[q] = __ldcg(src + (size_t)((tid >> 6) + 4 * q) * ld + (tid & 63));
+#pragma unroll
+  for (int q = 0; q < 16; q++) dst[((tid >> 6) + 4 * q) * IWVI_LDS + (tid & 63)] = v[q];
 }
 
 template <int KIND>
@@ -498,20 +501,36 @@ __global__ void __launch_bounds__(256) pbwd_gram_kernel(const PbwdParams p) {
   const double variance = consts[IWVI_C_VARIANCE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 8 + warp;
+  // the scaled inducing inputs are staged once per CTA (row stride ldz + 1: conflict-free for lanes = consecutive rows)
+  extern __shared__ __align__(16) double zs[];
+  const int lds = ldz + 1;
+  for (int idx = threadIdx.x; idx < Mp * ldz; idx += 256) zs[(idx / ldz) * lds + idx % ldz] = Zt[idx];
+  __syncthreads();
   if (i < Mp) {
     double dz[IWVI_MAX_D], dl[IWVI_MAX_D];
 #pragma unroll
     for (int k = 0; k < IWVI_MAX_D; k++) { dz[k] = 0.0; dl[k] = 0.0; }
     double dv = 0.0;
     if (i < M) {
-      const double* zi = Zt + (size_t)i * ldz;
-      for (int j = lane; j < M; j += 32) {
-        const double* zj = Zt + (size_t)j * ldz;
-        const double kb = 0.5 * (Kp[(size_t)i * Mp + j] + Kp[(size_t)j * Mp + i]);
+      const double* zi = zs + (size_t)i * lds;
+      // symmetrised cotangent of this row, all loads in flight at once (M <= 512: at most 16 per lane)
+      double kbv[IWVI_MAX_M / 32];
+#pragma unroll
+      for (int q = 0; q < IWVI_MAX_M / 32; q++) {
+        const int j = lane + 32 * q;
+        kbv[q] = (j < M) ? 0.5 * (Kp[(size_t)i * Mp + j] + Kp[(size_t)j * Mp + i]) : 0.0;
+      }
+      const double zni = zn[i];
+#pragma unroll
+      for (int q = 0; q < IWVI_MAX_M / 32; q++) {
+        const int j = lane + 32 * q;
+        if (j >= M) break;
+        const double* zj = zs + (size_t)j * lds;
+        const double kb = kbv[q];
         double dot = 0.0;
         for (int k = 0; k < D; k++) dot += zi[k] * zj[k];
         double K, dK;
-        kern_k_dk(d.kern, zn[i] + zn[j] - 2.0 * dot, variance, K, dK);
+        kern_k_dk(d.kern, zni + zn[j] - 2.0 * dot, variance, K, dK);
         dv += kb * K;
         if (j != i) {
           const double G = kb * dK;
@@ -701,7 +720,12 @@ extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, con
   IWVI_CHECK_LAUNCH();
   pbwd_solve_kernel<1><<<al.Mp / PS_TP, 256, smem_bytes, st>>>(p, ws + wl.off_s1, ws + wl.off_p);
   IWVI_CHECK_LAUNCH();
-  pbwd_gram_kernel<<<(al.Mp + 7) / 8, 256, 0, st>>>(p);
+  {
+    const int gram_smem = al.Mp * (al.ldz + 1) * 8;
+    if (cudaFuncSetAttribute(pbwd_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem) != cudaSuccess)
+      return IWVI_ERR_LAUNCH;
+    pbwd_gram_kernel<<<(al.Mp + 7) / 8, 256, gram_smem, st>>>(p);
+  }
   IWVI_CHECK_LAUNCH();
   {
     const int n_all = d->R * d->M * d->M + d->M * d->R;

@@ -157,14 +157,34 @@ __global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
       gvb[pt * IWVI_MAX_R + r] = gv_;
     }
   }
-  // mean-function part of dX (the gram part is added by the tile kernel)
-  for (int idx = tid; idx < npts * D; idx += 256) {
-    const int n = idx / D, k = idx - n * D;
-    double v = 0.0;
-    if (d.mf == IWVI_MF_IDENTITY) v = ds[n][k] + dm[n][k];
-    else if (d.mf == IWVI_MF_LINEAR)
-      for (int q = 0; q < P; q++) v += (ds[n][q] + dm[n][q]) * p.mfA[k * P + q];
-    p.dX[(size_t)p0 * D + idx] = v;
+  // mean-function part of dX (the gram part is added by the tile kernel): Identity copies, Linear is the skinny product
+  // (d_sample + d_mean) [32, P] x mfA^T [P, D] on the tensor pipe, one 8-point row tile per warp
+  if (d.mf == IWVI_MF_LINEAR) {
+    if (tid < 128) {
+      const int lane = tid & 31, g = lane >> 2, t = lane & 3, n = (tid >> 5) * 8 + g;
+      double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      for (int q0 = 0; q0 < P; q0 += 4) {
+        const int q = q0 + t;
+        const double a = (q < P) ? ds[n][q] + dm[n][q] : 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int k = b * 8 + g;
+          dmma884(acc[b], a, (k < D && q < P) ? p.mfA[k * P + q] : 0.0);
+        }
+      }
+      if (n < npts) {
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            if (b * 8 + 2 * t + c < D) p.dX[((size_t)p0 + n) * D + b * 8 + 2 * t + c] = acc[b][c];
+      }
+    }
+  } else {
+    for (int idx = tid; idx < npts * D; idx += 256) {
+      const int n = idx / D, k = idx - n * D;
+      p.dX[(size_t)p0 * D + idx] = (d.mf == IWVI_MF_IDENTITY) ? ds[n][k] + dm[n][k] : 0.0;
+    }
   }
   double* part = p.ws + p.wl.off_epi + (size_t)blockIdx.x * EPI_STRIDE;
   const double tot = block_sum(gv_sum, red);
