@@ -513,20 +513,14 @@ __global__ void __launch_bounds__(256) pbwd_gram_kernel(const PbwdParams p) {
     double dv = 0.0;
     if (i < M) {
       const double* zi = zs + (size_t)i * lds;
-      // symmetrised cotangent of this row, all loads in flight at once (M <= 512: at most 16 per lane)
-      double kbv[IWVI_MAX_M / 32];
-#pragma unroll
-      for (int q = 0; q < IWVI_MAX_M / 32; q++) {
-        const int j = lane + 32 * q;
-        kbv[q] = (j < M) ? 0.5 * (Kp[(size_t)i * Mp + j] + Kp[(size_t)j * Mp + i]) : 0.0;
-      }
+      // symmetrised cotangent of this row; the next element's two loads are issued before the current one is used
+      auto load_kb = [&](int j) { return (j < M) ? 0.5 * (Kp[(size_t)i * Mp + j] + Kp[(size_t)j * Mp + i]) : 0.0; };
       const double zni = zn[i];
-#pragma unroll
-      for (int q = 0; q < IWVI_MAX_M / 32; q++) {
-        const int j = lane + 32 * q;
-        if (j >= M) break;
+      double kb_next = load_kb(lane);
+      for (int j = lane; j < M; j += 32) {
+        const double kb = kb_next;
+        kb_next = load_kb(j + 32);
         const double* zj = zs + (size_t)j * lds;
-        const double kb = kbv[q];
         double dot = 0.0;
         for (int k = 0; k < D; k++) dot += zi[k] * zj[k];
         double K, dK;

@@ -26,6 +26,7 @@ template <int TP> struct TileCfg {
   static constexpr int TN = WN / 8;
 };
 
+#define RED_NST 6          // ring depth of the reduce kernel: two stages per 64-point chunk step, three steps in flight
 #define EPI_STRIDE 1344   // >= P*R + D*P + P + 1 at the maxima (32*8 + 32*32 + 32 + 1 = 1313)
 #define EPI_PTS 32
 #define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
@@ -753,7 +754,7 @@ struct RedSeq {
 struct ReduceLoopArgs { const double *gvb, *gmb; int q; bool is_lm; int c0, c1, wm0, wn0, lane; };
 
 template <bool QMU>
-__device__ __forceinline__ void reduce_loop(RingT<4>& pipe, const ReduceLoopArgs& la, double (&acc)[4][2][2],
+__device__ __forceinline__ void reduce_loop(RingT<RED_NST>& pipe, const ReduceLoopArgs& la, double (&acc)[4][2][2],
                                             double (&accq)[4][2]) {
   const int g = la.lane >> 2, t = la.lane & 3;
   // per-point scale factors of this lane's k indices (k = 4*ks + t), prefetched one chunk ahead so that their
@@ -801,7 +802,7 @@ __device__ __forceinline__ void reduce_loop(RingT<4>& pipe, const ReduceLoopArgs
 // end: 72 instead of 128 DMMAs per warp per chunk, evenly spread over the four SM sub-partitions.  The per-point scale
 // multiplies the two A fragments (2 DMULs per k-step) instead of the up-to-8 B fragments.
 template <int WQ, bool QMU>
-__device__ __forceinline__ void reduce_diag(RingT<4>& pipe, const ReduceLoopArgs& la, int warp, double* scratch,
+__device__ __forceinline__ void reduce_diag(RingT<RED_NST>& pipe, const ReduceLoopArgs& la, int warp, double* scratch,
                                             double* out, double* oq) {
   const int g = la.lane >> 2, t = la.lane & 3;
   const int half = warp >> 2;
@@ -875,7 +876,6 @@ __device__ __forceinline__ void reduce_diag(RingT<4>& pipe, const ReduceLoopArgs
   }
 }
 
-#define RED_NST 4
 #define RED_THREADS 288   // 8 consumer warps + 1 producer warp
 __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) double smem[];
