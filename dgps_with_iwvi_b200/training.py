@@ -7,6 +7,7 @@ import torch
 import torch.distributed as dist
 
 from . import capi
+from . import natgrad as NG
 from .engine import FlatParams
 
 
@@ -108,3 +109,45 @@ class Trainer:
     def step(self, X_host, Y_host):
         """End-to-end call: host (pinned) minibatch in, ELBO (python float) out."""
         return float(self.step_device(X_host, Y_host).item())
+
+
+class ReferenceIterationTrainer(Trainer):
+    """The reference's full training iteration (experiments/build_models.py:284-300): a natural-gradient step with rate
+    gamma on the LAST GP layer's (q_mu, q_sqrt) evaluated on one minibatch, then an Adam step on every other trainable
+    parameter evaluated on a second minibatch with fresh noise; both rates decay by `decay` every 1000 iterations
+    (staircase).  Two ELBO forward+backward passes per iteration, as in the reference."""
+
+    def __init__(self, model, B_local, lr=5e-3, gamma=1e-2, lr_decay=0.98, gamma_decay=0.98, **kw):
+        from .layers import GPLayer
+        last = [l for l in model.layers if isinstance(l, GPLayer)][-1]
+        last.q_mu.set_trainable(False)          # handed to the natural-gradient optimiser (build_models.py:284-287)
+        last.q_sqrt.set_trainable(False)
+        kw['use_graph'] = False
+        super().__init__(model, B_local, lr=lr, lr_decay=lr_decay, **kw)
+        self.ng_layer = last
+        self.gamma, self.gamma_decay = gamma, gamma_decay
+        self.it = 0
+
+    NG_STEP_BASE = 1 << 40   # noise-step offset of the NatGrad evaluations: never collides with the Adam evaluations
+
+    def iteration(self, X1, Y1, X2, Y2):
+        """Returns (ELBO of the NatGrad evaluation, ELBO of the Adam evaluation) as 1-element device tensors."""
+        f, layer = self.flat, self.ng_layer
+        row0 = self.rank * self.B_local
+        # ---- NatGrad half
+        self.engine.set_batch(X1, Y1)
+        self.engine.draw_noise(None, seed=self.seed, step=self.NG_STEP_BASE + self.it, row0=row0)
+        self.engine.forward()
+        self.engine.backward()
+        if self.world_size > 1:
+            dist.all_reduce(f.g, op=dist.ReduceOp.SUM, group=self.pg)
+        elbo_ng = f.loss_slot.clone()
+        gamma = staircase_decay(self.gamma, self.it, 1000, self.gamma_decay)
+        mu_new, L_new = NG.natgrad_step(f.cview(layer.q_mu), f.cview(layer.q_sqrt), f.gview(layer.q_mu),
+                                        f.gview(layer.q_sqrt), gamma)
+        f.cview(layer.q_mu).copy_(mu_new)       # both are stored untransformed (q_sqrt: full array, tril on read)
+        f.cview(layer.q_sqrt).copy_(L_new)
+        # ---- Adam half (its own minibatch and noise); Trainer.step_device advances the step counter
+        elbo_adam = self.step_device(X2, Y2)
+        self.it += 1
+        return elbo_ng, elbo_adam

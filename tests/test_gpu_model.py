@@ -176,3 +176,46 @@ def test_trainer_cuda_graph_matches_eager():
     assert t0 == t1 == 6
     assert len(set(l1)) == 6 and l0 == l1, (l0, l1)
     assert torch.equal(x0, x1)
+
+
+def test_reference_iteration_natgrad_then_adam():
+    """Row f3: one reference-style iteration (NatGrad on the last layer's q(u), then Adam on the rest, two minibatches,
+    fresh noise each) against the oracle: the counter-based noise is regenerated with the numpy Philox restatement."""
+    from dgps_with_iwvi_b200.engine import FlatParams, layer_seed
+    from dgps_with_iwvi_b200.training import ReferenceIterationTrainer
+    from oracle import natgrad_oracle as NO
+    from oracle import philox_np
+    N, D, M, K, B = 90, 3, 21, 4, 30
+    X, Y = S.make_data(N, D, seed=61)
+    spec = S.make_spec(X, 'L1_G2', M, K, seed=61, perturb=0.3, inner_q_sqrt_scale=0.3)
+    m = _model(spec, X, Y)
+    tr = ReferenceIterationTrainer(m, B, lr=1e-2, gamma=0.3, seed=17)
+    X1, Y1, X2, Y2 = X[:B], Y[:B], X[B:2 * B], Y[B:2 * B]
+    e_ng, e_adam = tr.iteration(X1, Y1, X2, Y2)
+    tr.engine.check_info()
+
+    def noise(step):
+        out = []
+        for li, ls in enumerate(spec['layers']):
+            C = ls['latent_dim'] if ls['type'] == 'lv' else (ls['q_mu'].shape[1] if li < len(spec['layers']) - 1 else 0)
+            out.append(None if C == 0 else philox_np.normal(B * K, C, 0, layer_seed(17, step, li)).reshape(B, K, C))
+        return out
+    # NatGrad half
+    e1, g1 = O.iw_elbo_and_grads(spec, X1, Y1, noise(ReferenceIterationTrainer.NG_STEP_BASE))
+    assert abs(e_ng.item() - e1.item()) < RTOL * abs(e1.item())
+    last = len(spec['layers']) - 1
+    mu_new, L_new = NO.natgrad_step(spec['layers'][last]['q_mu'], spec['layers'][last]['q_sqrt'],
+                                    g1['layers.%d.q_mu' % last], g1['layers.%d.q_sqrt' % last], 0.3)
+    np.testing.assert_allclose(m.layers[last].q_mu.read_value(), mu_new.numpy(), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(np.tril(m.layers[last].q_sqrt.read_value()), L_new.numpy(), rtol=1e-8, atol=1e-10)
+    # Adam half: evaluated at the updated q(u), on the second minibatch, with the noise of optimiser step 1
+    spec2 = dict(spec, layers=[dict(l) for l in spec['layers']])
+    spec2['layers'][last]['q_mu'], spec2['layers'][last]['q_sqrt'] = mu_new.numpy(), L_new.numpy()
+    e2, g2 = O.iw_elbo_and_grads(spec2, X2, Y2, noise(1))
+    assert abs(e_adam.item() - e2.item()) < RTOL * abs(e2.item())
+    got = {k: v.cpu().numpy() for k, v in FlatParams.of(m).grads_by_name().items()}
+    H.assert_grads_close(got, {k: v.numpy() for k, v in g2.items()}, RTOL, 'adam half')
+    # the NatGrad-owned parameters are frozen for Adam; everything else moved
+    z0 = spec['layers'][1]['Z']
+    assert np.abs(m.layers[1].feature.feat.Z.read_value() - z0).max() > 1e-4
+    np.testing.assert_allclose(m.layers[last].q_mu.read_value(), mu_new.numpy(), rtol=1e-8, atol=1e-10)

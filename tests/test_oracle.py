@@ -215,3 +215,35 @@ def _functional_iw(spec, vals, X, Y, eps):
     model = O.DGP(layers, get('likelihood.variance', spec['lik_variance']), spec['num_data'],
                   spec['num_samples'])
     return model.iw_likelihood(T(X), T(Y), eps)
+
+
+def test_natgrad_conjugate_model_reaches_optimum_in_one_step():
+    """Row f3 (experiments/build_models.py:284-300): for a single GP layer with a Gaussian likelihood the bound is
+    conjugate in q(u), so ONE natural-gradient step with gamma = 1 from any start lands on the optimal whitened
+    posterior S* = (I + A A^T / s2)^-1, mu* = S* A (y - mf) / s2, A = Lm^-1 Kuf -- a closed form independent of the
+    natural-gradient code.  Also: the closed-form chain rule used by the product equals the autograd restatement."""
+    import scipy.linalg as sla
+    from dgps_with_iwvi_b200 import natgrad as NG
+    from oracle import natgrad_oracle as NO
+    from oracle import svgp_closed_form as SV
+    N, D, M = 80, 2, 17
+    X, Y = S.make_data(N, D, seed=9)
+    spec = S.make_spec(X, '', M, 1, seed=9, perturb=0.5, kern='Matern32', final_mf='Linear', lik_variance=0.3)
+    spec['num_data'] = N
+    g = spec['layers'][0]
+    _, grads = O.vi_elbo_and_grads(spec, X, Y, [None])
+    mu1, L1 = NO.natgrad_step(g['q_mu'], g['q_sqrt'], grads['layers.0.q_mu'], grads['layers.0.q_sqrt'], 1.0)
+    mu2, L2 = NG.natgrad_step(torch.as_tensor(g['q_mu']), torch.as_tensor(g['q_sqrt']), grads['layers.0.q_mu'],
+                              grads['layers.0.q_sqrt'], 1.0)
+    np.testing.assert_allclose(mu2.numpy(), mu1.numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(L2.numpy(), L1.numpy(), rtol=1e-9, atol=1e-11)
+    Kuu = SV.kernel(g['kern'], g['Z'], g['Z'], g['variance'], g['lengthscales']) + 1e-6 * np.eye(M)
+    Kuf = SV.kernel(g['kern'], g['Z'], X, g['variance'], g['lengthscales'])
+    Lm = np.linalg.cholesky(Kuu)
+    A = sla.solve_triangular(Lm, Kuf, lower=True)
+    s2 = float(spec['lik_variance'])
+    S_opt = np.linalg.inv(np.eye(M) + A @ A.T / s2)
+    resid = Y - (X @ g['mf_A'] + g['mf_b'])
+    mu_opt = S_opt @ A @ resid / s2
+    np.testing.assert_allclose(mu1.numpy(), mu_opt, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose((L1[0] @ L1[0].t()).numpy(), S_opt, rtol=1e-7, atol=1e-10)
