@@ -50,16 +50,20 @@ def model_from_spec(spec, X, Y, mode='iw', minibatch_size=None):
 
 
 def build_model(X, Y, configuration='L1_G5_G5', M=128, num_IW_samples=5, minibatch_size=512, likelihood_variance=1e-2,
-                mode='IWAE', fix_linear=True, Z=None, seed=0):
+                mode='IWAE', fix_linear=True, Z=None, seed=0, init='subset'):
     """experiments/build_models.py:146-287 for mode in {'IWAE', 'VI'}.  Z: [M, DX] initial inducing inputs (the
-    reference runs scipy kmeans2 on X, :179-183; pass its result here, or leave None for a random subset of rows)."""
+    reference runs scipy kmeans2 on X, :179-183).  Z=None: init='kmeans' does the same (scipy.cluster.vq.kmeans2 with
+    minit='points', host side, seconds at N=100k), init='subset' takes a random subset of rows (benchmarks)."""
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)
     N, DX = X.shape
     DY = Y.shape[1]
     rng = np.random.default_rng(seed)
     if Z is None:
-        if N > M:
+        if N > M and init == 'kmeans':
+            from scipy.cluster.vq import kmeans2
+            Z = kmeans2(X, M, minit='points', seed=seed)[0]
+        elif N > M:
             Z = X[rng.choice(N, M, replace=False)]
         else:
             Z = np.concatenate([X, rng.standard_normal((M - N, DX))], 0)
