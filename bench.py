@@ -401,7 +401,7 @@ def kernel_timings(eng, capi, LIB, torch, reps=5):
         capi.gp_rows_bwd(d, r['Lm'], r['aux'], r['save'], r['Fin'], W, mfA, mfb, r['eps'],
                          d_s if r['sampled'] else None, None if r['sampled'] else d_s, None if r['sampled'] else d_s,
                          r['dX'], scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], r['dLm'], dW, dA, db,
-                         eng.bwd_ws)
+                         r['bwd_ws'])
 
     bwd(0)
     cases = [

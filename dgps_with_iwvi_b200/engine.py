@@ -189,6 +189,8 @@ class Engine:
                     r['dX'] = z(T, D)
                     r['dls_vec'] = None if r['ard'] else z(D)
                     max_bwd_ws = max(max_bwd_ws, capi.gp_bwd_ws_doubles(d))
+                    r['bwd_ws'] = z(capi.gp_bwd_ws_doubles(d))    # per layer: the parameter reductions of layer l run on
+                    #                                               its side stream while layer l-1's tile kernel runs
                     r['pbwd_ws'] = z(capi.gp_pbwd_ws_doubles(d))   # per layer: prologue adjoints overlap on side streams
                 gi += 1
                 D_cur = P
@@ -207,7 +209,6 @@ class Engine:
             self.kl_cat = z(T, self.Lw_total) if len(self.lv_recs) > 1 else None
             self.dmean, self.dvar = z(T, self.Dy), z(T, self.Dy)
             self.dkl_local = z(T, self.Lw_total) if self.Lw_total else None
-            self.bwd_ws = z(max(max_bwd_ws, 1))
             self.lv_ws = z(max(max_lv_ws, 1))
         # once-per-layer prologue stages (Cholesky, KL and their adjoints) depend only on the parameters: they run on
         # side streams, concurrently with each other and with the per-point stages of other layers
@@ -353,16 +354,23 @@ class Engine:
                 gW = flat.gview(layer.kern.W) if (r['mix'] and layer.kern.W.trainable) else None
                 gA = flat.gview(layer.mean_function.A) if (lin and layer.mean_function.A.trainable) else None
                 gb = flat.gview(layer.mean_function.b) if (lin and layer.mean_function.b.trainable) else None
-                capi.gp_rows_bwd(r['d'], r['Lm'], r['aux'], r['save'], r['Fin'], W, mfA, mfb, r['eps'],
-                                 d_next if r['sampled'] else None,
-                                 self.dmean if is_last else None, self.dvar if is_last else None,
-                                 r['dX'], outs[0], outs[1], outs[2], outs[3], outs[4], r['dLm'], gW, gA, gb, self.bwd_ws)
+                # The per-point half (epilogue adjoint + tile kernel: dX for the layer below, Bbar, per-CTA partials) runs on
+                # the main stream; the parameter half (split-K reductions over the points, fixed-order sums, then the
+                # Cholesky / gram adjoint) follows on the layer's side stream, where it overlaps with the tile kernel of the
+                # layer below -- each fills the SMs the other leaves idle in its last wave.
+                args = (r['Lm'], r['aux'], r['save'], r['Fin'], W, mfA, mfb, r['eps'],
+                        d_next if r['sampled'] else None,
+                        self.dmean if is_last else None, self.dvar if is_last else None,
+                        r['dX'], outs[0], outs[1], outs[2], outs[3], outs[4], r['dLm'], gW, gA, gb, r['bwd_ws'])
+                fl = r['d'].flags
+                capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE), *args)
                 main = torch.cuda.current_stream()
                 gi = r['gi']
                 self.ev_rows[gi].record(main)
                 side = self.side[gi]
                 side.wait_event(self.ev_rows[gi])
                 with torch.cuda.stream(side):
+                    capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL), *args)
                     capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), r['Lm'], r['aux'], self._cv(feat.Z),
                                          r['ls'], self._cv(base.variance), self._cv(layer.q_mu),
                                          self._cv(layer.q_sqrt), r['dLm'], self.dkl, outs[0], outs[1], outs[2],

@@ -63,8 +63,10 @@ extern "C" {
 #define IWVI_FLAG_SAMPLE 1  /* eps given: produce sample = mean + eps*sqrt(var) (temp_workaround.py:89-91) */
 #define IWVI_FLAG_SAVE   2  /* keep A, U, latent mean/var for the backward pass */
 #define IWVI_FLAG_ACCUM  4  /* iwvi_gp_prologue_bwd adds into its outputs instead of overwriting them */
-/* measurement aid for iwvi_gp_rows_bwd: when any of these is set only the selected kernels of its four-launch
- * sequence run (on buffers a complete call has already filled), so each can be timed alone with CUDA events */
+/* iwvi_gp_rows_bwd is a four-launch sequence (epilogue adjoint, tile kernel, split-K reduce, finalize).  When any of
+ * these is set only the selected launches run, on the buffers the earlier ones have filled: used to time each alone,
+ * and by the host to run EPI|TILE (dX, Bbar, per-CTA partials) on one stream and REDUCE|FINAL (every parameter
+ * gradient) on another, so that the reductions of one layer overlap with the tile kernel of the layer below. */
 #define IWVI_FLAG_ONLY_EPI    16
 #define IWVI_FLAG_ONLY_TILE   32
 #define IWVI_FLAG_ONLY_REDUCE 64
