@@ -188,9 +188,10 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             for (int c = 0; c < 2; c++) acc[a][b][c] -= upd[a][b][c];
       }
       if (i == k) {
-        // ---- diagonal block: factorise with the trailing matrix held in REGISTERS (thread (row, cg) owns the
-        //      entries (row, cg + 4q), q < 16, of the lower triangle), one block barrier per column; then invert by
-        //      recursive doubling (8 -> 16 -> 32 -> 64) with DMMA tile products.
+        // ---- diagonal block: right-looking factorisation in shared memory with 8-wide panels -- (1) one warp factors the
+        //      8x8 pivot block (the only strictly serial part: 8 dependent reciprocal square roots), (2) one thread per
+        //      row below solves its 8 entries against it, (3) the trailing matrix gets its rank-8 update as 8x8x4 DMMA
+        //      tiles -- then inversion by recursive doubling (8 -> 16 -> 32 -> 64) with DMMA tile products.
         __syncthreads();
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -200,46 +201,63 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             for (int c = 0; c < 2; c++)
               S[(wm0 + a * 8 + g) * IWVI_LDS + wn0 + b * 8 + 2 * t + c] = acc[a][b][c];
         __syncthreads();
-        {
-          const int row = tid & 63, cg = tid >> 6;
-          double e[16];
-#pragma unroll
-          for (int q = 0; q < 16; q++) e[q] = S[row * IWVI_LDS + cg + 4 * q];
-          double* colb = St;   // [2][64] column exchange buffer (double buffered: one barrier per step)
-#pragma unroll
-          for (int j = 0; j < IWVI_BLK; j++) {   // fully unrolled: the owner's register index j >> 2 is a constant
-            double* col = colb + (j & 1) * IWVI_BLK;
-            const int qj = j >> 2;
-            const bool owner = (cg == (j & 3)) && row >= j;
-            if (owner) {
-              double v = 0.0;
-#pragma unroll
-              for (int q = 0; q < 16; q++) if (q == qj) v = e[q];
-              col[row] = v;
-            }
-            __syncthreads();
-            const double djj = col[j];
-            if (tid == 0 && !(djj > 0.0)) atomicCAS(p.info, 0, k * IWVI_BLK + j + 1);
-            const double rs = rsqrt(djj);          // one reciprocal square root serves the update and the scaling
-            const double lr = col[row] * (rs * rs);
-            if (row > j) {
-#pragma unroll
-              for (int q = 0; q < 16; q++) {
-                const int c = cg + 4 * q;
-                if (c > j && c <= row) e[q] -= lr * col[c];
-              }
-            }
-            if (owner) {
-#pragma unroll
-              for (int q = 0; q < 16; q++) if (q == qj) e[q] *= rs;
+        double* rdiag = St;                               // [64] reciprocals of the diagonal of L(k,k)
+        for (int p0 = 0; p0 < IWVI_BLK; p0 += 8) {
+          double* P = S + p0 * IWVI_LDS + p0;             // pivot block corner
+          if (warp == 0) {
+            const int r = lane & 7, cq = lane >> 3;        // lane handles (r, cq) and (r, cq + 4) of the 8x8 block
+            for (int j = 0; j < 8; j++) {
+              const double dj = P[j * IWVI_LDS + j];
+              if (lane == 0 && !(dj > 0.0)) atomicCAS(p.info, 0, k * IWVI_BLK + p0 + j + 1);
+              const double rs = rsqrt(dj);
+              const double lrj = P[r * IWVI_LDS + j] * rs;               // L(r, j) for r >= j (r == j: sqrt(dj))
+              const double lc0 = P[cq * IWVI_LDS + j] * rs, lc1 = P[(cq + 4) * IWVI_LDS + j] * rs;
+              __syncwarp();
+              if (cq == (j & 3) && r >= j) P[r * IWVI_LDS + j] = lrj;    // column j final (one lane per row)
+              if (lane == 0) rdiag[p0 + j] = rs;                         // 1 / L(j,j): divisions below become products
+              if (cq > j && r >= cq) P[r * IWVI_LDS + cq] -= lrj * lc0;
+              if (cq + 4 > j && r >= cq + 4) P[r * IWVI_LDS + cq + 4] -= lrj * lc1;
+              __syncwarp();
             }
           }
           __syncthreads();
-          // L(k,k): row-major copy in S (upper part zero) and to global; Dv := 0
+          const int nb = IWVI_BLK - p0 - 8;                // rows below the pivot block
+          if (tid < nb) {                                  // (2) row i of the panel: x L11^T = s
+            double* rowp = S + (p0 + 8 + tid) * IWVI_LDS + p0;
+            double x[8];
 #pragma unroll
-          for (int q = 0; q < 16; q++) {
-            const int c = cg + 4 * q;
-            const double v = (c <= row) ? e[q] : 0.0;
+            for (int c = 0; c < 8; c++) {
+              double s_ = rowp[c];
+#pragma unroll
+              for (int q = 0; q < 8; q++)
+                if (q < c) s_ -= x[q] * P[c * IWVI_LDS + q];
+              x[c] = s_ * rdiag[p0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) rowp[c] = x[c];
+          }
+          __syncthreads();
+          // (3) trailing update, lower 8x8 tiles only: S22 -= X X^T  (X = the panel just solved, K = 8: two DMMAs per tile)
+          const int nt = nb >> 3;
+          for (int tl = warp; tl < nt * (nt + 1) / 2; tl += 8) {
+            int ti = 0;
+            while ((ti + 1) * (ti + 2) / 2 <= tl) ti++;
+            const int tj = tl - ti * (ti + 1) / 2;
+            const double* Xi = S + (p0 + 8 + ti * 8) * IWVI_LDS + p0;
+            const double* Xj = S + (p0 + 8 + tj * 8) * IWVI_LDS + p0;
+            double* Cc = S + (p0 + 8 + ti * 8 + g) * IWVI_LDS + p0 + 8 + tj * 8 + 2 * t;
+            double c2[2] = {-Cc[0], -Cc[1]};
+            dmma884(c2, Xi[g * IWVI_LDS + t], Xj[g * IWVI_LDS + t]);
+            dmma884(c2, Xi[g * IWVI_LDS + 4 + t], Xj[g * IWVI_LDS + 4 + t]);
+            Cc[0] = -c2[0]; Cc[1] = -c2[1];
+          }
+          __syncthreads();
+        }
+        {
+          // L(k,k): zero the upper part of S, copy to global; Dv := 0
+          for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
+            const int row = idx >> 6, c = idx & 63;
+            const double v = (c <= row) ? S[row * IWVI_LDS + c] : 0.0;
             S[row * IWVI_LDS + c] = v;
             Lm[(size_t)(k * IWVI_BLK + row) * Mp + k * IWVI_BLK + c] = v;
           }
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
 #pragma unroll
             for (int j = 0; j < 8; j++)
               if (j < i2) s_ -= S[(b0 + i2) * IWVI_LDS + b0 + j] * x[j];
-            x[i2] = (i2 < c) ? 0.0 : s_ / S[(b0 + i2) * IWVI_LDS + b0 + i2];
+            x[i2] = (i2 < c) ? 0.0 : s_ * rdiag[b0 + i2];
           }
 #pragma unroll
           for (int i2 = 0; i2 < 8; i2++) Dv[(b0 + i2) * IWVI_LDS + b0 + c] = x[i2];
@@ -300,8 +318,14 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
       } else {
         // ---- L(i,k) = S(i,k) Dinv_k^T, with row k's inverted diagonal block fetched once it is published
         wait_row(k, k + 1);
-        for (int idx = tid; idx < IWVI_STAGE_DOUBLES; idx += 256)
-          Dv[idx] = __ldcg(Lmb + (size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES + idx);
+        {
+          const double* src = Lmb + (size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES;
+          double v[IWVI_STAGE_DOUBLES / 256];                        // 17 loads in flight per thread
+#pragma unroll
+          for (int q = 0; q < IWVI_STAGE_DOUBLES / 256; q++) v[q] = __ldcg(src + tid + 256 * q);
+#pragma unroll
+          for (int q = 0; q < IWVI_STAGE_DOUBLES / 256; q++) Dv[tid + 256 * q] = v[q];
+        }
         __syncthreads();
 #pragma unroll
         for (int a = 0; a < 4; a++)
