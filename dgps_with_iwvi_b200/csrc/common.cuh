@@ -513,7 +513,7 @@ int iwvi_check_gp_desc(const iwvi_gp_desc* d);
 // Optional phase timing (tools/phase_timing.py builds a second library with -DIWVI_PHASE_TIMING): thread 0 of every CTA
 // accumulates clock64() deltas per phase; the totals land in a device array read back through iwvi_debug_phase_cycles.
 #ifdef IWVI_PHASE_TIMING
-extern __device__ unsigned long long iwvi_phase_cycles[2][16];
+extern __device__ unsigned long long iwvi_phase_cycles[3][16];
 #define PHASE_DECL long long ph_t_ = clock64(); long long ph_acc_[16] = {0}
 #define PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); ph_acc_[k] += now_ - ph_t_; ph_t_ = now_; } } while (0)
 #define PHASE_FLUSH(kern) do { if (threadIdx.x == 0) for (int k_ = 0; k_ < 16; k_++) atomicAdd(&iwvi_phase_cycles[kern][k_], (unsigned long long)ph_acc_[k_]); } while (0)

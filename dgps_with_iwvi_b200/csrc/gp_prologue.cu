@@ -144,32 +144,47 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   };
   for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zi[idx] = Zt[(size_t)i * IWVI_BLK * ldz + idx];
 
+  PHASE_DECL;
+  // gram block (i, kk) of Kuu + jitter I (identity on the padding) into `out`; the kernel function is evaluated in lock step
+  // over the 4 entries of an accumulator row (see kern_n)
+  auto gram_block = [&](int kk, double (&out)[4][2][2]) {
+    __syncthreads();
+    for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zk[idx] = Zt[(size_t)kk * IWVI_BLK * ldz + idx];
+    __syncthreads();
+    acc_zero<4, 2>(out);
+    warp_gemm<4, 2, 0, 0>(out, zi + wm0 * ldz, ldz, zk + wn0 * ldz, ldz, Dk, lane);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int mg = i * IWVI_BLK + wm0 + a * 8 + g;
+      double kv[4], unused[4];
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int ng = kk * IWVI_BLK + wn0 + b * 8 + 2 * t + c;
+          kv[b * 2 + c] = zn[mg] + zn[ng] - 2.0 * out[a][b][c];
+        }
+      kern_n<KIND, 4, false>(kv, unused, variance);
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int ng = kk * IWVI_BLK + wn0 + b * 8 + 2 * t + c;
+          double v = (mg == ng) ? 1.0 : 0.0;
+          if (mg < M && ng < M) v = kv[b * 2 + c] + ((mg == ng) ? jitter : 0.0);
+          out[a][b][c] = v;
+        }
+    }
+  };
+  double acc[4][2][2], acc_next[4][2][2];
+  gram_block(0, acc_next);
   for (int k = 0; k <= i; k++) {
     {
-      __syncthreads();
-      for (int idx = tid; idx < IWVI_BLK * ldz; idx += 256) zk[idx] = Zt[(size_t)k * IWVI_BLK * ldz + idx];
-      __syncthreads();
-      // gram block (i,k) of Kuu + jitter I, identity on the padding
-      double acc[4][2][2];
-      acc_zero<4, 2>(acc);
-      warp_gemm<4, 2, 0, 0>(acc, zi + wm0 * ldz, ldz, zk + wn0 * ldz, ldz, Dk, lane);
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++)
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int mg = i * IWVI_BLK + wm0 + a * 8 + g;
-            const int ng = k * IWVI_BLK + wn0 + b * 8 + 2 * t + c;
-            double v;
-            if (mg < M && ng < M) {
-              v = kern_k(KIND, zn[mg] + zn[ng] - 2.0 * acc[a][b][c], variance);
-              if (mg == ng) v += jitter;
-            } else {
-              v = (mg == ng) ? 1.0 : 0.0;
-            }
-            acc[a][b][c] = v;
-          }
+        for (int b = 0; b < 2; b++) { acc[a][b][0] = acc_next[a][b][0]; acc[a][b][1] = acc_next[a][b][1]; }
+      PHASE_MARK(0);
       // left-looking update: -= sum_{j<k} L(i,j) L(k,j)^T
       for (int j = 0; j < k; j++) {
         __syncthreads();
@@ -187,6 +202,9 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
 #pragma unroll
             for (int c = 0; c < 2; c++) acc[a][b][c] -= upd[a][b][c];
       }
+      // the next column's gram block does not depend on other rows: form it before waiting for row k's diagonal block
+      if (k < i) gram_block(k + 1, acc_next);
+      PHASE_MARK(1);
       if (i == k) {
         // ---- diagonal block: right-looking factorisation in shared memory with 8-wide panels -- (1) one warp factors the
         //      8x8 pivot block (the only strictly serial part: 8 dependent reciprocal square roots), (2) one thread per
@@ -253,6 +271,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
           }
           __syncthreads();
         }
+        PHASE_MARK(2);
         {
           // L(k,k): zero the upper part of S, copy to global; Dv := 0
           for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
@@ -309,6 +328,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
           const int c = idx % IWVI_LDS;
           Lmb[(size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES + idx] = (c < IWVI_BLK) ? Dv[idx] : 0.0;
         }
+        PHASE_MARK(3);
         // zero the blocks to the right of the diagonal
         for (int jb = k + 1; jb < NB; jb++)
           for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += 256) {
@@ -318,6 +338,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
       } else {
         // ---- L(i,k) = S(i,k) Dinv_k^T, with row k's inverted diagonal block fetched once it is published
         wait_row(k, k + 1);
+        PHASE_MARK(4);
         {
           const double* src = Lmb + (size_t)iwvi_pair(k, k) * IWVI_STAGE_DOUBLES;
           double v[IWVI_STAGE_DOUBLES / 256];                        // 17 loads in flight per thread
@@ -350,10 +371,12 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             }
       }
     }
+    PHASE_MARK(5);
     // publish block (i,k)
     __syncthreads();
     if (tid == 0) { __threadfence(); st_release(prog + i, k + 1); }
   }
+  if (i == NB - 1) PHASE_FLUSH(2);
   if (i == NB - 1 && tid == 0) {   // the last row depends on every other row: it finishes last
     double s = 0.0;
     for (int q = 0; q < IWVI_PACK_GRID; q++) s += aux[al.off_scratch + q];

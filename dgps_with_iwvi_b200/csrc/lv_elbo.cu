@@ -597,10 +597,10 @@ extern "C" int iwvi_adam_step_counter(double* x, const double* grad_elbo, double
 }
 
 #ifdef IWVI_PHASE_TIMING
-__device__ unsigned long long iwvi_phase_cycles[2][16];
-// debug only (not part of the ABI): copies the 2 x 16 phase totals to host memory and clears them
+__device__ unsigned long long iwvi_phase_cycles[3][16];
+// debug only (not part of the ABI): copies the 3 x 16 phase totals to host memory and clears them
 extern "C" __attribute__((visibility("default"))) int iwvi_debug_phase_cycles(unsigned long long* host_out) {
-  unsigned long long zero[2][16] = {};
+  unsigned long long zero[3][16] = {};
   if (cudaDeviceSynchronize() != cudaSuccess) return IWVI_ERR_LAUNCH;
   if (cudaMemcpyFromSymbol(host_out, iwvi_phase_cycles, sizeof(zero)) != cudaSuccess) return IWVI_ERR_LAUNCH;
   if (cudaMemcpyToSymbol(iwvi_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return IWVI_ERR_LAUNCH;

@@ -20,7 +20,7 @@ model = build_model(X, Y, cfg['configuration'], M=cfg['M'], num_IW_samples=cfg['
                     likelihood_variance=cfg['lik_variance'], mode='IWAE', seed=0)
 tr = Trainer(model, cfg['B'])
 lib = C.CDLL(_lib.LIB_PATH)
-buf = (C.c_ulonglong * 32)()
+buf = (C.c_ulonglong * 48)()
 steps = 5
 for i in range(steps + 1):
     idx = torch.arange(i * cfg['B'], (i + 1) * cfg['B'], device=model.X.device) % cfg['N']
@@ -32,7 +32,10 @@ FWD = ['x tile', 'G gram+kernel fn', 'T forward subst', 'S fvar0/gmean + A save'
 BWD = ['tile prologue', 'part 1 (A stream)', 'part 2 (Lq V)', 'back substitution', 'Bbar store', 'gram adjoint (loop exit)',
        'dX final', 'start-of-tile barrier', 'ga: Zt wait + gram GEMM', 'ga: kernel fn, G, row/col sums', 'ga: barrier',
        'ga: dX DMMAs', 'ga: dZ DMMAs + adds']
-for k, (title, names) in enumerate([('gp_rows_fwd_kernel', FWD), ('gp_tile_bwd_kernel', BWD)]):
+CHOL = ['gram block', 'updates (incl. waits for other rows)', 'diagonal factorisation', 'inversion + copies', 'wait for Dinv_k',
+        'panel product / zero fill']
+for k, (title, names) in enumerate([('gp_rows_fwd_kernel', FWD), ('gp_tile_bwd_kernel', BWD),
+                                    ('gp_chol_kernel (last block row only)', CHOL)]):
     vals = [buf[k * 16 + j] for j in range(16)]
     tot = sum(vals)
     print('%s: all layers, %d steps, %.1f Mcycles on thread 0 of every CTA' % (title, steps, tot / 1e6))
