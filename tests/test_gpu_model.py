@@ -219,3 +219,35 @@ def test_reference_iteration_natgrad_then_adam():
     z0 = spec['layers'][1]['Z']
     assert np.abs(m.layers[1].feature.feat.Z.read_value() - z0).max() > 1e-4
     np.testing.assert_allclose(m.layers[last].q_mu.read_value(), mu_new.numpy(), rtol=1e-8, atol=1e-10)
+
+
+def test_full_size_properties_c3():
+    """BASELINE config 3 at full per-GPU size (L1_G5_G5, D=16, M=256, K=50, B=512: 25 600 points per layer), properties
+    that need no oracle run: bit-identical repeat (fixed-order reductions, side-stream overlap included), ELBO
+    reassembled from the per-row outputs, exact zeros above q_sqrt's diagonal, finite gradients, and the training step
+    (CUDA graph) moving the bound."""
+    from dgps_with_iwvi_b200.build_models import build_model
+    from dgps_with_iwvi_b200.training import Trainer
+    c = S.CONFIGS['c3']
+    N = 20000
+    X, Y = S.make_data(N, c['D'], seed=0)
+    m = build_model(X, Y, c['configuration'], M=c['M'], num_IW_samples=c['K'], minibatch_size=c['B'],
+                    likelihood_variance=c['lik_variance'], mode='IWAE', seed=0)
+    B, K = c['B'], c['K']
+    Xb, Yb = X[:B], Y[:B]
+    e1, g1 = m.compute_log_likelihood_and_grads(Xb, Yb)
+    eng = m.engine(B, K)
+    np.testing.assert_allclose(eng.w.cpu().numpy().sum(1), 1.0, rtol=0, atol=1e-13)
+    kl = eng.kls[:eng.n_gp].cpu().numpy().sum()
+    assert abs(e1 - (N / B * eng.logp.cpu().numpy().sum() - kl)) < 1e-10 * abs(e1)
+    for k, v in g1.items():
+        assert np.isfinite(v).all(), k
+        if k.endswith('q_sqrt'):
+            assert np.all(np.triu(v, 1) == 0), k
+    m._evals -= 1
+    e2, g2 = m.compute_log_likelihood_and_grads(Xb, Yb)
+    assert e1 == e2 and all(np.array_equal(g1[k], g2[k]) for k in g1)
+    tr = Trainer(m, B, lr=1e-2, seed=3)
+    losses = [tr.step(X[i * B:(i + 1) * B], Y[i * B:(i + 1) * B]) for i in range(12)]
+    tr.engine.check_info()
+    assert np.isfinite(losses).all() and np.mean(losses[-3:]) > np.mean(losses[:3])
