@@ -68,6 +68,10 @@ SHAPES = [
     (700,   512, 8,  2, 2, False, 'Zero',     'Matern32'),
     (130,   130, 4,  8, 8, False, 'Zero',     'Matern12'),
     (257,   200, 32, 3, 32, True, 'Identity', 'RBF'),
+    (5,     7,   1,  1, 1, False, 'Zero',     'RBF'),        # fewer points than one tile, one input column
+    (64,    512, 32, 8, 32, True, 'Linear',   'Matern52'),   # every limit of the build at once (M, D, R, P)
+    (193,   320, 20, 1, 1, False, 'Zero',     'RBF'),        # NB = 5, D at the ldz = 20 boundary
+    (129,   64,  21, 2, 4, True,  'Zero',     'Matern32'),   # D just over the ldz boundary (ldz = 36)
 ]
 
 
