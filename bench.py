@@ -344,13 +344,15 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         spec = spec_from_model(model)
         Bs = cpu_sample_rows(cfg)
-        times, threads = cpu_eval_time(cfg, spec, X, Y, Bs, reps=3, warm=1)
+        t_probe, threads = cpu_eval_time(cfg, spec, X, Y, Bs, reps=1, warm=1)
+        reps = int(min(30, max(3, 12.0 / max(t_probe[0], 1e-3))))      # about 10-15 s of CPU work in total
+        times, threads = cpu_eval_time(cfg, spec, X, Y, Bs, reps=reps, warm=0)
         v = Bs * K / float(np.mean(times))
         out['cpu_baseline'] = {'value': v, 'unit': 'KxN samples/s', 'cores': threads, 'kind': 'port',
                                'ms_per_eval': float(np.mean(times)) * 1e3,
                                'sample': 'oracle (torch-CPU fp64 restatement of the reference, KxK final layer) '
-                                         'forward+autograd on %d of %d minibatch rows x K=%d, 3 evals after 1 warm-up, no '
-                                         'optimiser step' % (Bs, B, K)}
+                                         'forward+autograd on %d of %d minibatch rows x K=%d, %d evals after warm-up, no '
+                                         'optimiser step' % (Bs, B, K, reps)}
     emit(out)
     if world > 1:
         dist.destroy_process_group()
