@@ -14,6 +14,7 @@ KERN_IDS = {'RBF': 0, 'Matern12': 1, 'Matern32': 2, 'Matern52': 3}
 MF_IDS = {'Zero': 0, 'Identity': 1, 'Linear': 2}
 FLAG_SAMPLE, FLAG_SAVE, FLAG_ACCUM = 1, 2, 4
 FLAG_ONLY_EPI, FLAG_ONLY_TILE, FLAG_ONLY_REDUCE, FLAG_ONLY_FINAL = 16, 32, 64, 128
+FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
 
 ERRORS = {-1: 'bad descriptor', -2: 'unsupported size', -3: 'CUDA launch failure', -4: 'null pointer'}
 

@@ -119,7 +119,7 @@ def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, 
 
 
 def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls, dvariance, dq_mu, dq_sqrt, ws):
-    _count(6)
+    _count(1 if d.flags & L.FLAG_ONLY_KL else (5 if d.flags & L.FLAG_SKIP_KL else 6))
     L.check(L.load().iwvi_gp_prologue_bwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(Z), _ptr(ls), _ptr(variance),
                                           _ptr(q_mu), _ptr(q_sqrt), _ptr(dLm), _ptr(dkl), _ptr(dZ), _ptr(dls),
                                           _ptr(dvariance), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(ws), _stream()),

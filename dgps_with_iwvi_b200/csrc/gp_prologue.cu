@@ -748,6 +748,8 @@ extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, con
   p.dLm = dLm; p.dkl = dkl; p.dZ = dZ; p.dls = dls; p.dvariance = dvariance; p.dq_mu = dq_mu; p.dq_sqrt = dq_sqrt;
   p.ws = ws; p.accumulate = (d->flags & IWVI_FLAG_ACCUM) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool only_kl = (d->flags & IWVI_FLAG_ONLY_KL) != 0, skip_kl = (d->flags & IWVI_FLAG_SKIP_KL) != 0;
+  if (!only_kl) {
   const int phi_smem = 2 * IWVI_STAGE_DOUBLES * 8;
   if (cudaFuncSetAttribute(pbwd_phi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phi_smem) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
@@ -768,15 +770,18 @@ extern "C" int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, con
     pbwd_gram_kernel<<<(al.Mp + 7) / 8, 256, gram_smem, st>>>(p);
   }
   IWVI_CHECK_LAUNCH();
-  {
+  }
+  if (!skip_kl) {
     const int n_all = d->R * d->M * d->M + d->M * d->R;
     int grid = (n_all + 1023) / 1024;
     if (grid > 592) grid = 592;
     pbwd_kl_kernel<<<grid, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
-  pbwd_final_kernel<<<d->D + 1, 32, 0, st>>>(p);
-  IWVI_CHECK_LAUNCH();
+  if (!only_kl) {
+    pbwd_final_kernel<<<d->D + 1, 32, 0, st>>>(p);
+    IWVI_CHECK_LAUNCH();
+  }
   return IWVI_OK;
 }
 

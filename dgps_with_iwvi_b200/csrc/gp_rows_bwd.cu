@@ -103,6 +103,8 @@ struct BwdParams {
   double *dX, *dZ, *dls, *dvariance, *dq_mu, *dq_sqrt, *dLm, *dW, *dmfA, *dmfb, *ws;
   BwdWs wl;
   int ntiles, grid_tile;
+  int q_lo;      // reduce kernel: first matrix index of this launch (0 .. R; R == dLm)
+  int fin_part;  // finalize kernel: 0 = everything, 1 = part A outputs, 2 = part B outputs
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // decode the work item
-  int item = blockIdx.x;
+  int item = blockIdx.x + p.q_lo * wl.S * wl.npairs;
   const int pair = item % wl.npairs; item /= wl.npairs;
   const int s = item % wl.S;
   const int q = item / wl.S;                                     // q < R: dLq_q ; q == R: dLm
@@ -1015,6 +1017,7 @@ __global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p)
       const int off = (int)(e % BB);
       const int64_t e2 = e / BB;
       const int pair = (int)(e2 % wl.npairs), q = (int)(e2 / wl.npairs);
+      if (p.fin_part && (p.fin_part == 1) != (q == R)) return;   // part A owns dLm, part B the dLq_r
       int bi = 0;
       while ((bi + 1) * (bi + 2) / 2 <= pair) bi++;
       const int bj = pair - bi * (bi + 1) / 2;
@@ -1032,6 +1035,7 @@ __global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p)
       const int64_t e2 = e / BB;
       const int nup = NB * (NB - 1) / 2;
       const int up = (int)(e2 % nup), q = (int)(e2 / nup);
+      if (p.fin_part && (p.fin_part == 1) != (q == R)) return;
       int bj = 1;                                  // block column bj > block row bi; enumerate (bi, bj) with bi < bj
       while (bj * (bj + 1) / 2 <= up) bj++;
       const int bi = up - bj * (bj - 1) / 2;
@@ -1041,7 +1045,7 @@ __global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p)
       return;
     }
     e -= f.n_up;
-    if (e < f.n_qmu) {
+    if (e < f.n_qmu && p.fin_part != 1) {
       const int m = (int)(e / R), r = (int)(e - (int64_t)m * R);
       const int bi = m / IWVI_BLK;
       double s = 0.0;
@@ -1051,7 +1055,8 @@ __global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p)
     }
     return;
   }
-  // ---- one warp per output: per-CTA partials of the tile kernel and of the epilogue kernel
+  // ---- one warp per output: per-CTA partials of the tile kernel and of the epilogue kernel (part A)
+  if (p.fin_part == 2) return;
   const int lane = threadIdx.x & 31;
   const int o = ((int)blockIdx.x - f.grid_elem) * 8 + (threadIdx.x >> 5);
   if (o >= f.n_warp_out) return;
@@ -1155,6 +1160,7 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
   cudaStream_t st = (cudaStream_t)stream;
   const int only = d->flags & IWVI_FLAG_ONLY_MASK;
+  p.q_lo = 0; p.fin_part = 0;
 
   if (!only || (only & IWVI_FLAG_ONLY_EPI)) {
     gp_epi_bwd_kernel<<<p.wl.n_epi, 256, 0, st>>>(p);
@@ -1166,16 +1172,24 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
     if (rc != IWVI_OK) return rc;
   }
 
+  // IWVI_FLAG_PART_A / _B restrict the reduce + finalize launches to one half of the parameter gradients, so that the
+  // caller can start iwvi_gp_prologue_bwd (needs dLm, dZ, dls, dvariance only) while the other half is still running:
+  //   A: reduce (dLm items), finalize (dLm, dZ, dls, dvariance, dW, dmfA, dmfb)      B: reduce (dLq_r items, dq_mu), finalize (dq_sqrt, dq_mu)
+  const int part = d->flags & (IWVI_FLAG_PART_A | IWVI_FLAG_PART_B);
+  const bool do_a = part != IWVI_FLAG_PART_B, do_b = part != IWVI_FLAG_PART_A;
   if (!only || (only & IWVI_FLAG_ONLY_REDUCE)) {
     const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * RED_NST) * 8;
     if (cudaFuncSetAttribute(gp_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem) != cudaSuccess)
       return IWVI_ERR_LAUNCH;
-    const int red_grid = (d->R + 1) * p.wl.S * p.wl.npairs;
-    gp_reduce_bwd_kernel<<<red_grid, RED_THREADS, red_smem, st>>>(p);
+    const int per_q = p.wl.S * p.wl.npairs;
+    p.q_lo = (do_a && !do_b) ? d->R : 0;
+    const int nq = (do_a && do_b) ? d->R + 1 : (do_a ? 1 : d->R);
+    gp_reduce_bwd_kernel<<<nq * per_q, RED_THREADS, red_smem, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
   if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {
     const FinalLayout fl = final_layout(*d, p.wl);
+    p.fin_part = (do_a && do_b) ? 0 : (do_a ? 1 : 2);
     gp_finalize_bwd_kernel<<<fl.grid_elem + fl.grid_warp, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }

@@ -217,6 +217,8 @@ class Engine:
         self.ev_pro = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.ev_rows = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.ev_pbwd = [torch.cuda.Event() for _ in range(self.n_gp)]
+        self.side_b = torch.cuda.Stream(device=dev)      # second half of the first GP layer's reductions (backward)
+        self.ev_part_b = torch.cuda.Event()
         self.X_tiled = None
         if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
             self.X_tiled = z(T, self.Dx)
@@ -369,15 +371,32 @@ class Engine:
                 self.ev_rows[gi].record(main)
                 side = self.side[gi]
                 side.wait_event(self.ev_rows[gi])
-                with torch.cuda.stream(side):
-                    capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL), *args)
-                    capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), r['Lm'], r['aux'], self._cv(feat.Z),
-                                         r['ls'], self._cv(base.variance), self._cv(layer.q_mu),
-                                         self._cv(layer.q_sqrt), r['dLm'], self.dkl, outs[0], outs[1], outs[2],
-                                         outs[3], outs[4], r['pbwd_ws'])
-                    if not r['ard']:
-                        torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
-                    self.ev_pbwd[gi].record(side)
+                pargs = (r['Lm'], r['aux'], self._cv(feat.Z), r['ls'], self._cv(base.variance), self._cv(layer.q_mu),
+                         self._cv(layer.q_sqrt), r['dLm'], self.dkl, outs[0], outs[1], outs[2], outs[3], outs[4],
+                         r['pbwd_ws'])
+                red = fl | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL
+                if gi == 0:
+                    # The first GP layer comes last in the backward pass, so nothing is left to hide its Cholesky / gram
+                    # adjoint chain behind -- except its own reductions: dLm first (part A), then the chain on this stream
+                    # while dq_sqrt / dq_mu (part B) are formed on a second one; the KL adjoint adds into part B's outputs.
+                    with torch.cuda.stream(side):
+                        capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_A), *args)
+                        capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), *pargs)
+                        if not r['ard']:
+                            torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                        self.ev_pbwd[gi].record(side)
+                    self.side_b.wait_event(self.ev_rows[gi])
+                    with torch.cuda.stream(self.side_b):
+                        capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_B), *args)
+                        capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_ONLY_KL), *pargs)
+                        self.ev_part_b.record(self.side_b)
+                else:
+                    with torch.cuda.stream(side):
+                        capi.gp_rows_bwd(capi.with_flags(r['d'], red), *args)
+                        capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), *pargs)
+                        if not r['ard']:
+                            torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                        self.ev_pbwd[gi].record(side)
                 d_next = r['dX']
             else:
                 Lw = r['Lw']
@@ -398,6 +417,8 @@ class Engine:
         main = torch.cuda.current_stream()
         for ev in self.ev_pbwd:
             main.wait_event(ev)
+        if self.n_gp:
+            main.wait_event(self.ev_part_b)
         return flat.g
 
     def elbo_and_grads(self, X, Y, eps=None, seed=0, step=0, row0=0):

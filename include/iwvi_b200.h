@@ -72,6 +72,14 @@ extern "C" {
 #define IWVI_FLAG_ONLY_REDUCE 64
 #define IWVI_FLAG_ONLY_FINAL  128
 #define IWVI_FLAG_ONLY_MASK   (16 | 32 | 64 | 128)
+/* The reduce + finalize launches in two halves, so that iwvi_gp_prologue_bwd (needs dLm, dZ, dls, dvariance only) can
+ * overlap with the second one on another stream:  PART_A: dLm, dZ, dls, dvariance, dW, dmfA, dmfb;  PART_B: dq_mu, dq_sqrt.
+ * Neither flag: everything.  With the split, run iwvi_gp_prologue_bwd with IWVI_FLAG_SKIP_KL after part A and with
+ * IWVI_FLAG_ONLY_KL (the whitened-KL adjoint, which adds into dq_mu / dq_sqrt) after part B. */
+#define IWVI_FLAG_PART_A   256
+#define IWVI_FLAG_PART_B   512
+#define IWVI_FLAG_SKIP_KL  1024
+#define IWVI_FLAG_ONLY_KL  2048
 
 typedef struct iwvi_gp_desc {
   int32_t T;      /* points in this call                                    */
