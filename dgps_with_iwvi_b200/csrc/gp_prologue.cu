@@ -176,19 +176,25 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
         }
     }
   };
-  double acc[4][2][2], acc_next[4][2][2];
-  gram_block(0, acc_next);
+  // The row's own diagonal block is on the critical path of every row below it: its gram block is formed up front and each
+  // L(i,k) is folded into it (acc_diag -= L(i,k) L(i,k)^T) right after it has been published, while the row would otherwise
+  // be waiting -- so when column i is reached the block only has to be factorised.
+  double acc[4][2][2], acc_next[4][2][2], acc_diag[4][2][2];
+  gram_block(i, acc_diag);
+  if (i > 0) gram_block(0, acc_next);
   for (int k = 0; k <= i; k++) {
     {
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) { acc[a][b][0] = acc_next[a][b][0]; acc[a][b][1] = acc_next[a][b][1]; }
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) acc[a][b][c] = (k == i) ? acc_diag[a][b][c] : acc_next[a][b][c];
       PHASE_MARK(0);
-      // left-looking update: -= sum_{j<k} L(i,j) L(k,j)^T
-      for (int j = 0; j < k; j++) {
+      // left-looking update of an off-diagonal block: -= sum_{j<k} L(i,j) L(k,j)^T
+      for (int j = 0; j < k && k < i; j++) {
         __syncthreads();
-        if (k < i) wait_row(k, j + 1);      // L(k,j) is another row's block
+        wait_row(k, j + 1);                 // L(k,j) is another row's block
         load_block(bufA, Lm + (size_t)(i * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
         load_block_cg(bufB, Lm + (size_t)(k * IWVI_BLK) * Mp + j * IWVI_BLK, Mp, tid);
         __syncthreads();
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
             for (int c = 0; c < 2; c++) acc[a][b][c] -= upd[a][b][c];
       }
       // the next column's gram block does not depend on other rows: form it before waiting for row k's diagonal block
-      if (k < i) gram_block(k + 1, acc_next);
+      if (k + 1 < i) gram_block(k + 1, acc_next);
       PHASE_MARK(1);
       if (i == k) {
         // ---- diagonal block: right-looking factorisation in shared memory with 8-wide panels -- (1) one warp factors the
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
               const int rr = wm0 + a * 8 + g, cc = wn0 + b * 8 + 2 * t + c;
               Lm[(size_t)(i * IWVI_BLK + rr) * Mp + k * IWVI_BLK + cc] = out[a][b][c];
               Lmb[(size_t)iwvi_pair(i, k) * IWVI_STAGE_DOUBLES + rr * IWVI_LDS + cc] = out[a][b][c];
+              bufA[rr * IWVI_LDS + cc] = out[a][b][c];     // kept for the update of this row's diagonal block below
             }
       }
     }
@@ -375,6 +382,17 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
     // publish block (i,k)
     __syncthreads();
     if (tid == 0) { __threadfence(); st_release(prog + i, k + 1); }
+    if (k < i) {   // fold L(i,k) (in bufA) into the row's diagonal block
+      double upd[4][2][2];
+      acc_zero<4, 2>(upd);
+      warp_gemm<4, 2, 0, 0>(upd, bufA + wm0 * IWVI_LDS, IWVI_LDS, bufA + wn0 * IWVI_LDS, IWVI_LDS, IWVI_BLK, lane);
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) acc_diag[a][b][c] -= upd[a][b][c];
+    }
   }
   if (i == NB - 1) PHASE_FLUSH(2);
   if (i == NB - 1 && tid == 0) {   // the last row depends on every other row: it finishes last
