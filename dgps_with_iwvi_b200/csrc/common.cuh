@@ -14,7 +14,8 @@
 #define IWVI_BLK 64            // block size of the blocked triangular algorithms
 #define IWVI_LDS 68            // leading dimension of a staged 64x64 block in shared memory (== 4 mod 16)
 #define IWVI_STAGE_DOUBLES (IWVI_BLK * IWVI_LDS)
-#define IWVI_PACK_GRID 64      // CTAs of the prologue pack kernel (== number of KL partial sums)
+#define IWVI_PACK_SMALL 8      // CTAs of the prologue pack kernel that prepare Z / ls, |z|^2, q_mu, constants
+#define IWVI_PACK_GRID (IWVI_PACK_SMALL + IWVI_MAX_R * 36)   // + one CTA per lower block of every tril(q_sqrt_r): KL partial slots
 
 __host__ __device__ inline int iwvi_round_up(int x, int m) { return (x + m - 1) / m * m; }
 // leading dimension of length-scaled inputs (Zt rows in aux, x tile in smem): == 4 (mod 16), >= round_up(D,4)

@@ -33,55 +33,55 @@ __global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const int M = d.M, D = d.D, R = d.R, Mp = al.Mp, ldz = al.ldz;
   double* aux = p.aux;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
   double klp = 0.0;
-  // tril(q_sqrt) as block-major padded [64][68] lower blocks; trace and log-det terms of the KL
-  const int64_t nlq = (int64_t)R * al.npairs * IWVI_STAGE_DOUBLES;
-  for (int64_t e = gtid; e < nlq; e += gsz) {
-    const int r = (int)(e / ((int64_t)al.npairs * IWVI_STAGE_DOUBLES));
-    int64_t rem = e - (int64_t)r * al.npairs * IWVI_STAGE_DOUBLES;
-    const int pr = (int)(rem / IWVI_STAGE_DOUBLES);
-    rem -= (int64_t)pr * IWVI_STAGE_DOUBLES;
-    const int row = (int)(rem / IWVI_LDS), col = (int)(rem - (int64_t)row * IWVI_LDS);
+  if (blockIdx.x >= IWVI_PACK_SMALL) {
+    // one CTA per lower 64x64 block of tril(q_sqrt_r): block-major padded [64][68] copy; trace and log-det terms of the KL
+    const int blk = blockIdx.x - IWVI_PACK_SMALL;
+    const int r = blk / al.npairs, pr = blk - r * al.npairs;
     int bi = 0;
     while ((bi + 1) * (bi + 2) / 2 <= pr) bi++;
     const int bj = pr - bi * (bi + 1) / 2;
-    const int a = bi * IWVI_BLK + row, b = bj * IWVI_BLK + col;
-    double v = 0.0;
-    if (col < IWVI_BLK && a < M && b <= a) {
-      v = p.q_sqrt[((size_t)r * M + a) * M + b];
-      klp += v * v;
-      if (a == b) klp -= log(v * v);
+    double* dst = aux + al.off_lqb + (size_t)blk * IWVI_STAGE_DOUBLES;
+    for (int e = threadIdx.x; e < IWVI_STAGE_DOUBLES; e += 256) {
+      const int row = e / IWVI_LDS, col = e - row * IWVI_LDS;
+      const int a = bi * IWVI_BLK + row, b = bj * IWVI_BLK + col;
+      double v = 0.0;
+      if (col < IWVI_BLK && a < M && b <= a) {
+        v = p.q_sqrt[((size_t)r * M + a) * M + b];
+        klp += v * v;
+        if (a == b) klp -= log(v * v);
+      }
+      dst[e] = v;
     }
-    aux[al.off_lqb + e] = v;
+  } else {
+    const int gtid = blockIdx.x * 256 + threadIdx.x, gsz = IWVI_PACK_SMALL * 256;
+    // Zt = Z / ls
+    for (int e = gtid; e < Mp * ldz; e += gsz) {
+      const int m = e / ldz, k = e - m * ldz;
+      aux[al.off_zt + e] = (m < M && k < D) ? p.Z[(size_t)m * D + k] / p.ls[k] : 0.0;
+    }
+    for (int m = gtid; m < Mp; m += gsz) {
+      double s = 0.0;
+      if (m < M)
+        for (int k = 0; k < D; k++) { const double v = p.Z[(size_t)m * D + k] / p.ls[k]; s += v * v; }
+      aux[al.off_zn + m] = s;
+    }
+    // q_mu padded to [Mp, 8]; mahalanobis term of the KL
+    for (int e = gtid; e < Mp * IWVI_MAX_R; e += gsz) {
+      const int m = e / IWVI_MAX_R, r = e - m * IWVI_MAX_R;
+      double v = 0.0;
+      if (m < M && r < R) { v = p.q_mu[(size_t)m * R + r]; klp += v * v; }
+      aux[al.off_qmu + e] = v;
+    }
+    if (gtid < 64) {
+      double v = 0.0;
+      if (gtid == IWVI_C_VARIANCE) v = p.variance[0];
+      else if (gtid >= IWVI_C_INVLS && gtid < IWVI_C_INVLS + D) v = 1.0 / p.ls[gtid - IWVI_C_INVLS];
+      aux[al.off_consts + gtid] = v;
+    }
+    if (gtid < 16) reinterpret_cast<int*>(aux + al.off_prog)[gtid] = 0;   // Cholesky hand-off counters
+    if (gtid == 0) p.info[0] = 0;
   }
-  // Zt = Z / ls
-  for (int64_t e = gtid; e < (int64_t)Mp * ldz; e += gsz) {
-    const int m = (int)(e / ldz), k = (int)(e - (int64_t)m * ldz);
-    aux[al.off_zt + e] = (m < M && k < D) ? p.Z[(size_t)m * D + k] / p.ls[k] : 0.0;
-  }
-  for (int64_t m = gtid; m < Mp; m += gsz) {
-    double s = 0.0;
-    if (m < M)
-      for (int k = 0; k < D; k++) { const double v = p.Z[(size_t)m * D + k] / p.ls[k]; s += v * v; }
-    aux[al.off_zn + m] = s;
-  }
-  // q_mu padded to [Mp, 8]; mahalanobis term of the KL
-  for (int64_t e = gtid; e < (int64_t)Mp * IWVI_MAX_R; e += gsz) {
-    const int m = (int)(e / IWVI_MAX_R), r = (int)(e - (int64_t)m * IWVI_MAX_R);
-    double v = 0.0;
-    if (m < M && r < R) { v = p.q_mu[(size_t)m * R + r]; klp += v * v; }
-    aux[al.off_qmu + e] = v;
-  }
-  for (int64_t e = gtid; e < 64; e += gsz) {
-    double v = 0.0;
-    if (e == IWVI_C_VARIANCE) v = p.variance[0];
-    else if (e >= IWVI_C_INVLS && e < IWVI_C_INVLS + D) v = 1.0 / p.ls[e - IWVI_C_INVLS];
-    aux[al.off_consts + e] = v;
-  }
-  if (gtid < 16) reinterpret_cast<int*>(aux + al.off_prog)[gtid] = 0;   // Cholesky hand-off counters
-  if (gtid == 0) p.info[0] = 0;
   const double tot = block_sum(klp, red);
   if (threadIdx.x == 0) aux[al.off_scratch + blockIdx.x] = tot;
 }
@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   if (i == NB - 1) PHASE_FLUSH(2);
   if (i == NB - 1 && tid == 0) {   // the last row depends on every other row: it finishes last
     double s = 0.0;
-    for (int q = 0; q < IWVI_PACK_GRID; q++) s += aux[al.off_scratch + q];
+    const int nparts = IWVI_PACK_SMALL + d.R * al.npairs;   // CTAs of this layer's pack launch
+    for (int q = 0; q < nparts; q++) s += aux[al.off_scratch + q];
     p.kl[0] = 0.5 * (s - (double)M * (double)d.R);
   }
 }
@@ -738,7 +739,7 @@ extern "C" int iwvi_gp_prologue_fwd(const iwvi_gp_desc* d, const double* Z, cons
   p.d = *d; p.Z = Z; p.ls = ls; p.variance = variance; p.q_mu = q_mu; p.q_sqrt = q_sqrt;
   p.Lm = Lm; p.aux = aux; p.kl = kl; p.info = info;
   cudaStream_t st = (cudaStream_t)stream;
-  gp_pack_kernel<<<IWVI_PACK_GRID, 256, 0, st>>>(p);
+  gp_pack_kernel<<<IWVI_PACK_SMALL + d->R * iwvi_aux_layout(d->M, d->D, d->R).npairs, 256, 0, st>>>(p);
   IWVI_CHECK_LAUNCH();
   const int smem_bytes = (5 * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK * 36) * 8;
   switch (d->kern) {

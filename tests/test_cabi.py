@@ -48,7 +48,7 @@ def test_size_helpers_on_host(lib):
     d = capi.gp_desc(25600, 256, 17, 5, 16, 'RBF', True, 'Linear', 3)
     NB, blk = 4, 64 * 68
     npairs = NB * (NB + 1) // 2
-    assert capi.gp_aux_doubles(d) == npairs * blk * (1 + 5) + 256 * 20 + 256 + 256 * 8 + 64 + 64 + 8
+    assert capi.gp_aux_doubles(d) == npairs * blk * (1 + 5) + 256 * 20 + 256 + 256 * 8 + 64 + (8 + 8 * 36) + 8
     assert capi.gp_save_doubles(d) == (25600 // 64) * NB * blk * 6 + 2 * 25600 * 5
     assert capi.gp_bwd_ws_doubles(d) > 0 and capi.gp_pbwd_ws_doubles(d) == 2 * 256 * 256 + 256 * 32 + 256
     e = capi.elbo_desc(512, 50, 1, 1, True, True, 100.0)
