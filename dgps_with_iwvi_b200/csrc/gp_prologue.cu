@@ -1,17 +1,20 @@
 // gp_prologue.cu -- once-per-layer-per-step stage of a GPLayer and its adjoint.
 //
 // Forward (reference temp_workaround.py:39 Kuu + jitter, :48 tf.cholesky, layers.py:44 -> gauss_kl whitened):
-//   gp_pack_kernel   many CTAs: length-scaled inducing inputs Zt and their norms, zero-padded tril(q_sqrt), padded
-//                    q_mu, constants, per-CTA partial sums of the whitened KL.
-//   gp_chol_kernel   one CTA: left-looking blocked Cholesky of Kuu + jitter*I with 64x64 blocks.  The gram blocks
-//                    are produced on the fly (-2 Z Z^T GEMM + norm epilogue + kernel function, DMMA), the block
-//                    updates L(i,j) L(k,j)^T and the panel scaling S(i,k) Dinv_k^T run on the FP64 tensor pipe, the
-//                    64x64 diagonal factorisation and its inverse run in shared memory.  Also the final KL sum.
+//   gp_pack_kernel   length-scaled inducing inputs Zt and their norms, padded q_mu, constants (8 CTAs); one CTA per lower
+//                    block of every tril(q_sqrt_r) (block-major padded copy); per-CTA partial sums of the whitened KL.
+//   gp_chol_kernel   blocked Cholesky of Kuu + jitter*I with 64x64 blocks as a DATAFLOW over NB CTAs, one per block row,
+//                    handing finished blocks to the rows below through global memory (acquire/release counters).  The
+//                    gram blocks are produced on the fly (-2 Z Z^T GEMM + norm epilogue + kernel function, DMMA), the
+//                    block updates and the panel scaling S(i,k) Dinv_k^T run on the FP64 tensor pipe, the 64x64 diagonal
+//                    blocks are factorised in shared memory with 8-wide panels and inverted by recursive doubling.
+//                    The last row also forms the final KL sum.
 // Backward (the reference: tf.gradients; TF CholeskyGrad = Phi-form below):
 //   pbwd_phi_kernel    P = Phi(Lm^T tril(dLm))                     one 64x64 block per CTA, DMMA
 //   pbwd_solve_kernel  Out = In Lm^-1 (blocked back substitution on 32-row panels, same pipeline as the row stage);
 //                      run twice: S1^T = P^T Lm^-1, then Kbar' = S1 Lm^-1
-//   pbwd_gram_kernel   Kbar = sym(Kbar'), gram adjoint of Kuu (dZ, per-row partials of dls, dvariance), KL adjoint
+//   pbwd_gram_kernel   Kbar = sym(Kbar'), gram adjoint of Kuu (dZ, per-row partials of dls, dvariance)
+//   pbwd_kl_kernel     adjoint of the whitened KL (adds into dq_mu, dq_sqrt)
 //   pbwd_final_kernel  fixed-order sums of the per-row partials
 #include "common.cuh"
 

@@ -2,16 +2,20 @@
 // through temp_workaround.py:44-91,142-145 and layers.py:46-48; the formulas are derived in DESIGN.md and checked
 // against autograd in tests/test_staged.py.
 //
-// Four launches:
-//   1 gp_epi_bwd_kernel   per point: un-mix the cotangents (gmean_bar, gvar_bar), mean-function part of dX,
-//                         partial sums of dW / dmfA / dmfb / dvariance.
-//   2 gp_tile_bwd_kernel  persistent, one tile of TP points per CTA iteration, shared-memory resident panel:
-//        Abar  = q_mu gmean_bar^T - 2 A (sum_r gvar_bar_r) + 2 sum_r tril(Lq_r) (U_r * gvar_bar_r)
-//        Bbar  = Lm^-T Abar                              (blocked back substitution, in place; stored for 3)
-//        G     = Bbar * dK/dr2 ; dX += 2/ls (x~ colsum(G) - G^T z~) ; dZ, dls, dvariance partials per CTA
-//   3 gp_reduce_bwd_kernel  contractions over the T points, split-K, one 64x64 output block per CTA:
+// Four launches (the host may run 1-2 and 3-4 on different streams, see IWVI_FLAG_ONLY_* / IWVI_FLAG_PART_*):
+//   1 gp_epi_bwd_kernel   32 points per CTA: un-mix the cotangents (gmean_bar, gvar_bar), mean-function part of dX
+//                         (skinny DMMA), partial sums of dW / dmfA / dmfb / dvariance.
+//   2 gp_tile_bwd_kernel  persistent, one tile of TP points per CTA iteration, shared-memory resident panel
+//                         (block-major), producer warp + TMA ring as in the forward kernel:
+//        Abar/2 = q_mu gmean_bar^T / 2 - A (sum_r gvar_bar_r) + sum_r tril(Lq_r) (U_r * gvar_bar_r)
+//        Bbar/2 = Lm^-T Abar/2                           (blocked back substitution, in place; stored for 3; the exact
+//                                                         factor 2 is restored where Bbar is consumed)
+//        G      = Bbar * dK/dr2 ; dX += 2/ls (x~ colsum(G) - G^T z~) ; dZ, dls, dvariance partials per CTA
+//   3 gp_reduce_bwd_kernel  contractions over the T points, split-K, one 64x64 output block per CTA (diagonal blocks:
+//                         lower triangle only):
 //        dLq_r = 2 tril(A diag(gvar_bar_r) U_r^T),  dLm = -tril(Bbar A^T),  dq_mu = A gmean_bar
-//   4 gp_finalize_bwd_kernel  fixed-order sums of all partials (deterministic; no floating-point atomics to HBM).
+//   4 gp_finalize_bwd_kernel  fixed-order sums of all partials (deterministic; the only atomics are fire-and-forget
+//                         adds to addresses owned by a single thread).
 #include "common.cuh"
 
 namespace {

@@ -3,8 +3,9 @@
 // Replaces independent_multisample_sample_conditional (reference temp_workaround.py:44-91, diag branch),
 // the SharedMixedMok mixing (:142-145) and the mean-function add (layers.py:46-48) with ONE persistent kernel:
 // a CTA owns a tile of TP points, keeps the M x TP panel (Kuf -> A = Lm^-1 Kuf) resident in shared memory
-// (point-major, padded leading dimension), streams 64x64 blocks of Lm / inverted diagonal blocks / tril(q_sqrt)
-// from L2 through a bulk-TMA + mbarrier ring, and does every contraction on the FP64 tensor pipe (DMMA):
+// (block-major [m-block][point][68], the layout of the saved arrays), has a dedicated producer warp stream the 64x64
+// blocks of Lm / inverted diagonal blocks / tril(q_sqrt) from L2 through a bulk-TMA + mbarrier ring, and does every
+// contraction on the FP64 tensor pipe (DMMA); triangular diagonal blocks only issue the 8x8x4 tiles that touch the triangle:
 //
 //   G  Kuf_i   = k(|z|^2 + |x|^2 - 2 z.x)                (gram: -2XZ^T GEMM + norm epilogue + kernel function)
 //   T  A_i     = Dinv_i (Kuf_i - sum_{j<i} Lm_ij A_j)    (blocked forward substitution, inverted diagonal blocks)
