@@ -16,6 +16,7 @@
 //        dLq_r = 2 tril(A diag(gvar_bar_r) U_r^T),  dLm = -tril(Bbar A^T),  dq_mu = A gmean_bar
 //   4 gp_finalize_bwd_kernel  fixed-order sums of all partials (deterministic; the only atomics are fire-and-forget
 //                         adds to addresses owned by a single thread).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -45,6 +46,7 @@ struct BwdWs {   // workspace layout (doubles)
 // host-side list-scheduling model behind the choice of S (see bwd_ws_layout); the last answer is cached per thread
 // because the entry points recompute the layout on every call
 inline int pick_reduce_split(int items, int npairs, int nchunks, int nsm) {
+  if (const char* e = getenv("IWVI_REDUCE_S")) { const int v = atoi(e); if (v >= 1) return v < nchunks ? v : nchunks; }   // tuning aid
   static thread_local int key[4] = {-1, -1, -1, -1}, cached = 1;
   if (key[0] == items && key[1] == npairs && key[2] == nchunks && key[3] == nsm) return cached;
   int bestS = 1;
