@@ -15,7 +15,8 @@ drawn with torch.randn when omitted), `mean_function` and `jitter` (the referenc
 GPLayer.propagate, layers.py:46-48; here it is fused into the per-point kernel).
 
 Not on the hot path and therefore not in CUDA (raise NotImplementedError): white=False (:63-65, never taken,
-layers.py:42), q_sqrt=None (:174-184, SGHMC only), 2-D diagonal q_sqrt (:72-73), full_output_cov=True.  full_cov=True
+layers.py:42) and full_output_cov=True.  q_sqrt=None (:174-184, SGHMC) and the 2-D diagonal q_sqrt (:72-73) are mapped
+onto the same kernels (zero / diagonal Cholesky factors).  full_cov=True
 (:55-57,82-83, whose joint sampler :92-96 has a shape bug and is dead code in training) is served
 forward-only from the saved A / U panels with library GEMMs, for predict_f_full_cov and API completeness."""
 import numpy as np
@@ -108,7 +109,8 @@ class _GPConditional(torch.autograd.Function):
         capi.gp_rows_bwd(d, Lm, aux, save, Xc, Wc, Ac, bc, ec,
                          _c(d_sample) if (sampled and d_sample is not None and d_sample.numel()) else None,
                          _c(d_mean), _c(d_var), dX, dZ, dls, dv, dqm, dqs, dLm, dW, dA, db, ws)
-        capi.gp_prologue_bwd(capi.with_flags(d, d.flags | LIB.FLAG_ACCUM), Lm, aux, Zc, lsc, vc, qmc, qsc, dLm, z(1),
+        # (the KL is a separate operator, gauss_kl: its adjoint is skipped here)
+        capi.gp_prologue_bwd(capi.with_flags(d, d.flags | LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), Lm, aux, Zc, lsc, vc, qmc, qsc, dLm, z(1),
                              dZ, dls, dv, dqm, dqs, z(capi.gp_pbwd_ws_doubles(d)))
         return dX, dZ, dls, dv.reshape(ctx.var_shape), dqm, dqs, dW, dA, db, None, None
 
@@ -139,18 +141,24 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
     Returns sample, mean [S, N, P], var [S, N, P] (full_cov=False) or [S, R, N, N] (full_cov=True, forward only)."""
     if not white:
         raise NotImplementedError('white=False (temp_workaround.py:63-65) is never taken by GPLayer (layers.py:42)')
-    if q_sqrt is None:
-        raise NotImplementedError('q_sqrt=None is the SGHMC branch (temp_workaround.py:174-184), outside the IW-ELBO path')
     X = _t(Xnew)
     lead = X.shape[:-1]
     D = X.shape[-1]
     X2 = X.reshape(-1, D)
     T = X2.shape[0]
     Z = _t(feat.feat.Z if hasattr(feat, 'feat') else feat.Z)
-    q_mu, q_sq = _t(f), _t(q_sqrt)
-    if q_sq.dim() != 3:
-        raise NotImplementedError('diagonal q_sqrt [M, R] (temp_workaround.py:72-73) is not used by GPLayer (layers.py:21-25)')
+    q_mu = _t(f)
     M, R = q_mu.shape
+    if q_sqrt is None:
+        # temp_workaround.py:71 skipped (the SGHMC case, q(u) a point mass): tril(0)^T A = 0 adds nothing to the variance
+        q_sq = torch.zeros(R, M, M, dtype=F64, device=q_mu.device)
+    else:
+        q_sq = _t(q_sqrt)
+        if q_sq.dim() == 2:
+            # diagonal form [M, R] (temp_workaround.py:72-73): LTA = A * q_sqrt^T, i.e. a diagonal Cholesky factor per output
+            q_sq = torch.diag_embed(q_sq.t())
+        elif q_sq.dim() != 3:
+            raise ValueError('Bad dimension for q_sqrt: %s' % str(q_sq.dim()))
     ls, variance = _t(kern.lengthscales), _t(kern.variance)
     ls_vec = ls.expand(D) if ls.dim() == 0 or ls.numel() == 1 else ls
     Wt = _t(W)
@@ -239,8 +247,13 @@ def gauss_kl(q_mu, q_sqrt, K=None):
     if K is not None:
         raise NotImplementedError('GPLayer uses the whitened KL (K=None, layers.py:44)')
     if q_sqrt is None:
-        raise NotImplementedError('q_sqrt=None is the SGHMC branch (temp_workaround.py:174-184)')
-    return _GaussKL.apply(_t(q_mu), _t(q_sqrt))
+        # temp_workaround.py:174-184: minus the log density of q_mu under N(0, I), summed over outputs
+        qm = _t(q_mu)
+        return 0.5 * (qm * qm).sum() + 0.5 * qm.numel() * float(np.log(2.0 * np.pi))
+    q_sq = _t(q_sqrt)
+    if q_sq.dim() == 2:
+        q_sq = torch.diag_embed(q_sq.t())      # gpflow gauss_kl's diagonal form [M, R]
+    return _GaussKL.apply(_t(q_mu), q_sq)
 
 
 # ------------------------------------------------------------------------------------------------------------------

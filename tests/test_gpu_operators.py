@@ -85,7 +85,7 @@ def test_gauss_kl_operator():
     (2.5 * k).backward()
     close('kl', k, ko); close('dq_mu', ag.grad, 2.5 * a.grad); close('dq_sqrt', bg.grad, 2.5 * torch.tril(b.grad))
     with pytest.raises(NotImplementedError):
-        tw.gauss_kl(ag, None)
+        tw.gauss_kl(ag, bg, K=torch.eye(M, dtype=torch.float64).cuda())   # only the whitened KL is on the path
 
 
 @pytest.mark.parametrize('sampled,amortised', [(True, True), (False, True), (True, False)])
@@ -153,3 +153,37 @@ def test_full_cov_branch_and_predict_f_full_cov():
     with pytest.raises(NotImplementedError):
         tw.multisample_sample_conditional(T64(F).cuda(), layer.feature, layer.kern, layer.q_mu, q_sqrt=layer.q_sqrt,
                                           white=False)
+
+
+@pytest.mark.parametrize('form', ['none', 'diag'])
+def test_conditional_q_sqrt_none_and_diagonal(form):
+    """temp_workaround.py:71-73: q_sqrt=None (SGHMC, no variance contribution) and the 2-D diagonal q_sqrt [M, R];
+    gauss_kl's matching branches (:174-188)."""
+    from dgps_with_iwvi_b200 import temp_workaround as tw
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    D, M = 3, 29
+    X, Y = S.make_data(40, D, seed=7)
+    spec = S.make_spec(X, 'G2', M, 3, seed=7, perturb=0.3, inner_q_sqrt_scale=0.3, kern='Matern32')
+    layer = model_from_spec(spec, X, Y).layers[0]
+    omodel, _ = O.build_from_spec(spec)
+    ol = omodel.layers[0]
+    rng = np.random.default_rng(3)
+    F = rng.standard_normal((4, 6, D)); eps = rng.standard_normal((4, 6, 2))
+    qd = np.abs(rng.standard_normal((M, 2))) + 0.2
+    Fo, Fg = T64(F).requires_grad_(True), T64(F).cuda().requires_grad_(True)
+    qo = None if form == 'none' else T64(qd).requires_grad_(True)
+    qg = None if form == 'none' else T64(qd).cuda().requires_grad_(True)
+    so, mo, vo = O.multisample_sample_conditional(Fo, ol.Z, ol.kern, ol.q_mu, q_sqrt=qo, white=True, eps=T64(eps))
+    s, m, v = tw.multisample_sample_conditional(Fg, layer.feature, layer.kern, layer.q_mu, q_sqrt=qg, white=True,
+                                                eps=T64(eps).cuda(), mean_function=None)
+    close('sample', s, so); close('mean', m, mo); close('var', v, vo)
+    c = T64(rng.standard_normal(so.shape))
+    ((so * c).sum() + (vo * c).sum()).backward()
+    ((s * c.cuda()).sum() + (v * c.cuda()).sum()).backward()
+    close('dF', Fg.grad, Fo.grad)
+    if form == 'diag':
+        close('dq_sqrt', qg.grad, qo.grad)
+    # the KL wrapper's branches
+    ko = O.gauss_kl(ol.q_mu, None if form == 'none' else T64(np.stack([np.diag(qd[:, r]) for r in range(2)])))
+    kg = tw.gauss_kl(layer.q_mu, None if form == 'none' else T64(qd).cuda())
+    close('kl', kg, ko)
