@@ -159,7 +159,13 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and is meant to use every host
+    # core the box gives this process, so the thread pools are sized from the affinity mask before torch is imported
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[var] = str(cores)
     import torch
+    torch.set_num_threads(cores)
     cfg = CONFIGS[args.config]
     X, Y = make_data(min(cfg['N'], 20000), cfg['D'], seed=0)
     spec = oracle_spec(cfg, X, Y)
