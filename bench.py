@@ -30,6 +30,19 @@ CONFIGS = {
 FP64_DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200 (profiles/FP64_PEAK_r01.md); MEASURED_PEAKS.json has no fp64 entry
 
 
+def _hbm_peak():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling recipe's
+    fallback figure."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs'])
+    except (OSError, KeyError, ValueError):
+        return 6650.0   # "of fallback" (B200_PROFILING.md)
+
+
+HBM_PEAK_GBS = _hbm_peak()
+
+
 _STDOUT = None
 
 
@@ -345,6 +358,8 @@ def main():
                      'peak_source': 'FP64 DMMA issue-rate probe measured on this pool (profiles/FP64_PEAK_r01.md); '
                                     'MEASURED_PEAKS.json carries only bf16 and HBM'},
         'kernels': kern,
+        'hbm_kernels': hbm_kernel_timings(eng, capi, LIB, torch, HBM_PEAK_GBS),
+        'hbm_peak_gbs': HBM_PEAK_GBS,
         'elbo_last': last_elbo,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -432,6 +447,58 @@ def kernel_timings(eng, capi, LIB, torch, reps=5):
         out.append({'kernel': name, 'layer': 'M=%d D=%d R=%d T=%d' % (M, D, R, T), 'ms': ms, 'gflop': fl / 1e9,
                     'tflops': fl / (ms * 1e-3) / 1e12, 'frac_of_fp64_dmma_peak': fl / (ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
                     'launches_per_step': n_like})
+    return out
+
+
+def hbm_kernel_timings(eng, capi, LIB, torch, hbm_gbs, reps=20):
+    """The fused elementwise / reduction stages of the step (HBM-bound), each timed alone with CUDA events
+    on the buffers the last step left behind.  Algorithmic bytes = unique input + output bytes of the launch.  At c3 the
+    working sets are 0.2-8 MB (L2-resident, a few microseconds per launch): the fractions say how far launch latency
+    keeps these from the HBM copy peak, they are not where the step's time goes."""
+    T, B, K = eng.T, eng.B, eng.K
+    out = []
+
+    def timed(name, fn, nbytes, note):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        gbs = nbytes / (us * 1e-6) / 1e9
+        out.append({'kernel': name, 'us': us, 'algorithmic_mb': nbytes / 1e6, 'gbs': gbs,
+                    'frac_of_hbm_peak': gbs / hbm_gbs, 'bytes': note})
+
+    lv = eng.lv_recs[0] if eng.lv_recs else None
+    if lv is not None and lv.get('bcast'):
+        Lw, Df, Dxy = lv['Lw'], lv['Df'], eng.Dx + eng.Dy
+        timed('normal_fill_kernel', lambda: capi.normal_fill(lv['eps'], T, Lw, 0, 1234), 8 * T * Lw, '8*T*Lw written')
+        timed('lv_fwd_kernel',
+              lambda: capi.lv_fwd(lv['d'], eng.X, eng.XY, lv['params'], lv['eps'], lv['samples'], lv['kl'], lv['mu'],
+                                  lv['sigma']),
+              8 * (T * (Lw + Df + Lw + Lw) + B * (Df + Dxy + 2 * Lw)),
+              '8*[T*(eps Lw + samples Df+Lw + kl Lw) + B*(X + XY + mu,sigma)]')
+    gps = [r for r in eng.recs if r['type'] == 'gp']
+    inner = [r for r in gps if r['sampled']]
+    if inner:
+        r = inner[-1]
+        timed('normal_fill_kernel[T,R]', lambda: capi.normal_fill(r['eps'], T, r['R'], 0, 99), 8 * T * r['R'], '8*T*R written')
+    last = gps[-1]
+    lik = eng.flat.cview(eng.model.likelihood.variance)
+    kl_local = eng.lv_recs[0]['kl'] if len(eng.lv_recs) == 1 else eng.kl_cat
+    Lw_t, Dy = eng.Lw_total, eng.Dy
+    timed('elbo_fwd_kernel(+final)',
+          lambda: capi.iwelbo_fwd(eng.ed, last['mean'], last['var'], eng.Y, lik, kl_local, eng.elbo_data, eng.logp, eng.w,
+                                  eng.elbo_ws),
+          8 * (T * (2 * Dy + Lw_t + 1) + B * (Dy + 1)), '8*[T*(mean,var 2Dy + kl Lw + w 1) + B*(Y + logp)]')
+    gl = torch.zeros_like(eng.flat.gview(eng.model.likelihood.variance))
+    timed('elbo_bwd_kernel(+final)',
+          lambda: capi.iwelbo_bwd(eng.ed, last['mean'], last['var'], eng.Y, lik, eng.w, eng.one, eng.dmean, eng.dvar,
+                                  eng.dkl_local, gl, eng.elbo_ws),
+          8 * (T * (2 * Dy + 1 + 2 * Dy + Lw_t) + B * Dy), '8*[T*(mean,var,w read; dmean,dvar,dkl written) + B*Y]')
     return out
 
 
