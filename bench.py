@@ -459,12 +459,18 @@ def hbm_kernel_timings(eng, capi, LIB, torch, hbm_gbs, reps=20):
     out = []
 
     def timed(name, fn, nbytes, note):
+        # `reps` launches replayed as one CUDA graph: an eager loop of microsecond kernels times the host, not the GPU
         fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(reps):
+                fn()
+        graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            fn()
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / reps * 1e3

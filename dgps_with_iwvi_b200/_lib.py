@@ -50,6 +50,7 @@ SIGNATURES = {
     'iwvi_gp_rows_fwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 12),
     'iwvi_gp_rows_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 23),
     'iwvi_gp_prologue_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 16),
+    'iwvi_gp_fullcov_fwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 5 + [C.c_double] + [P] * 4),
     'iwvi_gauss_kl_fwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 4),
     'iwvi_gauss_kl_bwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 6),
     'iwvi_lv_param_doubles': (C.c_int64, [C.POINTER(LvDesc)]),

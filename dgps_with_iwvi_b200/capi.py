@@ -126,6 +126,13 @@ def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls
             'iwvi_gp_prologue_bwd')
 
 
+def gp_fullcov_fwd(d, S, N, aux, X, save, mean, eps, chol_jitter, cov, sample, info):
+    _count(1)
+    L.check(L.load().iwvi_gp_fullcov_fwd(C.byref(d), int(S), int(N), _ptr(aux), _ptr(X), _ptr(save), _ptr(mean),
+                                         _ptr(eps), float(chol_jitter), _ptr(cov), _ptr(sample), _ptr(info), _stream()),
+            'iwvi_gp_fullcov_fwd')
+
+
 def gauss_kl_fwd(M, R, q_mu, q_sqrt, kl):
     _count(1)
     L.check(L.load().iwvi_gauss_kl_fwd(int(M), int(R), _ptr(q_mu), _ptr(q_sqrt), _ptr(kl), _stream()), 'iwvi_gauss_kl_fwd')

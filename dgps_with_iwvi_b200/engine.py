@@ -219,6 +219,8 @@ class Engine:
         self.ev_pbwd = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.side_b = torch.cuda.Stream(device=dev)      # second half of the first GP layer's reductions (backward)
         self.ev_part_b = torch.cuda.Event()
+        self.ev_elbo, self.ev_loss = torch.cuda.Event(), torch.cuda.Event()
+        self._loss_pending = False
         self.X_tiled = None
         if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
             self.X_tiled = z(T, self.Dx)
@@ -263,7 +265,9 @@ class Engine:
             else:
                 capi.normal_fill(buf, self.T, buf.shape[1], first, layer_seed(seed, step + step_add, r['idx']))
 
-    def forward(self):
+    def forward(self, join=True):
+        """join=False: the two-kernel assembly of the loss slot (data term minus the global KLs) is left running on a side
+        stream and joined at the end of backward(), off the critical path between the forward and the backward pass."""
         flat = self.flat
         flat.refresh_constrained()
         main = torch.cuda.current_stream()
@@ -328,9 +332,21 @@ class Engine:
         capi.iwelbo_fwd(self.ed, last['mean'], last['var'], self.Y, lik, kl_local, self.elbo_data, self.logp, self.w,
                         self.elbo_ws)
         # ELBO of this rank's shard; the global KL enters with weight 1/world_size so that a SUM all-reduce is exact
-        torch.sub(self.elbo_data, self.kls[:self.n_gp].sum().reshape(1), alpha=1.0 / self.world_size,
-                  out=flat.loss_slot)
+        self.ev_elbo.record(main)
+        self.side_b.wait_event(self.ev_elbo)
+        with torch.cuda.stream(self.side_b):
+            torch.sub(self.elbo_data, self.kls[:self.n_gp].sum().reshape(1), alpha=1.0 / self.world_size,
+                      out=flat.loss_slot)
+            self.ev_loss.record(self.side_b)
+        self._loss_pending = True
+        if join:
+            self._join_loss()
         return flat.loss_slot
+
+    def _join_loss(self):
+        if self._loss_pending:
+            torch.cuda.current_stream().wait_event(self.ev_loss)
+            self._loss_pending = False
 
     def backward(self):
         flat = self.flat
@@ -419,12 +435,13 @@ class Engine:
             main.wait_event(ev)
         if self.n_gp:
             main.wait_event(self.ev_part_b)
+        self._join_loss()
         return flat.g
 
     def elbo_and_grads(self, X, Y, eps=None, seed=0, step=0, row0=0):
         self.set_batch(X, Y)
         self.draw_noise(eps, seed, step, row0)
-        loss = self.forward()
+        loss = self.forward(join=False)
         self.backward()
         return loss
 

@@ -18,7 +18,8 @@ Not on the hot path and therefore not in CUDA (raise NotImplementedError): white
 layers.py:42) and full_output_cov=True.  q_sqrt=None (:174-184, SGHMC) and the 2-D diagonal q_sqrt (:72-73) are mapped
 onto the same kernels (zero / diagonal Cholesky factors).  full_cov=True
 (:55-57,82-83, whose joint sampler :92-96 has a shape bug and is dead code in training) is served
-forward-only from the saved A / U panels with library GEMMs, for predict_f_full_cov and API completeness."""
+forward-only by iwvi_gp_fullcov_fwd (csrc/gp_fullcov.cu: DMMA Gram products on the saved A / U panels, shared-memory
+Cholesky, corrected joint draw), for predict_f_full_cov and API completeness."""
 import numpy as np
 import torch
 
@@ -45,12 +46,6 @@ def _t(v, dev=None):
 
 def _c(t):
     return None if t is None else t.detach().contiguous()
-
-
-def _unblock(save, off, Tp, NB):
-    """Block-major [Tp/64][NB][64][68] panel (csrc/common.cuh SaveLayout) -> [Tp, 64*NB] row-major view copy."""
-    v = save[off:off + (Tp // 64) * NB * 64 * 68].view(Tp // 64, NB, 64, 68)[..., :64]
-    return v.permute(0, 2, 1, 3).reshape(Tp, NB * 64)
 
 
 class _GPConditional(torch.autograd.Function):
@@ -121,20 +116,6 @@ def _kern_parts(kern):
     return mix, base
 
 
-def _torch_K(kind, X, X2, ls, variance):
-    """Stationary kernel matrix in torch (GPflow 1.x formulas) -- only for the forward-only full-cov branch."""
-    Xs, X2s = X / ls, X2 / ls
-    r2 = (Xs * Xs).sum(-1)[..., :, None] + (X2s * X2s).sum(-1)[..., None, :] - 2.0 * Xs @ X2s.transpose(-1, -2)
-    if kind == 'RBF':
-        return variance * torch.exp(-0.5 * r2)
-    r = torch.sqrt(torch.clamp(r2, min=1e-40))
-    if kind == 'Matern12':
-        return variance * torch.exp(-r)
-    if kind == 'Matern32':
-        return variance * (1.0 + 3.0 ** 0.5 * r) * torch.exp(-3.0 ** 0.5 * r)
-    return variance * (1.0 + 5.0 ** 0.5 * r + 5.0 / 3.0 * r * r) * torch.exp(-5.0 ** 0.5 * r)
-
-
 def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=False, q_sqrt=None, white=False,
                                                eps=None, mean_function=None, jitter=1e-6, W=None, sample=True):
     """Reference temp_workaround.py:12-98.  Xnew [S, N, D] (or [T, D]); f = q_mu [M, R]; q_sqrt [R, M, M].
@@ -175,30 +156,31 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
     mean_o = mean.reshape(*lead, P)
     if not full_cov:
         return (smp.reshape(*lead, P) if e is not None else None), mean_o, var.reshape(*lead, P)
-    # ---- full covariance over the inner axis (forward only; library GEMMs on the saved panels) ----
+    # ---- full covariance over the inner axis and the joint draw (forward only): iwvi_gp_fullcov_fwd on the saved panels
     if Wt is not None:
         raise NotImplementedError('the Mok branch forces full_cov=False (temp_workaround.py:125-129)')
+    S_ = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
+    N = lead[-1]
+    if N > 64:
+        raise NotImplementedError('full_cov=True is built for inner axes of at most 64 points (N = %d)' % N)
     with torch.no_grad():
         save, Lm, aux, d = meta['_save']
-        S_ = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
-        N = lead[-1]
-        Tp = (T + 127) // 128 * 128
-        NB = capi.gp_mp(M) // 64
-        stride = (Tp // 64) * NB * 64 * 68
-        A = _unblock(save, 0, Tp, NB)[:T].reshape(S_, N, NB * 64)
-        Knn = _torch_K(kern.kind, X.reshape(S_, N, D), X.reshape(S_, N, D), ls_vec, variance)
-        base = Knn - A @ A.transpose(1, 2)                                     # [S, N, N]
-        cov = []
-        for r in range(R):
-            U = _unblock(save, (1 + r) * stride, Tp, NB)[:T].reshape(S_, N, NB * 64)
-            cov.append(base + U @ U.transpose(1, 2))
-        cov = torch.stack(cov, 1)                                              # [S, R, N, N]
-        smp_o = None
+        cov = torch.zeros(S_, R, N, N, dtype=F64, device=X.device)
+        info = torch.zeros(1, dtype=torch.int32, device=X.device)
+        smp_o = z = None
         if sample:
-            # the joint draw the reference intends at :92-96 (its own version has a shape bug and never executes)
-            z = torch.randn(S_, R, N, 1, dtype=F64, device=X.device) if eps is None else _t(eps).reshape(S_, R, N, 1)
-            Lc = torch.linalg.cholesky(cov)
-            smp_o = (mean.reshape(S_, N, R).transpose(1, 2)[..., None] + Lc @ z)[..., 0].transpose(1, 2).reshape(*lead, R)
+            # the joint draw the reference intends at :92-96, in its [S, R, N, 1] noise order (:93-94)
+            z = torch.randn(S_, R, N, dtype=F64, device=X.device) if eps is None else _c(_t(eps).reshape(S_, R, N))
+            smp_o = torch.zeros(T, R, dtype=F64, device=X.device)
+        # 3-D inputs: tf.cholesky(fvar) as is (:95); 2-D inputs go through gpflow's _sample_mvn, which adds the jitter
+        capi.gp_fullcov_fwd(d, S_, N, aux, _c(X2), save, mean.detach(), z, 0.0 if len(lead) > 1 else float(jitter), cov,
+                            smp_o, info)
+        if sample:
+            i = int(info.item())
+            if i:
+                raise RuntimeError('Cholesky of the covariance over the inner axis failed: leading minor of order %d '
+                                   'is not positive definite' % i)
+            smp_o = smp_o.reshape(*lead, R)
     if len(lead) == 1:
         cov = cov[0]
     return smp_o, mean_o, cov

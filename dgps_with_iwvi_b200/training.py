@@ -60,7 +60,7 @@ class Trainer:
     # ---- the two halves of a step, written against device-side state only (capturable) ----
     def _fwd_bwd(self, row0):
         self.engine.draw_noise(None, seed=self.seed, row0=row0, state=self.state)
-        self.engine.forward()
+        self.engine.forward(join=False)
         self.engine.backward()
 
     def _update(self):

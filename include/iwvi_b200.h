@@ -152,6 +152,19 @@ int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* 
                          double* ws, void* stream);
 
 /*
+ * Covariance over the inner axis and the joint draw, forward, for plain-kernel layers: the full_cov=True branch of
+ * independent_multisample_sample_conditional (temp_workaround.py:45, :55-57, :82-83) and the joint sampler intended at
+ * :92-96 (the reference's own lines add an [S,N,R] mean to an [S,R,N,1] draw and never execute).  Runs after
+ * iwvi_gp_rows_fwd with IWVI_FLAG_SAVE on the same descriptor (d->T == S*N, d->mix == 0, N <= 64):
+ *   X [S*N,D]; save (A, U_r panels); mean [S*N,R] as written by iwvi_gp_rows_fwd; eps [S,R,N] (the [S,R,N,1] draw of :94)
+ *   out: cov [S,R,N,N] = k(X_s,X_s) - A_s^T A_s + U_rs^T U_rs (or NULL);
+ *        sample [S*N,R] = mean + chol(cov + chol_jitter I) eps (or NULL); info [1] (int32, first failing leading minor).
+ */
+int iwvi_gp_fullcov_fwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const double* aux, const double* X,
+                        const double* save, const double* mean, const double* eps, double chol_jitter,
+                        double* cov, double* sample, int32_t* info, void* stream);
+
+/*
  * Whitened KL[q(u)||p(u)] on its own, for callers of the operator-level gauss_kl(q_mu, q_sqrt) (temp_workaround.py:167-188
  * with K=None -> gpflow gauss_kl): kl = 0.5 (sum q_mu^2 - M R - sum log diag(Lq)^2 + sum Lq^2), Lq = tril(q_sqrt).
  * iwvi_gp_prologue_fwd returns the same number as a by-product.  dkl [1] device scalar cotangent; outputs overwritten.

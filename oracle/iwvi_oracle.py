@@ -199,11 +199,13 @@ class MeanFunction:
 # ----------------------------------------------------------------------------------------------
 
 def independent_multisample_sample_conditional(Xnew, Z, kern, f, *, full_cov=False, full_output_cov=False,
-                                               q_sqrt=None, white=False, eps=None, jitter=JITTER):
+                                               q_sqrt=None, white=False, eps=None, jitter=JITTER, eps_joint=None):
     """temp_workaround.py:12-98.  Xnew [S,N,D]; Z [M,D]; f [M,R]; q_sqrt [R,M,M] | [M,R] | None.
     eps [S,N,R] replaces tf.random_normal at :89.  Returns sample [S,N,R], fmean [S,N,R],
     fvar [S,N,R] (diag) or [S,R,N,N] (full_cov).  With full_cov=True the sample is None: the
-    reference's full-cov sampler (:93-96) has a shape bug and is dead code in training."""
+    reference's full-cov sampler (:93-96) has a shape bug and is dead code in training.
+    eps_joint [S,R,N] (the [S,R,N,1] draw of :94) asks for the joint draw those lines intend:
+    sample[s,:,r] = fmean[s,:,r] + chol(fvar[s,r]) z[s,r]  (no jitter, :95)."""
     if full_output_cov:
         raise NotImplementedError
     Kmm = Kuu(Z, kern, jitter)                                        # :39
@@ -239,8 +241,12 @@ def independent_multisample_sample_conditional(Xnew, Z, kern, f, *, full_cov=Fal
     if not full_cov:
         fvar = fvar.transpose(-1, -2)                                 # :90
         sample = None if eps is None else fmean + eps * fvar ** 0.5   # :91
-    else:
+    elif eps_joint is None:
         sample = None                                                 # :93-96 dead / buggy in the reference
+    else:
+        z = eps_joint.reshape(S, num_func, N, 1)                      # :93-94
+        sample_SRN1 = fmean.transpose(1, 2)[..., None] + torch.linalg.cholesky(fvar) @ z   # :95 with the mean transposed
+        sample = sample_SRN1[..., 0].transpose(1, 2)                  # :96
     return sample, fmean, fvar
 
 

@@ -187,3 +187,36 @@ def test_conditional_q_sqrt_none_and_diagonal(form):
     ko = O.gauss_kl(ol.q_mu, None if form == 'none' else T64(np.stack([np.diag(qd[:, r]) for r in range(2)])))
     kg = tw.gauss_kl(layer.q_mu, None if form == 'none' else T64(qd).cuda())
     close('kl', kg, ko)
+
+
+@pytest.mark.parametrize('S_,N,M,kern', [(5, 50, 100, 'RBF'), (3, 64, 37, 'Matern52'), (7, 8, 64, 'Matern32'),
+                                         (4, 1, 29, 'RBF'), (2, 20, 130, 'Matern12')])
+def test_full_cov_joint_draw(S_, N, M, kern):
+    """iwvi_gp_fullcov_fwd: covariance over the inner axis [S, R, N, N] (temp_workaround.py:55-57,82-83) and the joint
+    draw the reference intends at :92-96 (noise in its [S, R, N, 1] order), against the oracle; groups straddle the
+    64-point chunks of the saved panels, N is not a multiple of 8, M is not a multiple of 64."""
+    from dgps_with_iwvi_b200 import temp_workaround as tw
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    D = 3
+    X, Y = S.make_data(max(M, 40), D, seed=11)
+    spec = S.make_spec(X, 'G2', M, 3, seed=11, perturb=0.3, inner_q_sqrt_scale=0.3, kern=kern)
+    layer = model_from_spec(spec, X, Y).layers[0]
+    omodel, _ = O.build_from_spec(spec)
+    ol = omodel.layers[0]
+    okern = ol.kern.kernel if isinstance(ol.kern, O.Mok) else ol.kern
+    gkern = layer.kern.kernel if hasattr(layer.kern, 'W') else layer.kern
+    R = ol.q_mu.shape[1]
+    rng = np.random.default_rng(5)
+    F = rng.standard_normal((S_, N, D)); z = rng.standard_normal((S_, R, N))
+    so, mo, vo = O.independent_multisample_sample_conditional(T64(F), ol.Z, okern, ol.q_mu, full_cov=True,
+                                                              q_sqrt=ol.q_sqrt, white=True, eps_joint=T64(z))
+    s, m, v = tw.independent_multisample_sample_conditional(T64(F).cuda(), layer.feature, gkern, layer.q_mu,
+                                                            full_cov=True, q_sqrt=layer.q_sqrt, white=True,
+                                                            eps=T64(z).cuda())
+    assert v.shape == (S_, R, N, N) and s.shape == (S_, N, R)
+    # Matern12 is not smooth at r = 0: r = sqrt(max(r2, 1e-40)) turns the rounding noise of the expanded-form r2 on the
+    # Kuu diagonal into ~1e-8 noise, in the reference as much as here (see tests/test_gpu_stages.py)
+    tol = 1e-6 if kern == 'Matern12' else RTOL
+    close('mean', m, mo, tol); close('cov', v, vo, tol); close('sample', s, so, tol)
+    # exact symmetry of the DMMA Gram products
+    assert torch.equal(v, v.transpose(-1, -2))

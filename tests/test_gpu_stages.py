@@ -331,3 +331,57 @@ def test_ill_conditioned_kuu_forward():
     scale = L['variance']
     assert np.abs(mean.cpu().numpy() - ref['mean']).max() < 1e-6 * max(np.abs(ref['mean']).max(), 1.0)
     assert np.abs(var.cpu().numpy() - ref['var']).max() < 1e-6 * scale
+
+
+def test_fullcov_stage_info_and_errors():
+    """iwvi_gp_fullcov_fwd through the raw C ABI: covariance over the inner axis against numpy on the saved panels'
+    algebra, the LAPACK-style info of a failing inner Cholesky, and the descriptor checks."""
+    import ctypes as C
+    from dgps_with_iwvi_b200 import capi
+    from dgps_with_iwvi_b200 import _lib as LIB
+    S_, N, M, D, R = 6, 20, 70, 3, 2
+    T = S_ * N
+    rng = np.random.default_rng(17)
+    L = make_layer(rng, T, M, D, R, R, False, 'Zero', 'RBF')
+    g = run_prologue(L)
+    df = capi.with_flags(g['d'], LIB.FLAG_SAVE)
+    X = dev(L['X'])
+    mean, var = torch.zeros(T, R, dtype=torch.float64, device='cuda'), torch.zeros(T, R, dtype=torch.float64, device='cuda')
+    save = torch.zeros(capi.gp_save_doubles(df), dtype=torch.float64, device='cuda')
+    capi.gp_rows_fwd(df, g['Lm'], g['aux'], X, None, None, None, None, None, mean, var, save)
+    z = dev(rng.standard_normal((S_, R, N)))
+    cov = torch.full((S_, R, N, N), float('nan'), dtype=torch.float64, device='cuda')
+    smp = torch.full((T, R), float('nan'), dtype=torch.float64, device='cuda')
+    info = torch.zeros(1, dtype=torch.int32, device='cuda')
+    capi.gp_fullcov_fwd(df, S_, N, g['aux'], X, save, mean, z, 0.0, cov, smp, info)
+    assert int(info.item()) == 0
+    # numpy restatement of temp_workaround.py:44-57,78-83 for this layer
+    Xs, Zs = L['X'] / L['ls'], L['Z'] / L['ls']
+    sq = lambda A, B: (A * A).sum(1)[:, None] + (B * B).sum(1)[None, :] - 2.0 * A @ B.T
+    Kmm = L['variance'] * np.exp(-0.5 * sq(Zs, Zs)) + 1e-6 * np.eye(M)
+    Lm = np.linalg.cholesky(Kmm)
+    A = np.linalg.solve(Lm, L['variance'] * np.exp(-0.5 * sq(Zs, Xs)))          # [M, T]
+    want = np.zeros((S_, R, N, N))
+    for s in range(S_):
+        sl = slice(s * N, (s + 1) * N)
+        base = L['variance'] * np.exp(-0.5 * sq(Xs[sl], Xs[sl])) - A[:, sl].T @ A[:, sl]
+        for r in range(R):
+            U = np.tril(L['q_sqrt'][r]).T @ A[:, sl]
+            want[s, r] = base + U.T @ U
+    close('cov', cov, want)
+    Lc = np.linalg.cholesky(want)
+    want_s = mean.cpu().numpy().reshape(S_, N, R) + np.einsum('srij,srj->sir', Lc, z.cpu().numpy())
+    close('sample', smp.reshape(S_, N, R), want_s)
+    # the diagonal of the covariance is the variance of the per-point kernel
+    close('diag', torch.diagonal(cov, dim1=-2, dim2=-1).permute(0, 2, 1).reshape(T, R), var.cpu().numpy())
+    # a negative shift makes every inner Cholesky fail at its first pivot
+    capi.gp_fullcov_fwd(df, S_, N, g['aux'], X, save, mean, z, -10.0, None, smp, info)
+    assert int(info.item()) == 1
+    lib = LIB.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    args = [g['aux'].data_ptr(), X.data_ptr(), save.data_ptr(), mean.data_ptr(), z.data_ptr(), 0.0, cov.data_ptr(),
+            smp.data_ptr(), info.data_ptr(), stream]
+    assert lib.iwvi_gp_fullcov_fwd(C.byref(df), S_, N + 1, *args) == -1           # S*N != T
+    assert lib.iwvi_gp_fullcov_fwd(C.byref(capi.with_flags(df, df.flags, T=65 * 2)), 2, 65, *args) == -2   # N > 64
+    mixed = capi.gp_desc(T, M, D, R, 4, 'RBF', True, 'Zero', LIB.FLAG_SAVE, 1e-6)
+    assert lib.iwvi_gp_fullcov_fwd(C.byref(mixed), S_, N, *args) == -1            # the Mok branch forces full_cov=False

@@ -247,3 +247,32 @@ def test_natgrad_conjugate_model_reaches_optimum_in_one_step():
     mu_opt = S_opt @ A @ resid / s2
     np.testing.assert_allclose(mu1.numpy(), mu_opt, rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose((L1[0] @ L1[0].t()).numpy(), S_opt, rtol=1e-7, atol=1e-10)
+
+
+def test_joint_draw_reduces_to_diagonal_draw():
+    """The corrected joint sampler (temp_workaround.py:92-96 as intended) pins against the diagonal one (:89-91): with one
+    point per group chol(fvar) = sqrt(fvar), and for any N the draw is mean + L z with L L^T = fvar."""
+    import numpy as np
+    import torch
+    from oracle import iwvi_oracle as O
+    from oracle import synthetic as S
+    X, Y = S.make_data(40, 3, seed=2)
+    spec = S.make_spec(X, 'G2', 17, 3, seed=2, perturb=0.3, inner_q_sqrt_scale=0.3)
+    model, _ = O.build_from_spec(spec)
+    l = model.layers[0]
+    kern = l.kern.kernel if isinstance(l.kern, O.Mok) else l.kern
+    rng = np.random.default_rng(0)
+    R = l.q_mu.shape[1]
+    F = torch.as_tensor(rng.standard_normal((6, 1, 3)))
+    z = torch.as_tensor(rng.standard_normal((6, R, 1)))
+    sj, mj, vj = O.independent_multisample_sample_conditional(F, l.Z, kern, l.q_mu, full_cov=True, q_sqrt=l.q_sqrt,
+                                                              white=True, eps_joint=z)
+    sd, md, vd = O.independent_multisample_sample_conditional(F, l.Z, kern, l.q_mu, full_cov=False, q_sqrt=l.q_sqrt,
+                                                              white=True, eps=z.transpose(1, 2))
+    assert torch.allclose(sj, sd, rtol=1e-12, atol=1e-14) and torch.allclose(mj, md, rtol=1e-13, atol=1e-15)
+    F = torch.as_tensor(rng.standard_normal((2, 9, 3)))
+    z = torch.as_tensor(rng.standard_normal((2, R, 9)))
+    sj, mj, vj = O.independent_multisample_sample_conditional(F, l.Z, kern, l.q_mu, full_cov=True, q_sqrt=l.q_sqrt,
+                                                              white=True, eps_joint=z)
+    L = torch.linalg.cholesky(vj)
+    assert torch.allclose((sj - mj).transpose(1, 2)[..., None], L @ z[..., None], rtol=1e-12, atol=1e-14)
