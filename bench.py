@@ -220,6 +220,11 @@ def main():
     ap.add_argument('--config', default='c3', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-reference-iteration', action='store_true',
+                    help='skip the extra timing of the reference-faithful iteration (NatGrad + Adam, N=1 only)')
+    ap.add_argument('--global-rows', type=int, default=0,
+                    help='strong scaling: fix the GLOBAL minibatch (rows) and split it over the GPUs (SURVEY.md 8(d): 4096 '
+                         'for c3); default 0 = weak scaling with the config\'s rows per GPU')
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that chat on stdout (NCCL prints its version there) are sent to
     # stderr for the duration of the run, and the line is written to the saved descriptor
@@ -247,7 +252,12 @@ def main():
     from dgps_with_iwvi_b200.models import Minibatch
     from dgps_with_iwvi_b200.training import Trainer
 
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    strong = args.global_rows > 0
+    if strong:
+        if args.global_rows % world:
+            raise SystemExit('bench.py: --global-rows %d is not divisible by %d GPUs' % (args.global_rows, world))
+        cfg['B'] = args.global_rows // world
     B, K, N = cfg['B'], cfg['K'], cfg['N']
     Bg = B * world
     X, Y = make_data(N, cfg['D'], seed=0)
@@ -342,7 +352,8 @@ def main():
     out = {
         'metric': 'iw_elbo_train_KxN_samples_per_s', 'value': value, 'unit': 'KxN samples/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'steps_per_s': 1.0 / sec,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
         'config': workload_config(args.config, cfg, world),
         'clocks': clocks,
         'e2e': {'value': Bg * K / (ms_e2e / 1e3 / args.steps), 'unit': 'KxN samples/s',
@@ -374,9 +385,51 @@ def main():
                                'sample': 'oracle (torch-CPU fp64 restatement of the reference, KxK final layer) '
                                          'forward+autograd on %d of %d minibatch rows x K=%d, %d evals after warm-up, no '
                                          'optimiser step' % (Bs, B, K, reps)}
+        # the same oracle with the final layer's variance taken directly (the maths the GPU path runs)
+        t_diag, _ = cpu_eval_time(cfg, spec, X, Y, Bs, reps=3, warm=1, reference_style=False)
+        out['cpu_baseline']['value_diag_only'] = Bs * K / float(np.mean(t_diag))
+    if world == 1 and not args.no_reference_iteration:
+        out['reference_iteration'] = reference_iteration_timing(cfg, X, Y, torch)
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_iteration_timing(cfg, X, Y, torch, iters=20, warm=3):
+    """the reference-faithful training iteration (experiments/build_models.py:284-300) -- a NatGrad step
+    on the last layer's q(u) evaluated on one minibatch, then an Adam step on everything else evaluated on a second one:
+    two IW-ELBO forward+backward passes per iteration.  Reported beside the headline (one pass + Adam per step)."""
+    from dgps_with_iwvi_b200.build_models import build_model
+    from dgps_with_iwvi_b200.models import Minibatch
+    from dgps_with_iwvi_b200.training import ReferenceIterationTrainer
+    B, K, N = cfg['B'], cfg['K'], cfg['N']
+    model = build_model(X, Y, cfg['configuration'], M=cfg['M'], num_IW_samples=K, minibatch_size=B,
+                        likelihood_variance=cfg['lik_variance'], mode='IWAE', seed=0)
+    tr = ReferenceIterationTrainer(model, B, lr=5e-3, gamma=1e-2, seed=0)
+    dev = tr.engine.dev
+    mb = Minibatch(N, B, seed=1)
+    idx = torch.as_tensor(np.stack([mb.next() for _ in range(2 * (iters + warm))]), device=dev)
+    Xd, Yd = model.X, model.Y
+
+    def it(i):
+        a, b = idx[2 * i], idx[2 * i + 1]
+        return tr.iteration(Xd[a], Yd[a], Xd[b], Yd[b])
+
+    for i in range(warm):
+        it(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        elbo_ng, elbo_adam = it(warm + i)
+    e1.record()
+    torch.cuda.synchronize()
+    tr.engine.check_info()
+    sec = e0.elapsed_time(e1) / 1e3 / iters
+    return {'ms_per_iteration': sec * 1e3, 'iterations_per_s': 1.0 / sec, 'KxN_samples_per_s': 2 * B * K / sec,
+            'iterations': iters, 'elbo_last': float(elbo_adam.item()),
+            'what': 'NatGrad(gamma=1e-2) on the last GP layer\'s q_mu/q_sqrt + Adam(5e-3) on the rest, two minibatches and '
+                    'two forward+backward passes per iteration (build_models.py:284-300); eager launches, no CUDA graph'}
 
 
 def ncu_traffic(config, kernel):
