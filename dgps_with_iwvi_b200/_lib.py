@@ -15,6 +15,7 @@ MF_IDS = {'Zero': 0, 'Identity': 1, 'Linear': 2}
 FLAG_SAMPLE, FLAG_SAVE, FLAG_ACCUM = 1, 2, 4
 FLAG_ONLY_EPI, FLAG_ONLY_TILE, FLAG_ONLY_REDUCE, FLAG_ONLY_FINAL = 16, 32, 64, 128
 FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
+FLAG_NO_KDIAG = 4096
 
 ERRORS = {-1: 'bad descriptor', -2: 'unsupported size', -3: 'CUDA launch failure', -4: 'null pointer'}
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     'iwvi_gp_rows_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 23),
     'iwvi_gp_prologue_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 16),
     'iwvi_gp_fullcov_fwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 5 + [C.c_double] + [P] * 4),
+    'iwvi_gp_fullcov_bwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 4 + [C.c_double] + [P] * 6),
     'iwvi_gauss_kl_fwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 4),
     'iwvi_gauss_kl_bwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 6),
     'iwvi_lv_param_doubles': (C.c_int64, [C.POINTER(LvDesc)]),

@@ -133,6 +133,13 @@ def gp_fullcov_fwd(d, S, N, aux, X, save, mean, eps, chol_jitter, cov, sample, i
             'iwvi_gp_fullcov_fwd')
 
 
+def gp_fullcov_bwd(d, S, N, aux, X, save, eps, chol_jitter, d_sample, d_cov, save2, dX_knn, part):
+    _count(1)
+    L.check(L.load().iwvi_gp_fullcov_bwd(C.byref(d), int(S), int(N), _ptr(aux), _ptr(X), _ptr(save), _ptr(eps),
+                                         float(chol_jitter), _ptr(d_sample), _ptr(d_cov), _ptr(save2), _ptr(dX_knn),
+                                         _ptr(part), _stream()), 'iwvi_gp_fullcov_bwd')
+
+
 def gauss_kl_fwd(M, R, q_mu, q_sqrt, kl):
     _count(1)
     L.check(L.load().iwvi_gauss_kl_fwd(int(M), int(R), _ptr(q_mu), _ptr(q_sqrt), _ptr(kl), _stream()), 'iwvi_gauss_kl_fwd')

@@ -12,8 +12,9 @@
 //
 // A = Lm^-1 Kuf and U_r = tril(q_sqrt_r)^T A are the block-major panels iwvi_gp_rows_fwd saved (IWVI_FLAG_SAVE); `mean`
 // is its output (mean function included, layers.py:46-48).  One CTA owns a group: the N x N Gram products run on the
-// FP64 tensor pipe (DMMA, one 8-row tile of C per warp), operands staged one 64-wide m-block at a time; the N x N
-// Cholesky (N <= 64) is a right-looking factorisation in shared memory, one barrier pair per column.
+// FP64 tensor pipe (DMMA, one 8-row tile of C per warp), operands staged one 64-wide m-block at a time; covariances
+// of any N are produced in 64 x 64 blocks; the joint draw (N <= 64) factorises C_r by a right-looking Cholesky in
+// shared memory, a few barriers per column.
 #include "common.cuh"
 
 namespace {
@@ -30,11 +31,12 @@ struct FullCovParams {
   int* info;
 };
 
-// acc[j][c] (+)= sum_m P(8 w + g, m) P(8 j + 2 t + c, m) over the 64 columns of one staged slab P [Np][68]
-__device__ __forceinline__ void slab_syrk(double (&acc)[8][2], const double* __restrict__ slab, int warp, int lane, int ntn) {
+// acc[j][c] (+)= sum_m Pi(8 w + g, m) Pj(8 j + 2 t + c, m) over the 64 columns of the staged slabs Pi, Pj [64][68]
+__device__ __forceinline__ void slab_syrk(double (&acc)[8][2], const double* __restrict__ slab_i,
+                                          const double* __restrict__ slab_j, int warp, int lane, int ntn) {
   const int g = lane >> 2, t = lane & 3;
-  const double* ap = slab + (warp * 8 + g) * IWVI_LDS + t;
-  const double* bp = slab + g * IWVI_LDS + t;
+  const double* ap = slab_i + (warp * 8 + g) * IWVI_LDS + t;
+  const double* bp = slab_j + g * IWVI_LDS + t;
 #pragma unroll 4
   for (int k0 = 0; k0 < IWVI_BLK; k0 += 4) {
     const double a = ap[k0];
@@ -44,62 +46,92 @@ __device__ __forceinline__ void slab_syrk(double (&acc)[8][2], const double* __r
   }
 }
 
+// one m-block of a saved block-major panel, rows pt0 .. pt0 + n - 1 (rows >= n zero), into a [64][68] slab
+__device__ __forceinline__ void load_slab(double* slab, const double* __restrict__ panel, int64_t pt0, int n, int mb, int NB,
+                                          int tid) {
+  for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += FC_THREADS) {
+    const int r = idx >> 6, c = idx & 63;
+    slab[r * IWVI_LDS + c] = (r < n) ? panel[iwvi_blk_off((int)(pt0 + r), mb * IWVI_BLK + c, NB)] : 0.0;
+  }
+}
+
+// Work item = (group s, 64-point row block bi, 64-point column block bj) of the N x N covariances of the group; the
+// joint draw needs the whole matrix in one CTA and is built for N <= 64 (one block).
 __global__ void __launch_bounds__(FC_THREADS) gp_fullcov_fwd_kernel(const FullCovParams p) {
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
   const int N = p.N, R = d.R, D = d.D, NB = al.NB;
-  const int Np = iwvi_round_up(N, 8), ntn = Np / 8;
-  double* slab = smem;                               // [64][68] one m-block of A_s or U_{r,s}, rows >= N zero
-  double* C0 = slab + IWVI_STAGE_DOUBLES;            // [64][65] k(X_s, X_s) - A_s^T A_s
+  const int nblk = (N + IWVI_BLK - 1) / IWVI_BLK;
+  double* slab_i = smem;                             // [64][68] one m-block of A_s or U_{r,s}, row points of the item
+  double* slab_jb = slab_i + IWVI_STAGE_DOUBLES;     // the same for the column points (unused on diagonal items)
+  double* C0 = slab_jb + IWVI_STAGE_DOUBLES;         // [64][65] k(X_i, X_j) - A_i^T A_j
   double* Cr = C0 + IWVI_BLK * FC_LDC;               // [64][65] C_r, then its Cholesky factor
-  double* xs = Cr + IWVI_BLK * FC_LDC;               // [64][D] length-scaled inputs of the group
-  double* xn = xs + IWVI_BLK * IWVI_MAX_D;           // [64]
+  double* xs_i = Cr + IWVI_BLK * FC_LDC;             // [64][D] length-scaled inputs of the row / column points
+  double* xs_j = xs_i + IWVI_BLK * IWVI_MAX_D;
+  double* xn_i = xs_j + IWVI_BLK * IWVI_MAX_D;       // [64] squared norms
+  double* xn_j = xn_i + IWVI_BLK;
   __shared__ int bad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const double* consts = p.aux + al.off_consts;
   const double variance = consts[IWVI_C_VARIANCE];
-  const bool active = warp * 8 < Np;                 // this warp owns rows 8 warp .. 8 warp + 7 of C
+  const double* Apanel = p.save + sv.off_a;
 
-  for (int s = blockIdx.x; s < p.S; s += gridDim.x) {
-    const int64_t pt0 = (int64_t)s * N;
+  const int64_t n_items = (int64_t)p.S * nblk * nblk;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int s = (int)(item / (nblk * nblk));
+    const int bi = (int)(item % (nblk * nblk)) / nblk, bj = (int)(item % (nblk * nblk)) % nblk;
+    const int i0 = bi * IWVI_BLK, j0 = bj * IWVI_BLK;
+    const int ni = min(IWVI_BLK, N - i0), nj = min(IWVI_BLK, N - j0);
+    const int64_t pt_i = (int64_t)s * N + i0, pt_j = (int64_t)s * N + j0;
+    const bool diag = bi == bj;
+    const double* slab_j = diag ? slab_i : slab_jb;
+    const int ntn = iwvi_round_up(nj, 8) / 8;
+    const bool active = warp * 8 < iwvi_round_up(ni, 8);   // this warp owns rows 8 warp .. 8 warp + 7 of the block
     __syncthreads();
-    // ---- k(X_s, X_s) with gpflow's expanded squared distance
-    for (int idx = tid; idx < N * D; idx += FC_THREADS) {
+    // ---- k(X_i, X_j) with gpflow's expanded squared distance
+    for (int idx = tid; idx < ni * D; idx += FC_THREADS) {
       const int n = idx / D, k = idx - n * D;
-      xs[n * IWVI_MAX_D + k] = p.X[(pt0 + n) * D + k] * consts[IWVI_C_INVLS + k];
+      xs_i[n * IWVI_MAX_D + k] = p.X[(pt_i + n) * D + k] * consts[IWVI_C_INVLS + k];
+    }
+    for (int idx = tid; idx < nj * D; idx += FC_THREADS) {
+      const int n = idx / D, k = idx - n * D;
+      xs_j[n * IWVI_MAX_D + k] = p.X[(pt_j + n) * D + k] * consts[IWVI_C_INVLS + k];
     }
     __syncthreads();
-    if (tid < N) {
+    if (tid < ni) {
       double q = 0.0;
-      for (int k = 0; k < D; k++) { const double v = xs[tid * IWVI_MAX_D + k]; q += v * v; }
-      xn[tid] = q;
+      for (int k = 0; k < D; k++) { const double v = xs_i[tid * IWVI_MAX_D + k]; q += v * v; }
+      xn_i[tid] = q;
+    } else if (tid >= IWVI_BLK && tid - IWVI_BLK < nj) {
+      const int n = tid - IWVI_BLK;
+      double q = 0.0;
+      for (int k = 0; k < D; k++) { const double v = xs_j[n * IWVI_MAX_D + k]; q += v * v; }
+      xn_j[n] = q;
     }
     __syncthreads();
     for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += FC_THREADS) {
       const int i = idx >> 6, j = idx & 63;
       double v = 0.0;
-      if (i < N && j < N) {
+      if (i < ni && j < nj) {
         double dot = 0.0;
-        for (int k = 0; k < D; k++) dot += xs[i * IWVI_MAX_D + k] * xs[j * IWVI_MAX_D + k];
-        v = kern_k(d.kern, xn[i] + xn[j] - 2.0 * dot, variance);
+        for (int k = 0; k < D; k++) dot += xs_i[i * IWVI_MAX_D + k] * xs_j[j * IWVI_MAX_D + k];
+        v = kern_k(d.kern, xn_i[i] + xn_j[j] - 2.0 * dot, variance);
       }
       C0[i * FC_LDC + j] = v;
     }
-    // ---- C0 -= A_s^T A_s
+    // ---- C0 -= A_i^T A_j
     double acc[8][2];
 #pragma unroll
     for (int j = 0; j < 8; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
     for (int mb = 0; mb < NB; mb++) {
       __syncthreads();
-      for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += FC_THREADS) {
-        const int n = idx >> 6, c = idx & 63;
-        slab[n * IWVI_LDS + c] = (n < N) ? p.save[sv.off_a + iwvi_blk_off((int)(pt0 + n), mb * IWVI_BLK + c, NB)] : 0.0;
-      }
+      load_slab(slab_i, Apanel, pt_i, ni, mb, NB, tid);
+      if (!diag) load_slab(slab_jb, Apanel, pt_j, nj, mb, NB, tid);
       __syncthreads();
-      if (active) slab_syrk(acc, slab, warp, lane, ntn);
+      if (active) slab_syrk(acc, slab_i, slab_j, warp, lane, ntn);
     }
     if (active) {
 #pragma unroll
@@ -110,7 +142,8 @@ __global__ void __launch_bounds__(FC_THREADS) gp_fullcov_fwd_kernel(const FullCo
         }
     }
     for (int r = 0; r < R; r++) {
-      // ---- C_r = C0 + U_r^T U_r (accumulators start from this thread's own entries of C0)
+      // ---- C_r = C0 + U_ri^T U_rj (accumulators start from this thread's own entries of C0)
+      const double* Upanel = p.save + sv.off_u + (int64_t)r * sv.u_stride;
       __syncthreads();
       if (active) {
 #pragma unroll
@@ -122,13 +155,10 @@ __global__ void __launch_bounds__(FC_THREADS) gp_fullcov_fwd_kernel(const FullCo
       }
       for (int mb = 0; mb < NB; mb++) {
         __syncthreads();
-        for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += FC_THREADS) {
-          const int n = idx >> 6, c = idx & 63;
-          slab[n * IWVI_LDS + c] =
-              (n < N) ? p.save[sv.off_u + (int64_t)r * sv.u_stride + iwvi_blk_off((int)(pt0 + n), mb * IWVI_BLK + c, NB)] : 0.0;
-        }
+        load_slab(slab_i, Upanel, pt_i, ni, mb, NB, tid);
+        if (!diag) load_slab(slab_jb, Upanel, pt_j, nj, mb, NB, tid);
         __syncthreads();
-        if (active) slab_syrk(acc, slab, warp, lane, ntn);
+        if (active) slab_syrk(acc, slab_i, slab_j, warp, lane, ntn);
       }
       if (active) {
 #pragma unroll
@@ -141,14 +171,14 @@ __global__ void __launch_bounds__(FC_THREADS) gp_fullcov_fwd_kernel(const FullCo
       if (tid == 0) bad = 0;
       __syncthreads();
       if (p.cov) {
-        double* dst = p.cov + ((int64_t)s * R + r) * N * N;
-        for (int idx = tid; idx < N * N; idx += FC_THREADS) {
-          const int i = idx / N, j = idx - i * N;
-          dst[idx] = Cr[i * FC_LDC + j];
+        double* dst = p.cov + ((int64_t)s * R + r) * N * N + (int64_t)i0 * N + j0;
+        for (int idx = tid; idx < ni * nj; idx += FC_THREADS) {
+          const int i = idx / nj, j = idx - i * nj;
+          dst[(int64_t)i * N + j] = Cr[i * FC_LDC + j];
         }
       }
       if (!p.sample) continue;
-      // ---- right-looking Cholesky of C_r + chol_jitter I, in place (lower)
+      // ---- right-looking Cholesky of C_r + chol_jitter I, in place (lower); N <= 64: the item is the whole matrix
       for (int j = 0; j < N; j++) {
         __syncthreads();
         const double piv = Cr[j * FC_LDC + j] + p.chol_jitter;
@@ -170,10 +200,279 @@ __global__ void __launch_bounds__(FC_THREADS) gp_fullcov_fwd_kernel(const FullCo
       // ---- joint draw over the group
       if (tid < N) {
         const double* z = p.eps + ((int64_t)s * R + r) * N;
-        double v = p.mean[(pt0 + tid) * R + r];
+        double v = p.mean[(pt_i + tid) * R + r];
         for (int j = 0; j <= tid; j++) v += Cr[tid * FC_LDC + j] * z[j];
-        p.sample[(pt0 + tid) * R + r] = v;
+        p.sample[(pt_i + tid) * R + r] = v;
       }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Adjoint of the stage above, in a form the existing per-point backward kernels can finish.
+//
+// With H_r = sym(dC_r) + 1/2 L_r^-T (P + P^T) L_r^-1, P = Phi(L_r^T Lbar_r), Lbar_r = tril(dsmp_r z_r^T) (the TF / torch
+// Cholesky adjoint, symmetrised; here L^T Lbar is rank one below the diagonal: P_ij = q_i z_j with q = L^T dsmp_r), the
+// cotangent of A is
+//     Abar / 2 = q_mu gmean_bar^T / 2 - A_s (sum_r H_r) + sum_r tril(Lq_r) (U_rs H_r),
+// which is gp_tile_bwd_kernel's formula with the per-point scalings diag(gvar_bar_r) replaced by the N x N matrices H_r.
+// This kernel therefore writes, in the block-major layout of the saved panels,
+//     save2.A  = A_s (sum_r H_r) / R          save2.U_r = U_rs H_r
+// so that iwvi_gp_rows_bwd run on save2 with d_var = 1 (gvar_bar = 1, sum over r = R; IWVI_FLAG_NO_KDIAG) yields Bbar,
+// dX, dZ, dls, dvariance of the Kuf path; its parameter reductions (dLm = -tril(Bbar A^T), dq_mu = A gmean_bar,
+// dLq_r = 2 tril(A (U_r H_r)^T)) then need the ORIGINAL A back in save2.A.  The adjoint of k(X_s, X_s) (cotangent
+// sum_r H_r) is formed here: dX_knn [T, D] and per-group partials part [S, 40] (dls at 0..D-1, dvariance at 32).
+struct FullCovBwdParams {
+  iwvi_gp_desc d;
+  int S, N;
+  const double *aux, *X, *save, *eps, *d_sample, *d_cov;
+  double chol_jitter;
+  double *save2, *dXk, *part;
+};
+
+// acc[j][c] = sum_i Hm(8 w + g, i) slab(i, 8 j + 2 t + c): Hm symmetric [64][65], slab [64][68] (rows = points)
+__device__ __forceinline__ void h_times_slab(double (&acc)[8][2], const double* __restrict__ Hm, const double* __restrict__ slab,
+                                             int warp, int lane, int kmax) {
+  const int g = lane >> 2, t = lane & 3;
+  const double* ap = Hm + (warp * 8 + g) * FC_LDC + t;
+  const double* bp = slab + t * IWVI_LDS + g;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+  for (int k0 = 0; k0 < kmax; k0 += 4) {
+    const double a = ap[k0];
+#pragma unroll
+    for (int j = 0; j < 8; j++) dmma884(acc[j], a, bp[k0 * IWVI_LDS + j * 8]);
+  }
+}
+
+__device__ __forceinline__ void store_rows(double* __restrict__ panel, const double (&acc)[8][2], int64_t pt0, int n, int mb,
+                                           int NB, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3, row = warp * 8 + g;
+  if (row >= n) return;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    double* dst = panel + iwvi_blk_off((int)(pt0 + row), mb * IWVI_BLK + j * 8 + 2 * t, NB);
+    dst[0] = acc[j][0];
+    dst[1] = acc[j][1];
+  }
+}
+
+__global__ void __launch_bounds__(FC_THREADS) gp_fullcov_bwd_kernel(const FullCovBwdParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
+  const int N = p.N, R = d.R, D = d.D, NB = al.NB;
+  const int Np = iwvi_round_up(N, 8), ntn = Np / 8;
+  double* slab = smem;                               // [64][68]
+  double* C0 = slab + IWVI_STAGE_DOUBLES;            // [64][65] k(X_s, X_s) - A_s^T A_s
+  double* Lr = C0 + IWVI_BLK * FC_LDC;               // C_r, then its Cholesky factor (lower)
+  double* Hr = Lr + IWVI_BLK * FC_LDC;               // H_r (symmetric, zero outside N x N)
+  double* Hs = Hr + IWVI_BLK * FC_LDC;               // sum_r H_r
+  double* Sc = Hs + IWVI_BLK * FC_LDC;               // scratch: Q -> L^-T Q -> L^-T Q L^-1 ; later Hs * dk/dr2
+  double* xs = Sc + IWVI_BLK * FC_LDC;               // [64][32] length-scaled inputs
+  double* xn = xs + IWVI_BLK * IWVI_MAX_D;           // [64]
+  double* dv = xn + IWVI_BLK;                        // [64] cotangent of the draw, output r
+  double* zv = dv + IWVI_BLK;                        // [64] its noise
+  double* qv = zv + IWVI_BLK;                        // [64] L^T dv
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double* consts = p.aux + al.off_consts;
+  const double variance = consts[IWVI_C_VARIANCE];
+  const double* Apanel = p.save + sv.off_a;
+  const bool active = warp * 8 < Np;
+
+  for (int s = blockIdx.x; s < p.S; s += gridDim.x) {
+    const int64_t pt0 = (int64_t)s * N;
+    __syncthreads();
+    for (int idx = tid; idx < N * D; idx += FC_THREADS) {
+      const int n = idx / D, k = idx - n * D;
+      xs[n * IWVI_MAX_D + k] = p.X[(pt0 + n) * D + k] * consts[IWVI_C_INVLS + k];
+    }
+    for (int idx = tid; idx < IWVI_BLK * FC_LDC; idx += FC_THREADS) Hs[idx] = 0.0;
+    __syncthreads();
+    if (tid < N) {
+      double q = 0.0;
+      for (int k = 0; k < D; k++) { const double v = xs[tid * IWVI_MAX_D + k]; q += v * v; }
+      xn[tid] = q;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += FC_THREADS) {
+      const int i = idx >> 6, j = idx & 63;
+      double v = 0.0;
+      if (i < N && j < N) {
+        double dot = 0.0;
+        for (int k = 0; k < D; k++) dot += xs[i * IWVI_MAX_D + k] * xs[j * IWVI_MAX_D + k];
+        v = kern_k(d.kern, xn[i] + xn[j] - 2.0 * dot, variance);
+      }
+      C0[i * FC_LDC + j] = v;
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    for (int mb = 0; mb < NB; mb++) {
+      __syncthreads();
+      load_slab(slab, Apanel, pt0, N, mb, NB, tid);
+      __syncthreads();
+      if (active) slab_syrk(acc, slab, slab, warp, lane, ntn);
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < ntn) {
+          C0[(warp * 8 + g) * FC_LDC + j * 8 + 2 * t] -= acc[j][0];
+          C0[(warp * 8 + g) * FC_LDC + j * 8 + 2 * t + 1] -= acc[j][1];
+        }
+    }
+    for (int r = 0; r < R; r++) {
+      const double* Upanel = p.save + sv.off_u + (int64_t)r * sv.u_stride;
+      double* Vpanel = p.save2 + sv.off_u + (int64_t)r * sv.u_stride;
+      const double* dc = p.d_cov ? p.d_cov + ((int64_t)s * R + r) * N * N : nullptr;
+      __syncthreads();
+      // ---- H_r starts as sym(dC_r)
+      for (int idx = tid; idx < IWVI_BLK * IWVI_BLK; idx += FC_THREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        Hr[i * FC_LDC + j] = (dc && i < N && j < N) ? 0.5 * (dc[i * N + j] + dc[j * N + i]) : 0.0;
+      }
+      if (p.d_sample) {
+        // ---- C_r and its Cholesky factor, as in the forward kernel
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < ntn) {
+              acc[j][0] = C0[(warp * 8 + g) * FC_LDC + j * 8 + 2 * t];
+              acc[j][1] = C0[(warp * 8 + g) * FC_LDC + j * 8 + 2 * t + 1];
+            }
+        }
+        for (int mb = 0; mb < NB; mb++) {
+          __syncthreads();
+          load_slab(slab, Upanel, pt0, N, mb, NB, tid);
+          __syncthreads();
+          if (active) slab_syrk(acc, slab, slab, warp, lane, ntn);
+        }
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < ntn) {
+              Lr[(warp * 8 + g) * FC_LDC + j * 8 + 2 * t] = acc[j][0];
+              Lr[(warp * 8 + g) * FC_LDC + j * 8 + 2 * t + 1] = acc[j][1];
+            }
+        }
+        for (int j = 0; j < N; j++) {
+          __syncthreads();
+          const double dj = sqrt(Lr[j * FC_LDC + j] + p.chol_jitter);
+          const double inv = 1.0 / dj;
+          __syncthreads();
+          if (tid == 0) Lr[j * FC_LDC + j] = dj;
+          for (int i = j + 1 + tid; i < N; i += FC_THREADS) Lr[i * FC_LDC + j] *= inv;
+          __syncthreads();
+          const int n_tr = N - j - 1;
+          for (int idx = tid; idx < n_tr * n_tr; idx += FC_THREADS) {
+            const int a = idx / n_tr, b = idx - a * n_tr;
+            if (b <= a) Lr[(j + 1 + a) * FC_LDC + j + 1 + b] -= Lr[(j + 1 + a) * FC_LDC + j] * Lr[(j + 1 + b) * FC_LDC + j];
+          }
+        }
+        if (tid < N) {
+          dv[tid] = p.d_sample[(pt0 + tid) * R + r];
+          zv[tid] = p.eps[((int64_t)s * R + r) * N + tid];
+        }
+        __syncthreads();
+        if (tid < N) {        // q = L^T dv
+          double q = 0.0;
+          for (int k = tid; k < N; k++) q += Lr[k * FC_LDC + tid] * dv[k];
+          qv[tid] = q;
+        }
+        __syncthreads();
+        // Q = P + P^T, P = Phi(L^T Lbar): Q_ij = q_i z_j (i > j), q_j z_i (i < j), q_i z_i (i == j)
+        for (int idx = tid; idx < N * N; idx += FC_THREADS) {
+          const int i = idx / N, j = idx - i * N;
+          Sc[i * FC_LDC + j] = i >= j ? qv[i] * zv[j] : qv[j] * zv[i];
+        }
+        __syncthreads();
+        if (tid < N) {        // Y = L^-T Q, one column per thread (back substitution)
+          const int c = tid;
+          for (int i = N - 1; i >= 0; i--) {
+            double v = Sc[i * FC_LDC + c];
+            for (int k = i + 1; k < N; k++) v -= Lr[k * FC_LDC + i] * Sc[k * FC_LDC + c];
+            Sc[i * FC_LDC + c] = v / Lr[i * FC_LDC + i];
+          }
+        }
+        __syncthreads();
+        if (tid < N) {        // S1 = Y L^-1: row c of S1 solves L^T w = (row c of Y)^T
+          const int c = tid;
+          for (int i = N - 1; i >= 0; i--) {
+            double v = Sc[c * FC_LDC + i];
+            for (int k = i + 1; k < N; k++) v -= Lr[k * FC_LDC + i] * Sc[c * FC_LDC + k];
+            Sc[c * FC_LDC + i] = v / Lr[i * FC_LDC + i];
+          }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < N * N; idx += FC_THREADS) {
+          const int i = idx / N, j = idx - i * N;
+          Hr[i * FC_LDC + j] += 0.25 * (Sc[i * FC_LDC + j] + Sc[j * FC_LDC + i]);
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < IWVI_BLK * FC_LDC; idx += FC_THREADS) Hs[idx] += Hr[idx];
+      // ---- save2.U_r = U_rs H_r
+      for (int mb = 0; mb < NB; mb++) {
+        __syncthreads();
+        load_slab(slab, Upanel, pt0, N, mb, NB, tid);
+        __syncthreads();
+        if (active) {
+          h_times_slab(acc, Hr, slab, warp, lane, Np);
+          store_rows(Vpanel, acc, pt0, N, mb, NB, warp, lane);
+        }
+      }
+    }
+    // ---- save2.A = A_s (sum_r H_r) / R
+    __syncthreads();
+    const double invR = 1.0 / (double)R;
+    for (int idx = tid; idx < IWVI_BLK * FC_LDC; idx += FC_THREADS) Hr[idx] = Hs[idx] * invR;
+    for (int mb = 0; mb < NB; mb++) {
+      __syncthreads();
+      load_slab(slab, Apanel, pt0, N, mb, NB, tid);
+      __syncthreads();
+      if (active) {
+        h_times_slab(acc, Hr, slab, warp, lane, Np);
+        store_rows(p.save2 + sv.off_a, acc, pt0, N, mb, NB, warp, lane);
+      }
+    }
+    // ---- adjoint of k(X_s, X_s) with cotangent Hs: Sc = Hs * dk/dr2, dvariance partial = sum Hs * k / variance
+    __syncthreads();
+    double vpart = 0.0;
+    for (int idx = tid; idx < N * N; idx += FC_THREADS) {
+      const int i = idx / N, j = idx - i * N;
+      double dot = 0.0;
+      for (int k = 0; k < D; k++) dot += xs[i * IWVI_MAX_D + k] * xs[j * IWVI_MAX_D + k];
+      double K, dK;
+      kern_k_dk(d.kern, xn[i] + xn[j] - 2.0 * dot, variance, K, dK);
+      const double h = Hs[i * FC_LDC + j];
+      Sc[i * FC_LDC + j] = h * dK;
+      vpart += h * K;
+    }
+    vpart = block_sum(vpart, red);      // total in thread 0
+    if (tid == 0) qv[0] = vpart;
+    __syncthreads();
+    // dx~_id = 4 sum_j (Hs dk)_ij (x~_id - x~_jd); C0 is free now: C0[i][d] = -dx~_id x~_id / ls_d (dls summands)
+    for (int idx = tid; idx < N * D; idx += FC_THREADS) {
+      const int i = idx / D, k = idx - i * D;
+      const double xi = xs[i * IWVI_MAX_D + k];
+      double sum = 0.0;
+      for (int j = 0; j < N; j++) sum += Sc[i * FC_LDC + j] * (xi - xs[j * IWVI_MAX_D + k]);
+      const double dx = 4.0 * sum * consts[IWVI_C_INVLS + k];
+      p.dXk[(pt0 + i) * D + k] = dx;
+      C0[i * FC_LDC + k] = -dx * xi;
+    }
+    __syncthreads();
+    double* part = p.part + (int64_t)s * 40;
+    if (tid < 40) {
+      double v = 0.0;
+      if (tid < D) for (int i = 0; i < N; i++) v += C0[i * FC_LDC + tid];
+      else if (tid == 32) v = qv[0] / variance;
+      part[tid] = v;
     }
   }
 }
@@ -188,7 +487,7 @@ extern "C" int iwvi_gp_fullcov_fwd(const iwvi_gp_desc* d, int32_t S, int32_t N, 
   if (d->M > IWVI_MAX_M || d->D > IWVI_MAX_D || d->R > IWVI_MAX_R) return IWVI_ERR_UNSUPPORTED;
   if (d->mix || d->P != d->R) return IWVI_ERR_BAD_DESC;            // the Mok branch forces full_cov=False (:125-129)
   if (S < 0 || N < 1 || (int64_t)S * N != d->T) return IWVI_ERR_BAD_DESC;
-  if (N > IWVI_BLK) return IWVI_ERR_UNSUPPORTED;
+  if (sample && N > IWVI_BLK) return IWVI_ERR_UNSUPPORTED;        // the joint draw factorises the group in one CTA
   if (!aux || !X || !save) return IWVI_ERR_NULL;
   if (sample && (!eps || !mean)) return IWVI_ERR_NULL;
   if (!cov && !sample) return IWVI_ERR_NULL;
@@ -196,14 +495,43 @@ extern "C" int iwvi_gp_fullcov_fwd(const iwvi_gp_desc* d, int32_t S, int32_t N, 
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const int smem_bytes = (IWVI_STAGE_DOUBLES + 2 * IWVI_BLK * FC_LDC + IWVI_BLK * IWVI_MAX_D + IWVI_BLK) * 8;
+  const int smem_bytes = (2 * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK * FC_LDC + 2 * IWVI_BLK * IWVI_MAX_D + 2 * IWVI_BLK) * 8;
   if (cudaFuncSetAttribute(gp_fullcov_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
   FullCovParams p;
   p.d = *d; p.S = S; p.N = N; p.aux = aux; p.X = X; p.save = save; p.mean = mean; p.eps = eps;
   p.chol_jitter = chol_jitter; p.cov = cov; p.sample = sample; p.info = info;
-  const int grid = S < 2 * nsm ? S : 2 * nsm;
+  const int nblk = (N + IWVI_BLK - 1) / IWVI_BLK;
+  const int64_t items = (int64_t)S * nblk * nblk;
+  const int grid = (int)(items < nsm ? items : nsm);
   gp_fullcov_fwd_kernel<<<grid, FC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_gp_fullcov_bwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const double* aux, const double* X,
+                                   const double* save, const double* eps, double chol_jitter, const double* d_sample,
+                                   const double* d_cov, double* save2, double* dX_knn, double* part, void* stream) {
+  if (!d) return IWVI_ERR_NULL;
+  if (d->T < 0 || d->M < 1 || d->D < 1 || d->R < 1) return IWVI_ERR_BAD_DESC;
+  if (d->M > IWVI_MAX_M || d->D > IWVI_MAX_D || d->R > IWVI_MAX_R) return IWVI_ERR_UNSUPPORTED;
+  if (d->mix || d->P != d->R) return IWVI_ERR_BAD_DESC;
+  if (S < 0 || N < 1 || (int64_t)S * N != d->T) return IWVI_ERR_BAD_DESC;
+  if (N > IWVI_BLK) return IWVI_ERR_UNSUPPORTED;
+  if (!aux || !X || !save || !save2 || !dX_knn || !part) return IWVI_ERR_NULL;
+  if (d_sample && !eps) return IWVI_ERR_NULL;
+  if (S == 0) return IWVI_OK;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int smem_bytes = (IWVI_STAGE_DOUBLES + 5 * IWVI_BLK * FC_LDC + IWVI_BLK * IWVI_MAX_D + 4 * IWVI_BLK) * 8;
+  if (cudaFuncSetAttribute(gp_fullcov_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+    return IWVI_ERR_LAUNCH;
+  FullCovBwdParams p;
+  p.d = *d; p.S = S; p.N = N; p.aux = aux; p.X = X; p.save = save; p.eps = eps; p.d_sample = d_sample; p.d_cov = d_cov;
+  p.chol_jitter = chol_jitter; p.save2 = save2; p.dXk = dX_knn; p.part = part;
+  const int grid = S < nsm ? S : nsm;
+  gp_fullcov_bwd_kernel<<<grid, FC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }

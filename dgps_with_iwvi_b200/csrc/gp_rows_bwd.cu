@@ -196,8 +196,10 @@ __global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
     }
   }
   double* part = p.ws + p.wl.off_epi + (size_t)blockIdx.x * EPI_STRIDE;
+  // (the Kdiag term of dvariance: d fvar / d variance = 1 per point and output; absent when the caller handles the prior
+  //  covariance k(X, X) itself, IWVI_FLAG_NO_KDIAG -- the full-covariance adjoint in gp_fullcov.cu)
   const double tot = block_sum(gv_sum, red);
-  if (tid == 0) part[P * R + D * P + P] = tot;
+  if (tid == 0) part[P * R + D * P + P] = (d.flags & IWVI_FLAG_NO_KDIAG) ? 0.0 : tot;
   // partial sums over this CTA's points of dW, dmfA, dmfb
   const int nW = (d.mix && p.dW) ? P * R : 0;
   const int nA = (d.mf == IWVI_MF_LINEAR && p.dmfA) ? D * P : 0;

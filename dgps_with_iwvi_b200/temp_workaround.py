@@ -18,8 +18,8 @@ Not on the hot path and therefore not in CUDA (raise NotImplementedError): white
 layers.py:42) and full_output_cov=True.  q_sqrt=None (:174-184, SGHMC) and the 2-D diagonal q_sqrt (:72-73) are mapped
 onto the same kernels (zero / diagonal Cholesky factors).  full_cov=True
 (:55-57,82-83, whose joint sampler :92-96 has a shape bug and is dead code in training) is served
-forward-only by iwvi_gp_fullcov_fwd (csrc/gp_fullcov.cu: DMMA Gram products on the saved A / U panels, shared-memory
-Cholesky, corrected joint draw), for predict_f_full_cov and API completeness."""
+by iwvi_gp_fullcov_fwd / _bwd (csrc/gp_fullcov.cu: DMMA Gram products on the saved A / U panels, shared-memory
+Cholesky and its adjoint, corrected joint draw), differentiable for groups of up to 64 points."""
 import numpy as np
 import torch
 
@@ -80,7 +80,6 @@ class _GPConditional(torch.autograd.Function):
         ctx.d, ctx.meta = d, meta
         ctx.saved = (Xc, Zc, lsc, vc, qmc, qsc, Wc, Ac, bc, ec, Lm, aux, save)
         ctx.var_shape = variance.shape
-        meta['_save'] = (save, Lm, aux, d)   # for the forward-only full-covariance branch
         if smp is None:
             smp = mean.new_zeros(0)
         ctx.mark_non_differentiable(kl)
@@ -108,6 +107,82 @@ class _GPConditional(torch.autograd.Function):
         capi.gp_prologue_bwd(capi.with_flags(d, d.flags | LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), Lm, aux, Zc, lsc, vc, qmc, qsc, dLm, z(1),
                              dZ, dls, dv, dqm, dqs, z(capi.gp_pbwd_ws_doubles(d)))
         return dX, dZ, dls, dv.reshape(ctx.var_shape), dqm, dqs, dW, dA, db, None, None
+
+
+class _GPFullCov(torch.autograd.Function):
+    """iwvi_gp_prologue_fwd + iwvi_gp_rows_fwd + iwvi_gp_fullcov_fwd: mean [T, R], covariance over the inner axis
+    [S, R, N, N] and (with noise z [S, R, N]) the joint draw [T, R].  backward = iwvi_gp_fullcov_bwd, which recasts the
+    N x N cotangents as panels the per-point backward kernels understand, then iwvi_gp_rows_bwd + iwvi_gp_prologue_bwd."""
+
+    @staticmethod
+    def forward(ctx, X, Z, ls, variance, q_mu, q_sqrt, mfA, mfb, z, meta):
+        LIB.load()
+        dev = X.device
+        T, D = X.shape
+        M, R = q_mu.shape
+        S_, N = meta['S'], meta['N']
+        d = capi.gp_desc(T, M, D, R, R, meta['kern'], False, meta['mf'], LIB.FLAG_SAVE, meta['jitter'])
+        zr = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        Mp = capi.gp_mp(M)
+        Lm, aux, kl = zr(Mp, Mp), zr(capi.gp_aux_doubles(d)), zr(1)
+        info = torch.zeros(2, dtype=torch.int32, device=dev)
+        Xc, Zc, lsc, vc, qmc, qsc = _c(X), _c(Z), _c(ls), _c(variance).reshape(1), _c(q_mu), _c(q_sqrt)
+        Ac, bc, zc = _c(mfA), _c(mfb), _c(z)
+        capi.gp_prologue_fwd(d, Zc, lsc, vc, qmc, qsc, Lm, aux, kl, info[:1])
+        mean, var = zr(T, R), zr(T, R)
+        save = zr(capi.gp_save_doubles(d))
+        capi.gp_rows_fwd(d, Lm, aux, Xc, None, Ac, bc, None, None, mean, var, save)
+        cov = zr(S_, R, N, N)
+        smp = zr(T, R) if zc is not None else None
+        capi.gp_fullcov_fwd(d, S_, N, aux, Xc, save, mean, zc, meta['chol_jitter'], cov, smp, info[1:])
+        i0, i1 = (int(v) for v in info.tolist())
+        if i0:
+            raise RuntimeError('Cholesky of Kuu failed: leading minor of order %d is not positive definite' % i0)
+        if i1:
+            raise RuntimeError('Cholesky of the covariance over the inner axis failed: leading minor of order %d is not '
+                               'positive definite' % i1)
+        ctx.d, ctx.meta = d, meta
+        ctx.saved = (Xc, Zc, lsc, vc, qmc, qsc, Ac, bc, zc, Lm, aux, save)
+        ctx.var_shape = variance.shape
+        return (smp if smp is not None else mean.new_zeros(0)), mean, cov
+
+    @staticmethod
+    def backward(ctx, d_sample, d_mean, d_cov):
+        Xc, Zc, lsc, vc, qmc, qsc, Ac, bc, zc, Lm, aux, save = ctx.saved
+        d, meta = ctx.d, ctx.meta
+        S_, N = meta['S'], meta['N']
+        if N > 64:
+            raise NotImplementedError('the adjoint of the covariance over the inner axis is built for at most 64 points '
+                                      'per group (N = %d)' % N)
+        dev = Xc.device
+        zr = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        T, D = Xc.shape
+        M, R = qmc.shape
+        Mp = Lm.shape[0]
+        ds = _c(d_sample) if (zc is not None and d_sample is not None and d_sample.numel()) else None
+        save2, dXk, part = torch.zeros_like(save), zr(T, D), zr(S_, 40)
+        capi.gp_fullcov_bwd(d, S_, N, aux, Xc, save, zc, meta['chol_jitter'], ds, _c(d_cov), save2, dXk, part)
+        gm = zr(T, R) if d_mean is None else d_mean.detach().clone()
+        if ds is not None:
+            gm += ds
+        ones = torch.ones(T, R, dtype=F64, device=dev)
+        dX, dZ, dls, dv, dqm, dqs, dLm = zr(T, D), zr(M, D), zr(D), zr(1), zr(M, R), zr(R, M, M), zr(Mp, Mp)
+        dA = zr(*Ac.shape) if Ac is not None else None
+        db = zr(*bc.shape) if bc is not None else None
+        ws = zr(capi.gp_bwd_ws_doubles(d))
+        fl = d.flags | LIB.FLAG_NO_KDIAG
+        args = (Lm, aux, save2, Xc, None, Ac, bc, None, None, gm, ones, dX, dZ, dls, dv, dqm, dqs, dLm, None, dA, db, ws)
+        capi.gp_rows_bwd(capi.with_flags(d, fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE), *args)
+        # the A panel is the first slot of the save layout (csrc/common.cuh SaveLayout): [Tp/64][Mp/64][64][68]
+        n_a = ((T + 127) // 128 * 2) * (Mp // 64) * 64 * 68
+        save2[:n_a].copy_(save[:n_a])
+        capi.gp_rows_bwd(capi.with_flags(d, fl | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL), *args)
+        dX += dXk
+        dls += part[:, :D].sum(0)
+        dv += part[:, 32].sum()
+        capi.gp_prologue_bwd(capi.with_flags(d, d.flags | LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), Lm, aux, Zc, lsc, vc, qmc, qsc,
+                             dLm, zr(1), dZ, dls, dv, dqm, dqs, zr(capi.gp_pbwd_ws_doubles(d)))
+        return dX, dZ, dls, dv.reshape(ctx.var_shape), dqm, dqs, dA, db, None, None
 
 
 def _kern_parts(kern):
@@ -147,43 +222,31 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
     mfA = _t(mean_function.A) if mf_kind == 'Linear' else None
     mfb = _t(mean_function.b) if mf_kind == 'Linear' else None
     P = Wt.shape[0] if Wt is not None else R
-    if sample and not full_cov:
-        e = torch.randn(T, R, dtype=F64, device=X.device) if eps is None else _t(eps).reshape(T, R)
-    else:
-        e = None
     meta = dict(kern=kern.kind, mf=mf_kind, jitter=float(jitter))
-    smp, mean, var, _ = _GPConditional.apply(X2, Z, ls_vec, variance, q_mu, q_sq, Wt, mfA, mfb, e, meta)
-    mean_o = mean.reshape(*lead, P)
     if not full_cov:
-        return (smp.reshape(*lead, P) if e is not None else None), mean_o, var.reshape(*lead, P)
-    # ---- full covariance over the inner axis and the joint draw (forward only): iwvi_gp_fullcov_fwd on the saved panels
+        e = None
+        if sample:
+            e = torch.randn(T, R, dtype=F64, device=X.device) if eps is None else _t(eps).reshape(T, R)
+        smp, mean, var, _ = _GPConditional.apply(X2, Z, ls_vec, variance, q_mu, q_sq, Wt, mfA, mfb, e, meta)
+        return (smp.reshape(*lead, P) if e is not None else None), mean.reshape(*lead, P), var.reshape(*lead, P)
+    # ---- full covariance over the inner axis and the joint draw: iwvi_gp_fullcov_fwd / _bwd on the saved panels
     if Wt is not None:
         raise NotImplementedError('the Mok branch forces full_cov=False (temp_workaround.py:125-129)')
     S_ = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
     N = lead[-1]
-    if N > 64:
-        raise NotImplementedError('full_cov=True is built for inner axes of at most 64 points (N = %d)' % N)
-    with torch.no_grad():
-        save, Lm, aux, d = meta['_save']
-        cov = torch.zeros(S_, R, N, N, dtype=F64, device=X.device)
-        info = torch.zeros(1, dtype=torch.int32, device=X.device)
-        smp_o = z = None
-        if sample:
-            # the joint draw the reference intends at :92-96, in its [S, R, N, 1] noise order (:93-94)
-            z = torch.randn(S_, R, N, dtype=F64, device=X.device) if eps is None else _c(_t(eps).reshape(S_, R, N))
-            smp_o = torch.zeros(T, R, dtype=F64, device=X.device)
-        # 3-D inputs: tf.cholesky(fvar) as is (:95); 2-D inputs go through gpflow's _sample_mvn, which adds the jitter
-        capi.gp_fullcov_fwd(d, S_, N, aux, _c(X2), save, mean.detach(), z, 0.0 if len(lead) > 1 else float(jitter), cov,
-                            smp_o, info)
-        if sample:
-            i = int(info.item())
-            if i:
-                raise RuntimeError('Cholesky of the covariance over the inner axis failed: leading minor of order %d '
-                                   'is not positive definite' % i)
-            smp_o = smp_o.reshape(*lead, R)
+    if sample and N > 64:
+        raise NotImplementedError('the joint draw is built for inner axes of at most 64 points (N = %d); the covariance '
+                                  'itself (sample=False) has no such limit' % N)
+    z = None
+    if sample:
+        # the joint draw the reference intends at :92-96, in its [S, R, N, 1] noise order (:93-94)
+        z = torch.randn(S_, R, N, dtype=F64, device=X.device) if eps is None else _t(eps).reshape(S_, R, N)
+    # 3-D inputs: tf.cholesky(fvar) as is (:95); 2-D inputs go through gpflow's _sample_mvn, which adds the jitter
+    meta.update(S=S_, N=N, chol_jitter=0.0 if len(lead) > 1 else float(jitter))
+    smp, mean, cov = _GPFullCov.apply(X2, Z, ls_vec, variance, q_mu, q_sq, mfA, mfb, z, meta)
     if len(lead) == 1:
         cov = cov[0]
-    return smp_o, mean_o, cov
+    return (smp.reshape(*lead, R) if sample else None), mean.reshape(*lead, R), cov
 
 
 def multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=False, full_output_cov=False, q_sqrt=None,

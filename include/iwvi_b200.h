@@ -80,6 +80,9 @@ extern "C" {
 #define IWVI_FLAG_PART_B   512
 #define IWVI_FLAG_SKIP_KL  1024
 #define IWVI_FLAG_ONLY_KL  2048
+/* iwvi_gp_rows_bwd: leave the Kdiag term (d var / d variance = 1 per point) out of dvariance -- set by callers that
+ * differentiate the prior covariance k(X, X) themselves (iwvi_gp_fullcov_bwd). */
+#define IWVI_FLAG_NO_KDIAG 4096
 
 typedef struct iwvi_gp_desc {
   int32_t T;      /* points in this call                                    */
@@ -155,7 +158,7 @@ int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* 
  * Covariance over the inner axis and the joint draw, forward, for plain-kernel layers: the full_cov=True branch of
  * independent_multisample_sample_conditional (temp_workaround.py:45, :55-57, :82-83) and the joint sampler intended at
  * :92-96 (the reference's own lines add an [S,N,R] mean to an [S,R,N,1] draw and never execute).  Runs after
- * iwvi_gp_rows_fwd with IWVI_FLAG_SAVE on the same descriptor (d->T == S*N, d->mix == 0, N <= 64):
+ * iwvi_gp_rows_fwd with IWVI_FLAG_SAVE on the same descriptor (d->T == S*N, d->mix == 0; sample needs N <= 64):
  *   X [S*N,D]; save (A, U_r panels); mean [S*N,R] as written by iwvi_gp_rows_fwd; eps [S,R,N] (the [S,R,N,1] draw of :94)
  *   out: cov [S,R,N,N] = k(X_s,X_s) - A_s^T A_s + U_rs^T U_rs (or NULL);
  *        sample [S*N,R] = mean + chol(cov + chol_jitter I) eps (or NULL); info [1] (int32, first failing leading minor).
@@ -163,6 +166,21 @@ int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* 
 int iwvi_gp_fullcov_fwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const double* aux, const double* X,
                         const double* save, const double* mean, const double* eps, double chol_jitter,
                         double* cov, double* sample, int32_t* info, void* stream);
+
+/*
+ * Adjoint of iwvi_gp_fullcov_fwd (tf.gradients through temp_workaround.py:45,55-57,82-83 and the joint draw; Cholesky
+ * adjoint as in TF's CholeskyGrad, symmetrised), N <= 64.  Cotangents d_sample [S*N,R] and d_cov [S,R,N,N] (either may
+ * be NULL).  It prepares what iwvi_gp_rows_bwd needs to finish the job with its existing kernels:
+ *   save2 (same size as save, zero-initialised by the caller): save2.A = A_s (sum_r H_r) / R, save2.U_r = U_rs H_r, with
+ *         H_r the symmetric N x N cotangent of C_r.  Run iwvi_gp_rows_bwd(IWVI_FLAG_ONLY_EPI | ONLY_TILE | NO_KDIAG) on
+ *         save2 with d_mean = d_mean + d_sample, d_var = ones [T,R], d_sample = NULL; then copy save.A over save2.A
+ *         and run the ONLY_REDUCE | ONLY_FINAL half on save2.
+ *   dX_knn [S*N,D] and part [S,40] (dls partials at 0..D-1, dvariance partial at 32): the adjoint of k(X_s, X_s); the
+ *         caller adds dX_knn to dX and the column sums of part to dls / dvariance.
+ */
+int iwvi_gp_fullcov_bwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const double* aux, const double* X,
+                        const double* save, const double* eps, double chol_jitter, const double* d_sample,
+                        const double* d_cov, double* save2, double* dX_knn, double* part, void* stream);
 
 /*
  * Whitened KL[q(u)||p(u)] on its own, for callers of the operator-level gauss_kl(q_mu, q_sqrt) (temp_workaround.py:167-188

@@ -251,3 +251,45 @@ def test_full_size_properties_c3():
     losses = [tr.step(X[i * B:(i + 1) * B], Y[i * B:(i + 1) * B]) for i in range(12)]
     tr.engine.check_info()
     assert np.isfinite(losses).all() and np.mean(losses[-3:]) > np.mean(losses[:3])
+
+
+def test_full_size_properties_c4_row_shards_add_up():
+    """BASELINE config 4 at full size (L1_G5, D=8, M=512, K=256, B=4096: 1 048 576 points per layer, the largest shapes
+    the build serves), size-independent properties: bit-identical repeat; the gradient bucket (last slot = ELBO) of the
+    full minibatch equals the SUM of the buckets of its two row shards evaluated as ranks 0 / 1 of a world of 2 (what
+    the single all-reduce of the data-parallel step adds up, models.py:144-150 with scale = num_data / B_global), and the
+    per-row log-weights of the shards are those of the full batch -- noise is keyed by the global point index."""
+    from dgps_with_iwvi_b200.build_models import build_model
+    from dgps_with_iwvi_b200.engine import FlatParams
+    c = S.CONFIGS['c4']
+    X, Y = S.make_data(c['N'], c['D'], seed=0)
+    m = build_model(X, Y, c['configuration'], M=c['M'], num_IW_samples=c['K'], minibatch_size=c['B'],
+                    likelihood_variance=c['lik_variance'], mode='IWAE', seed=0)
+    B, K = c['B'], c['K']
+    Xb, Yb = X[:B], Y[:B]
+    flat = FlatParams.of(m)
+    eng = m.engine(B, K)
+    eng.elbo_and_grads(Xb, Yb, None, seed=3, step=1, row0=0)
+    eng.check_info()
+    g_full, logp_full = flat.g.clone(), eng.logp.clone()
+    assert torch.isfinite(g_full).all()
+    eng.elbo_and_grads(Xb, Yb, None, seed=3, step=1, row0=0)
+    assert torch.equal(flat.g, g_full) and torch.equal(eng.logp, logp_full)
+    del eng
+    m._engines.clear()
+    torch.cuda.empty_cache()
+    g_sum, logp = torch.zeros_like(g_full), []
+    h = B // 2
+    for r in range(2):
+        e = m.engine(h, K, None, 2, r)
+        e.elbo_and_grads(Xb[r * h:(r + 1) * h], Yb[r * h:(r + 1) * h], None, seed=3, step=1, row0=r * h)
+        e.check_info()
+        g_sum += flat.g
+        logp.append(e.logp.clone())
+    logp = torch.cat(logp)
+    assert (logp - logp_full).abs().max().item() <= 1e-12 * logp_full.abs().max().item()
+    for name, off, size, _, _ in flat.entries.values():
+        a, b = g_sum[off:off + size], g_full[off:off + size]
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 1e-9 * max(scale, 1e-300), name
+    assert abs(g_sum[flat.n].item() - g_full[flat.n].item()) <= 1e-11 * abs(g_full[flat.n].item())

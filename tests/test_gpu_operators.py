@@ -128,7 +128,7 @@ def test_full_cov_branch_and_predict_f_full_cov():
     from dgps_with_iwvi_b200 import temp_workaround as tw
     from dgps_with_iwvi_b200.build_models import model_from_spec
     rng = np.random.default_rng(8)
-    N, D, M, Ns = 60, 2, 33, 21
+    N, D, M, Ns = 60, 2, 33, 150      # 150 test points: the covariance spans 3 x 3 blocks of 64, the last one ragged
     X, Y = S.make_data(N, D, seed=8)
     spec = S.make_spec(X, '', M, 1, seed=8, perturb=0.4, kern='Matern52', final_mf='Linear', lik_variance=0.1)
     g = spec['layers'][0]
@@ -150,6 +150,18 @@ def test_full_cov_branch_and_predict_f_full_cov():
                                                   q_sqrt=layer.q_sqrt, white=True, sample=False)
     close('mean3', mg, mo); close('cov3', vg, vo)
     assert vg.shape == (3, 1, 11, 11)
+    # more than 64 points per group: covariance in 64 x 64 blocks; the joint draw is limited to one block
+    F2 = rng.standard_normal((2, 97, D))
+    _, mo2, vo2 = O.independent_multisample_sample_conditional(T64(F2), omodel.layers[0].Z, omodel.layers[0].kern,
+                                                              omodel.layers[0].q_mu, full_cov=True,
+                                                              q_sqrt=omodel.layers[0].q_sqrt, white=True)
+    _, mg2, vg2 = tw.multisample_sample_conditional(T64(F2).cuda(), layer.feature, layer.kern, layer.q_mu, full_cov=True,
+                                                    q_sqrt=layer.q_sqrt, white=True, sample=False)
+    close('mean3b', mg2, mo2); close('cov3b', vg2, vo2)
+    assert torch.equal(vg2, vg2.transpose(-1, -2))
+    with pytest.raises(NotImplementedError):
+        tw.multisample_sample_conditional(T64(F2).cuda(), layer.feature, layer.kern, layer.q_mu, full_cov=True,
+                                          q_sqrt=layer.q_sqrt, white=True)
     with pytest.raises(NotImplementedError):
         tw.multisample_sample_conditional(T64(F).cuda(), layer.feature, layer.kern, layer.q_mu, q_sqrt=layer.q_sqrt,
                                           white=False)
@@ -220,3 +232,49 @@ def test_full_cov_joint_draw(S_, N, M, kern):
     close('mean', m, mo, tol); close('cov', v, vo, tol); close('sample', s, so, tol)
     # exact symmetry of the DMMA Gram products
     assert torch.equal(v, v.transpose(-1, -2))
+
+
+@pytest.mark.parametrize('conf,which,kern,S_,N', [('G2', 0, 'RBF', 3, 20), ('L1_G3', 2, 'Matern52', 2, 50),
+                                                  ('G3', 0, 'Matern32', 2, 64), ('G2', 1, 'RBF', 5, 1)])
+def test_full_cov_joint_draw_autograd(conf, which, kern, S_, N):
+    """Gradients through the covariance over the inner axis and the joint draw (iwvi_gp_fullcov_bwd + the per-point
+    backward kernels) against torch autograd on the oracle (Cholesky adjoint included): cotangents on the sample, the
+    mean and the full covariance; gradients of the inputs and of every parameter.  Final layers (one output, Linear mean
+    function) are taken as they are; of the Mok layers the shared base kernel and the latent q(u) are used (R > 1)."""
+    from dgps_with_iwvi_b200 import temp_workaround as tw
+    layer, ol, leaves, pre = _layer_pair(conf, 4, 37, kern=kern, which=which, final_mf='Linear')
+    mok = isinstance(ol.kern, O.Mok)
+    okern = ol.kern.kernel if mok else ol.kern
+    gkern = layer.kern.kernel if mok else layer.kern
+    gmf = None if mok else layer.mean_function
+    Din, R = ol.Z.shape[1], ol.q_mu.shape[1]
+    rng = np.random.default_rng(4)
+    F = rng.standard_normal((S_, N, Din)); z = rng.standard_normal((S_, R, N))
+    Fo = T64(F).requires_grad_(True)
+    so, mo, vo = O.independent_multisample_sample_conditional(Fo, ol.Z, okern, ol.q_mu, full_cov=True, q_sqrt=ol.q_sqrt,
+                                                              white=True, eps_joint=T64(z))
+    if not mok:
+        mf = ol.mean_function(Fo)
+        so, mo = so + mf, mo + mf
+    Fg = T64(F).cuda().requires_grad_(True)
+    for _, p in layer.named_parameters():
+        p.unconstrained.requires_grad_(True)
+    s, m, v = tw.independent_multisample_sample_conditional(Fg, layer.feature, gkern, layer.q_mu, full_cov=True,
+                                                            q_sqrt=layer.q_sqrt, white=True, eps=T64(z).cuda(),
+                                                            mean_function=gmf)
+    close('sample', s, so); close('mean', m, mo); close('cov', v, vo)
+    cs, cm = T64(rng.standard_normal(so.shape)), T64(rng.standard_normal(mo.shape))
+    cv = T64(rng.standard_normal(vo.shape))          # deliberately not symmetric
+    (so * cs).sum().add((mo * cm).sum()).add((vo * cv).sum()).backward()
+    (s * cs.cuda()).sum().add((m * cm.cuda()).sum()).add((v * cv.cuda()).sum()).backward()
+    close('dF', Fg.grad, Fo.grad)
+    feat = layer.feature.feat if hasattr(layer.feature, 'feat') else layer.feature
+    close('dZ', feat.Z.unconstrained.grad, leaves[pre + 'Z'].grad)
+    close('dq_mu', layer.q_mu.unconstrained.grad, leaves[pre + 'q_mu'].grad)
+    close('dq_sqrt', layer.q_sqrt.unconstrained.grad, torch.tril(leaves[pre + 'q_sqrt'].grad))
+    sig = lambda p: torch.sigmoid(p.unconstrained.detach())
+    close('dls', gkern.lengthscales.unconstrained.grad / sig(gkern.lengthscales), leaves[pre + 'kern.lengthscales'].grad)
+    close('dvariance', gkern.variance.unconstrained.grad / sig(gkern.variance), leaves[pre + 'kern.variance'].grad)
+    if not mok:
+        close('dA', layer.mean_function.A.unconstrained.grad, leaves[pre + 'mf.A'].grad)
+        close('db', layer.mean_function.b.unconstrained.grad, leaves[pre + 'mf.b'].grad)
