@@ -103,7 +103,8 @@ class DGP_VI(Parameterized):
         return out, {k: v.cpu().numpy() for k, v in FlatParams.of(self).grads_by_name().items()}
 
     # ---- prediction (reference models.py:89-107) --------------------------------------------
-    def predict_f_multisample(self, X, S, eps=None):
+    def _predict_device(self, X, S, eps=None):
+        """[S, N, Dy] mean and variance of the final layer as device tensors (views of the plan's buffers)."""
         X = np.asarray(X, dtype=np.float64)
         eng = self.engine(len(X), int(S), 'predict')
         eng.set_batch(X)
@@ -111,17 +112,26 @@ class DGP_VI(Parameterized):
         eng.draw_noise(eps, seed=self.noise_seed, step=self._evals)
         m, v = eng.forward()
         eng.check_info()
-        return (m.view(int(S), len(X), self.Dy).cpu().numpy(), v.view(int(S), len(X), self.Dy).cpu().numpy())
+        return m.view(int(S), len(X), self.Dy), v.view(int(S), len(X), self.Dy)
+
+    def predict_f_multisample(self, X, S, eps=None):
+        m, v = self._predict_device(X, S, eps)
+        return m.cpu().numpy(), v.cpu().numpy()
 
     def predict_y_samples(self, X, S, eps=None, eps_y=None):
-        m, v = self.predict_f_multisample(X, S, eps)
-        lik = float(self.likelihood.variance.read_value())
+        """reference models.py:99-107: y = f_mean + z sqrt(f_var + likelihood variance), z ~ N(0, 1) drawn on the device
+        (iwvi_normal_fill, keyed by the evaluation count) unless injected as eps_y [S, N, Dy]."""
+        from . import capi
+        from .engine import layer_seed
+        m, v = self._predict_device(X, S, eps)
         if eps_y is None:
             self._evals += 1
-            z = np.random.default_rng(self.noise_seed + self._evals).standard_normal(m.shape)
+            z = torch.empty_like(m)
+            capi.normal_fill(z, m.shape[0] * m.shape[1], self.Dy, 0, layer_seed(self.noise_seed, self._evals, 1 << 20))
         else:
-            z = np.asarray(eps_y).reshape(m.shape)
-        return m + z * (v + lik) ** 0.5
+            z = torch.as_tensor(np.asarray(eps_y, dtype=np.float64), dtype=settings.float_type).to(m.device).reshape(m.shape)
+        lik = FlatParams.of(self).cview(self.likelihood.variance)
+        return (m + z * torch.sqrt(v + lik)).cpu().numpy()
 
     def predict_f(self, X, eps=None):
         """GPModel.predict_f -> _build_predict(X, full_cov=False): one propagation of the 2-D inputs."""

@@ -76,6 +76,11 @@ def test_predict_matches_oracle():
     np.testing.assert_allclose(vv, v_ref.numpy(), rtol=1e-8, atol=1e-12)
     ys = m.predict_y_samples(X, Sn)
     assert ys.shape == (Sn, N, 1) and np.isfinite(ys).all()
+    # models.py:99-107 with the likelihood noise injected: y = mean + z sqrt(var + likelihood variance), on the device
+    eps_y = np.random.default_rng(33).standard_normal((Sn, N, 1))
+    ys_ref = model.predict_y_samples(T(X), Sn, [T(e) for e in eps], T(eps_y))
+    ys2 = m.predict_y_samples(X, Sn, [None if e is None else e.reshape(Sn * N, -1) for e in eps], eps_y)
+    np.testing.assert_allclose(ys2, ys_ref.numpy(), rtol=1e-8, atol=1e-10)
 
 
 def test_parameter_assignment_and_frozen_flags():
