@@ -284,6 +284,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Register reallocation between the roles of a warp-specialised CTA (setmaxnreg, sm_90+).  With a ninth warp one SM
+// sub-partition hosts three warps and ptxas must fit 3 x 32 x regs into its 16 K registers: 168 per thread for EVERY
+// warp.  Launching three full warpgroups (384 threads: 8 consumer warps, the producer warp and 3 idle warps that exit)
+// lets the producer warpgroup hand its registers back (dec) and the two consumer warpgroups grow (inc) -- the
+// instruction is warpgroup-aligned, which is why the producer side is padded to four warps.
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+#define IWVI_WS_THREADS 384         // 2 consumer warpgroups + 1 producer warpgroup (one active warp)
+#define IWVI_PRODUCER_REGS 24
+#define IWVI_CONSUMER_REGS 240      // 168 + (168 - 24) * 128 / 256
+
 template <int NST>
 struct RingT {
   uint64_t* full;    // [NST]

@@ -35,7 +35,7 @@ template <int TP> struct TileCfg {
 #define EPI_STRIDE 1344   // >= P*R + D*P + P + 1 at the maxima (32*8 + 32*32 + 32 + 1 = 1313)
 #define EPI_PTS 32
 #define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
-#define TILE_THREADS 288    // 8 consumer warps + 1 producer warp
+#define TILE_THREADS IWVI_WS_THREADS    // 8 consumer warps + the producer warpgroup (1 active warp)
 #define BAR_ALL 1
 #define BAR_COL 2
 
@@ -280,22 +280,45 @@ struct BwdSeq {
 // acc += Lq_block * V for one streamed 64x64 block of tril(q_sqrt_r) (row-major, A operand) and the register-resident
 // V fragments of this warp's 16 points.  DIAG: the block is lower triangular; row tile ti = WMI + WMG * a only needs
 // k < 8 (ti + 1), and because WMI is a template parameter the skipped DMMAs vanish at compile time.
+// The A fragments are fetched two k-step groups ahead of the DMMAs that consume them, with a warp barrier per group as
+// a scheduling fence: left to itself ptxas sinks every LDS next to its two DMMAs and recycles ONE register pair for
+// all 64 fragments (SASS: LDS R132 / DMMA / DMMA / LDS R132 ...), which exposes the shared-memory latency once per
+// two DMMAs (short-scoreboard stalls were a third of this loop's samples, profiles/ncu_c3_r01e.md).
 template <int TM, int WMG, int WMI, bool DIAG>
 __device__ __forceinline__ void lq_v_product(double (&acc)[TM][2][2], const double* __restrict__ ap,
                                              const double (&vb)[16][2]) {
+  constexpr int G = 2;               // k-steps per group
+  constexpr int NG = 16 / G;
+  double a[3][G][TM];
+  auto need = [](int ks, int a_) { return !DIAG || ks < 2 * (WMI + WMG * a_ + 1); };
+  auto fetch = [&](auto buf_c, auto grp_c) {
+    constexpr int buf = decltype(buf_c)::value, grp = decltype(grp_c)::value;
 #pragma unroll
-  for (int ks = 0; ks < 16; ks++) {
-    double a[TM];
+    for (int kk = 0; kk < G; kk++)
 #pragma unroll
-    for (int a_ = 0; a_ < TM; a_++)
-      if (!DIAG || ks < 2 * (WMI + WMG * a_ + 1)) a[a_] = ap[a_ * 8 * WMG * IWVI_LDS + ks * 4];
+      for (int a_ = 0; a_ < TM; a_++)
+        if (need(grp * G + kk, a_)) a[buf][kk][a_] = ap[a_ * 8 * WMG * IWVI_LDS + (grp * G + kk) * 4];
+  };
+  auto step = [&](auto grp_c) {
+    constexpr int grp = decltype(grp_c)::value, buf = grp % 3;
+    __syncwarp();
+    if constexpr (grp + 2 < NG) fetch(std::integral_constant<int, (grp + 2) % 3>(), std::integral_constant<int, grp + 2>());
 #pragma unroll
-    for (int a_ = 0; a_ < TM; a_++)
-      if (!DIAG || ks < 2 * (WMI + WMG * a_ + 1)) {
-        dmma884(acc[a_][0], a[a_], vb[ks][0]);
-        dmma884(acc[a_][1], a[a_], vb[ks][1]);
-      }
-  }
+    for (int kk = 0; kk < G; kk++)
+#pragma unroll
+      for (int a_ = 0; a_ < TM; a_++)
+        if (need(grp * G + kk, a_)) {
+          dmma884(acc[a_][0], a[buf][kk][a_], vb[grp * G + kk][0]);
+          dmma884(acc[a_][1], a[buf][kk][a_], vb[grp * G + kk][1]);
+        }
+  };
+  fetch(std::integral_constant<int, 0>(), std::integral_constant<int, 0>());
+  fetch(std::integral_constant<int, 1>(), std::integral_constant<int, 1>());
+  step(std::integral_constant<int, 0>()); step(std::integral_constant<int, 1>());
+  step(std::integral_constant<int, 2>()); step(std::integral_constant<int, 3>());
+  step(std::integral_constant<int, 4>()); step(std::integral_constant<int, 5>());
+  step(std::integral_constant<int, 6>()); step(std::integral_constant<int, 7>());
+  static_assert(NG == 8, "lq_v_product is written out for eight groups of two k-steps");
 }
 
 // acc[b] += sum_k a(k) * B(k, 8 b + g) for b < NB8: one 8-row A tile (this lane's element of k-step k0 is ap[k0 * a_stride])
@@ -366,7 +389,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   for (int idx = threadIdx.x; idx < NB * TP * 4; idx += TILE_THREADS) panel[(idx >> 2) * IWVI_LDS + IWVI_BLK + (idx & 3)] = 0.0;
   RingT<IWVI_NST> pipe;
   pipe.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages, C::NW);
-  if (warp == C::NW) {
+  if (warp >= C::NW) {
+    reg_dealloc<IWVI_PRODUCER_REGS>();
+    if (warp > C::NW) return;      // padding of the producer warpgroup
     // producer warp: the block sequence is the same for every tile
     BwdSeq seq;
     seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
@@ -381,6 +406,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     return;
   }
 
+  reg_alloc<IWVI_CONSUMER_REGS>();
   const int g = lane >> 2, t = lane & 3;
   // row tiles of a 64-row block dealt round-robin to the warps of a column group, order flipped in warps 4-7 (see
   // gp_rows_fwd.cu): balances the work skipped in triangular diagonal blocks across warps and SM sub-partitions
