@@ -109,6 +109,43 @@ __device__ __forceinline__ void warp_gemm(double (&acc)[TM][TN][2], const double
   }
 }
 
+// warp_gemm over a full 64-deep block with the operand fragments of k-step s + 1 fetched while the DMMAs of k-step s
+// issue (two register buffers).  In warp_gemm every iteration starts with its 12 fragment loads and then waits out the
+// shared-memory latency before its first DMMA; the two warps of an SM sub-partition leave a ring wait together, run
+// those phases in lock step, and the FP64 pipe idles once per iteration.  The warp barrier is a scheduling fence: it
+// keeps ptxas from sinking the prefetch loads back next to their consumers (needs the consumer register budget of
+// reg_alloc below).
+template <int TM, int TN, int ALAY, int BLAY, int MS = 1>
+__device__ __forceinline__ void warp_gemm_pf(double (&acc)[TM][TN][2], const double* __restrict__ As, int lda,
+                                             const double* __restrict__ Bs, int ldb, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const double* ap = ALAY == 0 ? As + g * lda + t : As + t * lda + g;
+  const double* bp = BLAY == 0 ? Bs + g * ldb + t : Bs + t * ldb + g;
+  double a0[TM], b0[TN], a1[TM], b1[TN];
+  auto fetch = [&](double (&a)[TM], double (&b)[TN], int k0) {
+#pragma unroll
+    for (int i = 0; i < TM; i++) a[i] = ALAY == 0 ? ap[i * 8 * MS * lda + k0] : ap[k0 * lda + i * 8 * MS];
+#pragma unroll
+    for (int j = 0; j < TN; j++) b[j] = BLAY == 0 ? bp[j * 8 * ldb + k0] : bp[k0 * ldb + j * 8];
+  };
+  auto mma = [&](const double (&a)[TM], const double (&b)[TN]) {
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++) dmma884(acc[i][j], a[i], b[j]);
+  };
+  fetch(a0, b0, 0);
+#pragma unroll 2
+  for (int k0 = 0; k0 < IWVI_BLK; k0 += 8) {
+    __syncwarp();
+    fetch(a1, b1, k0 + 4);
+    mma(a0, b0);
+    __syncwarp();
+    if (k0 + 8 < IWVI_BLK) fetch(a0, b0, k0 + 8);
+    mma(a1, b1);
+  }
+}
+
 // The same product for a TRIANGULAR 64x64 A block whose structural zeros are skipped at the granularity of the 8x8x4
 // DMMA: Ablk is the block's (0,0) corner, the warp's row tiles are mt0, mt0 + MS, ... (units of 8 rows).  The k range
 // is cut into segments inside which the set of active row tiles is a compile-time constant, so no DMMA is ever issued

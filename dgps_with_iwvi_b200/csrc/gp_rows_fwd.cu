@@ -90,7 +90,7 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int TP, int Mp, int ldx) {
   return s;
 }
 
-#define FWD_THREADS 288   // 8 consumer warps + 1 producer warp
+#define FWD_THREADS IWVI_WS_THREADS   // 8 consumer warps + the producer warpgroup (1 active warp)
 #define BAR_ALL 1         // named barrier of the 256 consumer threads
 #define BAR_COL 2         // + column-group index: the WMG warps that share a set of points
 
@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
   RingT<IWVI_NST> ring;
   ring.setup(reinterpret_cast<uint64_t*>(smem + sl.bars), smem + sl.stages, C::NW);
 
-  if (warp == C::NW) {
+  if (warp >= C::NW) {
+    reg_dealloc<IWVI_PRODUCER_REGS>();
+    if (warp > C::NW) return;      // padding of the producer warpgroup (setmaxnreg is warpgroup-aligned, common.cuh)
     // ---- producer warp: streams the tile-independent block sequence once per tile, running ahead of the consumers
     FwdSeq seq;
     seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     return;
   }
 
+  reg_alloc<IWVI_CONSUMER_REGS>();
   const int g = lane >> 2, t = lane & 3;
   // Row tiles (8 rows) of a 64-row block are dealt round-robin to the WMG warps of a column group: warp `wmi` owns
   // tiles wmi, wmi + WMG, ...  With the triangular diagonal blocks this balances the skipped work, and flipping the
@@ -245,8 +248,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
               acc[a][b][c] = -panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g];
         for (int j = 0; j < i; j++) {
           const double* st = ring.wait();
-          warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * IWVI_LDS, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS,
-                                                IWVI_LDS, IWVI_BLK, lane);
+          warp_gemm_pf<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * IWVI_LDS, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS,
+                                                   IWVI_LDS, lane);
           ring.release(lane);
         }
 #pragma unroll
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
           if (j == i)   // diagonal block of tril(q_sqrt_r), used transposed: upper triangular in (m, k)
             warp_gemm_tri<C::TM, C::TN, 1, 0, C::WMG, 0>(acc, st, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS, IWVI_LDS, wmi, lane);
           else
-            warp_gemm<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS, IWVI_LDS, IWVI_BLK, lane);
+            warp_gemm_pf<C::TM, C::TN, 1, 0, C::WMG>(acc, st + wr0, IWVI_LDS, panel + j * PSTR + wn0 * IWVI_LDS, IWVI_LDS, lane);
           ring.release(lane);
         }
 #pragma unroll
