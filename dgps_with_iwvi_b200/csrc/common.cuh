@@ -332,6 +332,15 @@ template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("set
 #define IWVI_PRODUCER_REGS 24
 #define IWVI_CONSUMER_REGS 240      // 168 + (168 - 24) * 128 / 256
 
+// Host-side guard: setmaxnreg.inc waits until the CTA's register pool (registers per thread at launch x threads) can
+// serve the request, so a build whose launch allocation could not cover consumers + producers would hang, not fail.
+template <class Kernel>
+inline bool iwvi_ws_pool_ok(Kernel kernel) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return false;
+  return (long)fa.numRegs * IWVI_WS_THREADS >= (long)IWVI_CONSUMER_REGS * 256 + (long)IWVI_PRODUCER_REGS * 128;
+}
+
 template <int NST>
 struct RingT {
   uint64_t* full;    // [NST]

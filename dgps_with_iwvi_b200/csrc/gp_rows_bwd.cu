@@ -1121,6 +1121,8 @@ __global__ void __launch_bounds__(256) gp_finalize_bwd_kernel(const BwdParams p)
 
 template <int TP, int KIND>
 static int launch_tile_k(const BwdParams& p, int smem_bytes, cudaStream_t st) {
+  static const bool pool_ok = iwvi_ws_pool_ok(gp_tile_bwd_kernel<TP, KIND>);
+  if (!pool_ok) return IWVI_ERR_LAUNCH;
   if (cudaFuncSetAttribute(gp_tile_bwd_kernel<TP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
   gp_tile_bwd_kernel<TP, KIND><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);

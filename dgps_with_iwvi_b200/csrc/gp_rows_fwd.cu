@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
 
 template <int TP, int KIND>
 int launch_fwd_k(const FwdParams& p, int smem_bytes, int grid, cudaStream_t stream) {
+  static const bool pool_ok = iwvi_ws_pool_ok(gp_rows_fwd_kernel<TP, KIND>);
+  if (!pool_ok) return IWVI_ERR_LAUNCH;
   if (cudaFuncSetAttribute(gp_rows_fwd_kernel<TP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
   gp_rows_fwd_kernel<TP, KIND><<<grid, FWD_THREADS, smem_bytes, stream>>>(p);
