@@ -49,6 +49,8 @@ SIGNATURES = {
     'iwvi_gp_pbwd_ws_doubles': (C.c_int64, [C.POINTER(GpDesc)]),
     'iwvi_gp_prologue_fwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 10),
     'iwvi_gp_rows_fwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 12),
+    'iwvi_gp_rows_fwd_range': (C.c_int, [C.POINTER(GpDesc)] + [P] * 11 + [C.c_int64, C.c_int64, P]),
+    'iwvi_gp_tile_points': (C.c_int, [C.POINTER(GpDesc)]),
     'iwvi_gp_rows_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 23),
     'iwvi_gp_prologue_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 16),
     'iwvi_gp_fullcov_fwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 5 + [C.c_double] + [P] * 4),

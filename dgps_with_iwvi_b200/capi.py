@@ -108,6 +108,20 @@ def gp_rows_fwd(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save):
             'iwvi_gp_rows_fwd')
 
 
+def gp_rows_fwd_range(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save, point_begin, point_end):
+    _count(1)
+    L.check(L.load().iwvi_gp_rows_fwd_range(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(X), _ptr(W), _ptr(mfA), _ptr(mfb),
+                                            _ptr(eps), _ptr(sample), _ptr(mean), _ptr(var), _ptr(save),
+                                            int(point_begin), int(point_end), _stream()), 'iwvi_gp_rows_fwd_range')
+
+
+def gp_tile_points(d):
+    tp = L.load().iwvi_gp_tile_points(C.byref(d))
+    if tp < 0:
+        L.check(tp, 'iwvi_gp_tile_points')
+    return tp
+
+
 def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu, dq_sqrt,
                 dLm, dW, dmfA, dmfb, ws):
     only = d.flags & 240

@@ -65,7 +65,7 @@ struct FwdParams {
   iwvi_gp_desc d;
   const double *Lm, *aux, *X, *W, *mfA, *mfb, *eps;
   double *sample, *mean, *var, *save;
-  int ntiles;
+  int tile0, ntiles;   // this launch covers tiles [tile0, ntiles)
 };
 
 // dynamic shared memory carve-up (doubles), shared with the host-side size computation
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
     FwdSeq seq;
     seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
     seq.Zt = aux + al.off_zt; seq.Lmb = aux + al.off_lmb; seq.Lqb = aux + al.off_lqb;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       seq.init();
       while (!seq.done()) { ring.produce(seq.get(), lane); seq.advance(); }
     }
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
   const bool do_sample = (d.flags & IWVI_FLAG_SAMPLE) != 0;
 
   PHASE_DECL;
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  for (int tile = p.tile0 + blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int n0 = tile * TP;
     if (warp == 0) bulk_wait_read();   // the previous tile's bulk stores no longer read the panel
     named_bar_sync(BAR_ALL, 256);      // previous tile fully done with every shared buffer
@@ -472,9 +472,22 @@ int iwvi_pick_tp(int T, int Mp, int ldz, int nsm, int max_smem, int* smem_bytes)
   return best;
 }
 
-extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
-                                const double* W, const double* mfA, const double* mfb, const double* eps,
-                                double* sample, double* mean, double* var, double* save, void* stream) {
+extern "C" int iwvi_gp_tile_points(const iwvi_gp_desc* d) {
+  int rc = iwvi_check_gp_desc(d);
+  if (rc != IWVI_OK) return rc;
+  int dev = 0, nsm = 148, max_smem = 0, smem_bytes = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const AuxLayout al = iwvi_aux_layout(d->M, d->D, d->R);
+  const int TP = iwvi_pick_tp(d->T, al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
+  return TP < 0 ? IWVI_ERR_UNSUPPORTED : TP;
+}
+
+extern "C" int iwvi_gp_rows_fwd_range(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
+                                      const double* W, const double* mfA, const double* mfb, const double* eps,
+                                      double* sample, double* mean, double* var, double* save,
+                                      int64_t point_begin, int64_t point_end, void* stream) {
   int rc = iwvi_check_gp_desc(d);
   if (rc != IWVI_OK) return rc;
   if (!Lm || !aux || !X || !mean || !var) return IWVI_ERR_NULL;
@@ -482,7 +495,8 @@ extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const d
   if (d->mf == IWVI_MF_LINEAR && (!mfA || !mfb)) return IWVI_ERR_NULL;
   if ((d->flags & IWVI_FLAG_SAMPLE) && (!eps || !sample)) return IWVI_ERR_NULL;
   if ((d->flags & IWVI_FLAG_SAVE) && !save) return IWVI_ERR_NULL;
-  if (d->T == 0) return IWVI_OK;
+  if (point_begin < 0 || point_end > d->T || point_begin > point_end) return IWVI_ERR_BAD_DESC;
+  if (d->T == 0 || point_begin == point_end) return IWVI_OK;
   int dev = 0, nsm = 148, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -491,13 +505,28 @@ extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const d
   int smem_bytes = 0;
   const int TP = iwvi_pick_tp(d->T, al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
   if (TP < 0) return IWVI_ERR_UNSUPPORTED;
+  if (point_begin % TP) return IWVI_ERR_BAD_DESC;                       // ranges start on a tile boundary ...
+  if (point_end != d->T && point_end % TP) return IWVI_ERR_BAD_DESC;    // ... and end on one, or at the last point
   FwdParams p;
   p.d = *d; p.Lm = Lm; p.aux = aux; p.X = X; p.W = W; p.mfA = mfA; p.mfb = mfb; p.eps = eps;
   p.sample = sample; p.mean = mean; p.var = var; p.save = save;
-  // when saving, cover the zero-padded rows of the saved arrays too (at most 128/TP - 1 extra, all-zero tiles)
-  p.ntiles = (d->flags & IWVI_FLAG_SAVE) ? iwvi_save_layout(d->T, d->M, d->R).Tp / TP : (d->T + TP - 1) / TP;
-  const int grid = p.ntiles < nsm ? p.ntiles : nsm;
+  p.tile0 = (int)(point_begin / TP);
+  // when saving, the range that ends at the last point also covers the zero-padded rows of the saved arrays (at most
+  // 128/TP - 1 extra, all-zero tiles)
+  if (point_end == d->T)
+    p.ntiles = (d->flags & IWVI_FLAG_SAVE) ? iwvi_save_layout(d->T, d->M, d->R).Tp / TP : (d->T + TP - 1) / TP;
+  else
+    p.ntiles = (int)(point_end / TP);
+  const int count = p.ntiles - p.tile0;
+  const int grid = count < nsm ? count : nsm;
   cudaStream_t st = (cudaStream_t)stream;
   if (TP == 64) return launch_fwd<64>(p, smem_bytes, grid, st);
   return launch_fwd<32>(p, smem_bytes, grid, st);
+}
+
+extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
+                                const double* W, const double* mfA, const double* mfb, const double* eps,
+                                double* sample, double* mean, double* var, double* save, void* stream) {
+  if (!d) return IWVI_ERR_NULL;
+  return iwvi_gp_rows_fwd_range(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save, 0, d->T, stream);
 }

@@ -101,7 +101,7 @@ class Engine:
        mode 'vi'      : DGP_VI._build_likelihood,   points = [S*B] sample-major (models.py:50-53), K := S
        mode 'predict' : propagate without amortisation inputs, points = [S, N] (models.py:93-107), B := N, K := S"""
 
-    def __init__(self, model, B, K, mode='iw', world_size=1, rank=0):
+    def __init__(self, model, B, K, mode='iw', world_size=1, rank=0, split_waves=True):
         from .layers import GPLayer, LatentVariableLayer
         if not torch.cuda.is_available():
             raise RuntimeError('dgps_with_iwvi_b200: no CUDA device -- the IW-ELBO path has no CPU fallback')
@@ -224,6 +224,25 @@ class Engine:
         self.X_tiled = None
         if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
             self.X_tiled = z(T, self.Dx)
+        # Points are independent through the whole chain of GP layers, and a layer's forward kernel is persistent over
+        # tiles of 64 (32) points: T / tile points is rarely a multiple of the SM count, so the last wave of every layer
+        # leaves SMs idle (c3: 400 tiles on 148 SMs = 2.7 waves run as 3).  The forward pass therefore runs the layer
+        # chain of the full waves on the main stream and the chain of the remaining tiles on a second stream; the two
+        # never exchange data before the likelihood, and the remainder's CTAs fill the SMs the other chain leaves free.
+        self.split = None
+        self.side_f = torch.cuda.Stream(device=dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        gps = [r for r in self.recs if r['type'] == 'gp']
+        first_gp = self.recs.index(gps[0])
+        if all(r['type'] == 'gp' for r in self.recs[first_gp:]) and split_waves:
+            tps = {capi.gp_tile_points(r['d']) for r in gps}
+            if len(tps) == 1:
+                tp = tps.pop()
+                nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+                tiles = -(-T // tp)
+                full = tiles // nsm * nsm
+                if full > 0 and tiles - full >= nsm // 8:
+                    self.split = full * tp
 
     # ------------------------------------------------------------------------------------------
     def _cv(self, p):
@@ -312,12 +331,25 @@ class Engine:
                 layer, base = r['layer'], r['base']
                 r['Fin'] = F
                 main.wait_event(self.ev_pro[r['gi']])
-                capi.gp_rows_fwd(r['d'], r['Lm'], r['aux'], F,
-                                 self._cv(layer.kern.W) if r['mix'] else None,
-                                 self._cv(layer.mean_function.A) if r['mf'] == 'Linear' else None,
-                                 self._cv(layer.mean_function.b) if r['mf'] == 'Linear' else None,
-                                 r['eps'], r['sample'], r['mean'], r['var'], r.get('save'))
+                args = (r['d'], r['Lm'], r['aux'], F,
+                        self._cv(layer.kern.W) if r['mix'] else None,
+                        self._cv(layer.mean_function.A) if r['mf'] == 'Linear' else None,
+                        self._cv(layer.mean_function.b) if r['mf'] == 'Linear' else None,
+                        r['eps'], r['sample'], r['mean'], r['var'], r.get('save'))
+                if self.split is None:
+                    capi.gp_rows_fwd(*args)
+                else:
+                    if r['gi'] == 0:          # the chain's inputs (latent-variable layer output, noise) are complete
+                        self.ev_fork.record(main)
+                        self.side_f.wait_event(self.ev_fork)
+                    self.side_f.wait_event(self.ev_pro[r['gi']])
+                    capi.gp_rows_fwd_range(*args, 0, self.split)
+                    with torch.cuda.stream(self.side_f):
+                        capi.gp_rows_fwd_range(*args, self.split, self.T)
                 F = r['sample']
+        if self.split is not None:
+            self.ev_join.record(self.side_f)
+            main.wait_event(self.ev_join)
         last = self.recs[-1]
         if self.mode == 'predict':
             return last['mean'], last['var']

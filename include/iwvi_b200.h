@@ -131,6 +131,18 @@ int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const double* aux,
                      double* sample, double* mean, double* var, double* save, void* stream);
 
 /*
+ * The same stage over the points [point_begin, point_end) only (all pointers and the descriptor are those of the whole
+ * call; point_begin a multiple of iwvi_gp_tile_points(d), point_end too unless it is d->T).  Points are independent
+ * through the whole layer chain, so a caller can run the chain of disjoint ranges on different streams -- the engine
+ * splits a minibatch into its full waves of tiles and the remainder, which fills the SMs the last wave leaves idle.
+ */
+int iwvi_gp_rows_fwd_range(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
+                           const double* W, const double* mfA, const double* mfb, const double* eps,
+                           double* sample, double* mean, double* var, double* save,
+                           int64_t point_begin, int64_t point_end, void* stream);
+int iwvi_gp_tile_points(const iwvi_gp_desc* d);        /* points per tile (64 or 32) the row kernels use for d */
+
+/*
  * Adjoint of iwvi_gp_rows_fwd (the reference: tf.gradients through temp_workaround.py:44-91,142-145,
  * layers.py:46-48; formulas in DESIGN.md).  Cotangents d_sample/d_mean/d_var [T,P] may be NULL.
  *   out (overwritten): dX [T,D], dZ [M,D], dls [D], dvariance [1], dq_mu [M,R], dq_sqrt [R,M,M] (lower),

@@ -252,6 +252,18 @@ def test_full_size_properties_c3():
     m._evals -= 1
     e2, g2 = m.compute_log_likelihood_and_grads(Xb, Yb)
     assert e1 == e2 and all(np.array_equal(g1[k], g2[k]) for k in g1)
+    # the forward pass runs the full waves of tiles and the remainder as two chains on two streams: same kernels on the
+    # same points, so the result must be bit-identical to the single-chain pass
+    from dgps_with_iwvi_b200.engine import Engine, FlatParams
+    flat = FlatParams.of(m)
+    assert eng.split == 296 * 64
+    eng.elbo_and_grads(Xb, Yb, None, seed=11, step=2)
+    g_split = flat.g.clone()
+    one = Engine(m, B, K, 'iw', split_waves=False)
+    assert one.split is None
+    one.elbo_and_grads(Xb, Yb, None, seed=11, step=2)
+    assert torch.equal(flat.g, g_split)
+    del one
     tr = Trainer(m, B, lr=1e-2, seed=3)
     losses = [tr.step(X[i * B:(i + 1) * B], Y[i * B:(i + 1) * B]) for i in range(12)]
     tr.engine.check_info()
