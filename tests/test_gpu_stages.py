@@ -385,3 +385,48 @@ def test_fullcov_stage_info_and_errors():
     assert lib.iwvi_gp_fullcov_fwd(C.byref(capi.with_flags(df, df.flags, T=65 * 2)), 2, 65, *args) == -2   # N > 64
     mixed = capi.gp_desc(T, M, D, R, 4, 'RBF', True, 'Zero', LIB.FLAG_SAVE, 1e-6)
     assert lib.iwvi_gp_fullcov_fwd(C.byref(mixed), S_, N, *args) == -1            # the Mok branch forces full_cov=False
+
+
+@pytest.mark.parametrize('T,M', [(20000, 100), (9700, 64)])
+def test_rows_fwd_range_equals_whole_call(T, M):
+    """iwvi_gp_rows_fwd_range over two disjoint point ranges (also on two streams at once) writes bit for bit what
+    iwvi_gp_rows_fwd writes in one call -- outputs and the saved panels -- and rejects ranges that do not start / end on
+    a tile boundary."""
+    import ctypes as C
+    from dgps_with_iwvi_b200 import capi
+    from dgps_with_iwvi_b200 import _lib as LIB
+    D, R, P = 5, 3, 4
+    rng = np.random.default_rng(T + M)
+    L = make_layer(rng, T, M, D, R, P, True, 'Linear', 'RBF')
+    g = run_prologue(L)
+    df = capi.with_flags(g['d'], LIB.FLAG_SAMPLE | LIB.FLAG_SAVE)
+    X, eps, W, mfA, mfb = dev(L['X']), dev(L['eps']), dev(L['W']), dev(L['mfA']), dev(L['mfb'])
+
+    def bufs():
+        o = [torch.full((T, P), float('nan'), dtype=torch.float64, device='cuda') for _ in range(3)]
+        # (the 4 pad columns of the saved U blocks are never written: the caller allocates `save` zeroed)
+        return o + [torch.zeros(capi.gp_save_doubles(df), dtype=torch.float64, device='cuda')]
+
+    s0, m0, v0, sv0 = bufs()
+    capi.gp_rows_fwd(df, g['Lm'], g['aux'], X, W, mfA, mfb, eps, s0, m0, v0, sv0)
+    tp = capi.gp_tile_points(df)
+    assert tp in (32, 64)
+    cut = (T // tp // 3) * tp
+    s1, m1, v1, sv1 = bufs()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    capi.gp_rows_fwd_range(df, g['Lm'], g['aux'], X, W, mfA, mfb, eps, s1, m1, v1, sv1, 0, cut)
+    with torch.cuda.stream(side):
+        capi.gp_rows_fwd_range(df, g['Lm'], g['aux'], X, W, mfA, mfb, eps, s1, m1, v1, sv1, cut, T)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for a, b in ((s0, s1), (m0, m1), (v0, v1), (sv0, sv1)):
+        assert torch.equal(a, b)
+    assert not torch.isnan(sv1).any()
+    lib = LIB.load()
+    ptrs = [t.data_ptr() for t in (g['Lm'], g['aux'], X, W, mfA, mfb, eps, s1, m1, v1, sv1)]
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, 1, T, stream) == -1          # not on a tile boundary
+    assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, 0, cut + 1, stream) == -1
+    assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, cut, T + 1, stream) == -1
+    assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, cut, cut, stream) == 0        # empty range: nothing to do
