@@ -1139,12 +1139,15 @@ static int launch_tile(const BwdParams& p, int smem_bytes, cudaStream_t st) {
   }
 }
 
-int pick_bwd_tp(int Mp, int ldz, int max_smem, int* smem_bytes) {
-  const int cands[2] = {64, 32};
-  for (int c = 0; c < 2; c++) {
-    const int bytes = tile_smem_layout(cands[c], Mp, ldz).total_doubles * 8;
-    if (bytes <= max_smem) { *smem_bytes = bytes; return cands[c]; }
-  }
+// tile width of the tile kernel: 64 points when that still gives every SM at least two tiles (or 32 does not fit),
+// else 32 -- the rule of the forward kernel (iwvi_pick_tp), c2: 0.529 -> 0.507 ms/step.  With few points (c2: 160 tiles of 64 on 148 SMs) the
+// wider tile left most of the second wave empty.
+int pick_bwd_tp(int Tp, int Mp, int ldz, int nsm, int max_smem, int* smem_bytes) {
+  const int b64 = tile_smem_layout(64, Mp, ldz).total_doubles * 8, b32 = tile_smem_layout(32, Mp, ldz).total_doubles * 8;
+  const bool fits64 = b64 <= max_smem, fits32 = b32 <= max_smem;
+  // (a single, partly filled wave of 64-point tiles is kept: at c1's size the narrower tiles measured slower)
+  if (fits64 && (Tp / 64 >= 2 * nsm || Tp / 64 <= nsm || !fits32)) { *smem_bytes = b64; return 64; }
+  if (fits32) { *smem_bytes = b32; return 32; }
   return -1;
 }
 
@@ -1190,7 +1193,7 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   p.dW = dW; p.dmfA = dmfA; p.dmfb = dmfb; p.ws = ws;
   p.wl = bwd_ws_layout(*d, nsm);
   int smem_bytes = 0;
-  const int TP = pick_bwd_tp(al.Mp, al.ldz, max_smem, &smem_bytes);
+  const int TP = pick_bwd_tp(p.wl.Tp, al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
   if (TP < 0) return IWVI_ERR_UNSUPPORTED;
   p.ntiles = p.wl.Tp / TP;   // covers the zero-padded rows too, so every row of Bbar is written
   p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
