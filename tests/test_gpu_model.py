@@ -310,3 +310,28 @@ def test_full_size_properties_c4_row_shards_add_up():
         scale = b.abs().max().item()
         assert (a - b).abs().max().item() <= 1e-9 * max(scale, 1e-300), name
     assert abs(g_sum[flat.n].item() - g_full[flat.n].item()) <= 1e-11 * abs(g_full[flat.n].item())
+
+
+def test_predict_two_chains_equals_single_chain():
+    """Prediction (models.py:93-98, no saved panels) over enough points for the forward pass to split into two point
+    chains: identical to the single-chain pass, and the ragged last tile (T not a multiple of the tile width) is served
+    by the remainder chain."""
+    from dgps_with_iwvi_b200.build_models import build_model
+    from dgps_with_iwvi_b200.engine import Engine
+    c = S.CONFIGS['c2']
+    X, Y = S.make_data(2000, c['D'], seed=4)
+    m = build_model(X, Y, c['configuration'], M=c['M'], num_IW_samples=c['K'], minibatch_size=c['B'],
+                    likelihood_variance=c['lik_variance'], mode='IWAE', seed=0)
+    N, Sn = 1003, 21                                    # 21 063 points
+    two = Engine(m, N, Sn, 'predict')
+    one = Engine(m, N, Sn, 'predict', split_waves=False)
+    assert two.split is not None and one.split is None and (N * Sn) % 32
+    outs = []
+    for eng in (two, one):
+        eng.set_batch(X[:N])
+        eng.draw_noise(None, seed=5, step=1)
+        mean, var = eng.forward()
+        eng.check_info()
+        outs.append((mean.clone(), var.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.isfinite(outs[0][0]).all() and (outs[0][1] > 0).all()
