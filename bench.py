@@ -86,7 +86,74 @@ def step_flops(cfg, B):
     return 3 * f
 
 
+class NvmlSampler:
+    """In-process NVML polling (every ~4 ms) of SM clock, power and clock-event reasons.  The thread runs from before the
+    warm-up; only samples whose timestamp falls inside [begin(), end()] -- the timed region -- are reported, so even a
+    timed region of a few tens of milliseconds is covered (a freshly spawned nvidia-smi needs ~100 ms for its first line)."""
+    MASKS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
+
+    def __init__(self, torch, local_rank):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        except Exception:
+            h = None
+        if h is None:
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else local_rank
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.h = h
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        self.samples, self.stop_flag, self.t0, self.t1 = [], False, None, None
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+
+    def start(self):
+        self.thread.start()
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=1)
+        win = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e300)]
+        if not win:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_sm, 'reasons': ['no samples']}
+        reasons = sorted(n for n, m in self.MASKS.items() if any(x[3] & m for x in win))
+        return {'sm_mhz': float(np.median([x[1] for x in win])), 'sm_max_mhz': self.max_sm,
+                'power_w_max': float(max(x[2] for x in win)), 'samples': len(win), 'reasons': reasons,
+                'source': 'nvml, 4 ms polling inside the timed region'}
+
+
 class ClockSampler:
+    def begin(self):
+        pass
+
+    def end(self):
+        pass
+
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
@@ -291,19 +358,30 @@ def main():
     for i in range(args.warmup):
         step_resident(i)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = None
     if rank == 0:
+        try:
+            sampler = NvmlSampler(torch, local_rank)
+        except Exception:
+            sampler = ClockSampler(local_rank)      # nvidia-smi -lms 25 in a subprocess
         sampler.start()
+        if isinstance(sampler, NvmlSampler):
+            time.sleep(0.02)
     l0 = capi.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.begin()
     ev0.record()
     for i in range(args.steps):
         loss = step_resident(args.warmup + i)
     ev1.record()
     barrier()
+    if sampler is not None:
+        sampler.end()
     ms = ev0.elapsed_time(ev1)
     launches = capi.LAUNCHES - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
