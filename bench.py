@@ -27,7 +27,46 @@ CONFIGS = {
     'c4': dict(configuration='L1_G5', N=16384, D=8, M=512, K=256, B=4096, lik_variance=0.01),
     'c5': dict(configuration='L1_G5_G5', N=1000000, D=8, M=256, K=50, B=512, lik_variance=0.01),
 }
-FP64_DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200 (profiles/FP64_PEAK_r01.md); MEASURED_PEAKS.json has no fp64 entry
+# Fallback FP64 tensor-pipe peak (profiles/FP64_PEAK_r01.md).  The figure the roofline uses is measured IN THE RUN by
+# measure_fp64_peak() (DMMA issue-rate probe of the library + cuBLAS DGEMM); MEASURED_PEAKS.json has no fp64 entry.
+FP64_DMMA_PEAK_TFLOPS = 37.05
+
+
+def measure_fp64_peak(torch, capi, dev):
+    """FP64 roofline denominator from this run: (a) the register-only DMMA.8x8x4 issue loop (csrc/probe.cu), one CTA of
+    8 warps per SM, best of 5; (b) cuBLAS DGEMM 4096^3 through torch.matmul, best of 5.  CUDA events, after a warm-up."""
+    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = torch.empty(nsm * 4 * 8 * 32, dtype=torch.float64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def best(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        b = 1e30
+        for _ in range(reps):
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            b = min(b, e0.elapsed_time(e1))
+        return b
+
+    iters = 20000
+    fl = [0.0]
+
+    def probe():
+        fl[0] = capi.probe_dmma(out, nsm * 4, 8, iters)
+    ms = best(probe)
+    dmma = fl[0] / (ms * 1e-3) / 1e12
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    ms = best(lambda: torch.matmul(a, b, out=c))
+    dgemm = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+    return {'dmma_probe_tflops': dmma, 'cublas_dgemm_tflops': dgemm,
+            'how': 'mma.sync.m8n8k4.f64 register-only issue loop, %d CTAs x 8 warps x %d iters x 8 accumulators, and '
+                   'torch.matmul fp64 %d^3; CUDA events, best of 5, measured in this run' % (nsm * 4, iters, n)}
 
 
 def _hbm_peak():
@@ -260,6 +299,7 @@ def run_reference(args):
         'steps_per_s': (Bs / cfg['B']) / sec, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args.config, cfg, args.gpus),
+        'arm': arm_description('reference', args.gpus),
         'cpu_baseline': {'value': value, 'unit': 'KxN samples/s', 'cores': threads, 'kind': 'port',
                          'sample': 'oracle/iwvi_oracle.py (torch-CPU fp64 op-for-op restatement, reference-style KxK final '
                                    'layer) forward+autograd on %d of %d minibatch rows x K=%d, no optimiser step; the '
@@ -270,12 +310,23 @@ def run_reference(args):
 
 
 def workload_config(name, cfg, gpus):
+    """The workload -- identical for both arms, and nothing but the workload (what each arm DOES with it is `arm`)."""
     return {'workload': '%s: %s N=%d D=%d M=%d K=%d B=%d/GPU (BASELINE.json configs)' % (
         name, cfg['configuration'], cfg['N'], cfg['D'], cfg['M'], cfg['K'], cfg['B']),
         'global_batch_rows': cfg['B'] * gpus, 'points_per_gpu_step': cfg['B'] * cfg['K'],
-        'parallelism': 'dp%d rows sharded, one all-reduce of the flat fp64 gradient bucket' % gpus,
-        'optimizer': 'adam (fused kernel)', 'launch': 'whole step replayed as a CUDA graph',
-        'l2': 'no explicit flush: each step streams its own A/U panels (> 126 MB L2) and rewrites every buffer'}
+        'step': 'IW-ELBO forward + backward over one minibatch of B rows x K importance samples',
+        'l2': 'inputs larger than L2: each step streams its own A/U panels (about 1 GB at c3 against 126 MB of L2) and '
+              'rewrites every buffer; no explicit flush'}
+
+
+def arm_description(arm, gpus):
+    if arm == 'reference':
+        return {'parallelism': 'none: rank 0 alone, all host cores (torch intra-op threads)',
+                'optimizer': 'none (forward + autograd of the IW-ELBO only: this arm does LESS work per step than the GPU arm)',
+                'launch': 'oracle/iwvi_oracle.py, float64 torch-CPU op-for-op restatement of the reference (TF1/GPflow1 '
+                          'cannot be installed here); each step = one evaluation on a bounded row sample of the minibatch'}
+    return {'parallelism': 'dp%d rows sharded, one NCCL all-reduce of the packed fp64 gradient bucket' % gpus,
+            'optimizer': 'adam (fused kernel)', 'launch': 'whole step replayed as a CUDA graph'}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -355,9 +406,9 @@ def main():
         idx = idx_all[i]
         return trainer.step_device(Xd[idx], Yd[idx])
 
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
+    # The clock sampler is constructed and started BEFORE the warm-up, on rank 0, so that nothing host-side happens on
+    # any rank between the pre-timing barrier and ev0.record(): a rank that reaches its first all-reduce while another
+    # is still setting up would wait there, and the bench takes the MAX over ranks (round-1 SCALE lost 28 % to this).
     sampler = None
     if rank == 0:
         try:
@@ -365,11 +416,11 @@ def main():
         except Exception:
             sampler = ClockSampler(local_rank)      # nvidia-smi -lms 25 in a subprocess
         sampler.start()
-        if isinstance(sampler, NvmlSampler):
-            time.sleep(0.02)
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
     l0 = capi.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     if sampler is not None:
         sampler.begin()
     ev0.record()
@@ -416,41 +467,59 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
 
+    # ---- N > 1, outside the timed region: the data-parallel evaluation (row shards + ONE all-reduce of the packed
+    # bucket, exactly the Trainer's exchange) against the same global minibatch evaluated by rank 0 alone ----
+    dp_parity = dp_parity_check(trainer, model, Xd, Yd, B, K, world, rank, torch, dist) if world > 1 else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- per-kernel timing of the three DMMA kernels of one GP layer (CUDA events on the launching stream) ----
-    kern = kernel_timings(eng, capi, LIB, torch)
+    peak = measure_fp64_peak(torch, capi, dev)
+    peak_tf = peak['dmma_probe_tflops']
+    kern = kernel_timings(eng, capi, LIB, torch, peak_tf)
     sec = ms / 1e3 / args.steps
     value = Bg * K / sec
     flops = step_flops(cfg, B)
     dom = max(kern, key=lambda k: k['ms'] * k['launches_per_step'])
+    # self-check: the end-to-end step does strictly more than the resident one (H2D + D2H every step), so a resident
+    # time ABOVE it means something host-side leaked into the resident region
+    ok_order = ms <= ms_e2e * 1.02
     out = {
         'metric': 'iw_elbo_train_KxN_samples_per_s', 'value': value, 'unit': 'KxN samples/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'steps_per_s': 1.0 / sec,
         'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': workload_config(args.config, cfg, world),
+        'arm': arm_description('b200', world),
         'clocks': clocks,
         'e2e': {'value': Bg * K / (ms_e2e / 1e3 / args.steps), 'unit': 'KxN samples/s',
                 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': B * (cfg['D'] + 1) * 8 + 0,
                 'd2h_bytes_per_step': 8},
         'gpu_launches': launches,
+        'self_check': {'resident_le_e2e': bool(ok_order), 'resident_ms': ms / args.steps, 'e2e_ms': ms_e2e / args.steps},
         'step_algorithmic_gflop_per_gpu': flops / 1e9,
         'step_tflops_per_gpu': flops / sec / 1e12,
-        'step_frac_of_fp64_dmma_peak': flops / sec / 1e12 / FP64_DMMA_PEAK_TFLOPS,
-        'roofline': {'bound': 'tensor', 'kernel': dom['kernel'], 'achieved': dom['tflops'], 'peak': FP64_DMMA_PEAK_TFLOPS,
-                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / FP64_DMMA_PEAK_TFLOPS,
+        'step_frac_of_fp64_dmma_peak': flops / sec / 1e12 / peak_tf,
+        'fp64_peak': peak,
+        'roofline': {'bound': 'tensor', 'kernel': dom['kernel'], 'achieved': dom['tflops'], 'peak': peak_tf,
+                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / peak_tf,
                      'traffic': ncu_traffic(args.config, dom['kernel']),
-                     'peak_source': 'FP64 DMMA issue-rate probe measured on this pool (profiles/FP64_PEAK_r01.md); '
-                                    'MEASURED_PEAKS.json carries only bf16 and HBM'},
+                     'peak_source': 'FP64 DMMA issue-rate probe measured in this run (fp64_peak; round-1 pool figure '
+                                    '%.2f); MEASURED_PEAKS.json carries only bf16 and HBM' % FP64_DMMA_PEAK_TFLOPS},
         'kernels': kern,
         'hbm_kernels': hbm_kernel_timings(eng, capi, LIB, torch, HBM_PEAK_GBS),
         'hbm_peak_gbs': HBM_PEAK_GBS,
         'elbo_last': last_elbo,
     }
+    if dp_parity is not None:
+        out['dp_parity_max_err'] = dp_parity['bucket_max_err_over_max']
+        out['dp_parity'] = dp_parity
+    if not ok_order:
+        sys.stderr.write('bench.py: SELF-CHECK FAILED: resident %.3f ms/step > end-to-end %.3f ms/step\n'
+                         % (ms / args.steps, ms_e2e / args.steps))
     if world == 1 and not args.no_cpu_baseline:
         spec = spec_from_model(model)
         Bs = cpu_sample_rows(cfg)
@@ -471,6 +540,41 @@ def main():
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_parity_check(trainer, model, Xd, Yd, B, K, world, rank, torch, dist):
+    """Correctness figure of the N-GPU line, outside the timed region: every rank evaluates its row shard of ONE fixed
+    global minibatch and the Trainer's exchange (packed bucket, one NCCL all-reduce) runs; rank 0 then evaluates the same
+    global minibatch alone (world size 1) and reports max|dp - single| / max|single| over the exchanged gradient entries
+    and the relative ELBO difference.  Noise is keyed by the global point index, so the two must agree to summation order."""
+    from dgps_with_iwvi_b200.models import Minibatch
+    eng, flat = trainer.engine, trainer.flat
+    N = Xd.shape[0]
+    Bg = B * world
+    gidx = torch.as_tensor(Minibatch(N, Bg, seed=123).next(), device=Xd.device)
+    mine = gidx[rank * B:(rank + 1) * B]
+    eng.elbo_and_grads(Xd[mine], Yd[mine], None, seed=77, step=1, row0=rank * B)
+    trainer.allreduce_grads()
+    torch.cuda.synchronize()
+    live = trainer.gbucket.index
+    g_dp = flat.g[live].clone()
+    out = None
+    if rank == 0:
+        eng1 = model.engine(Bg, K, None, 1, 0)
+        eng1.elbo_and_grads(Xd[gidx], Yd[gidx], None, seed=77, step=1, row0=0)
+        eng1.check_info()
+        g_1 = flat.g[live].clone()
+        scale = g_1[:-1].abs().max().item()
+        out = {'bucket_max_err_over_max': (g_dp[:-1] - g_1[:-1]).abs().max().item() / scale,
+               'elbo_rel_err': abs(g_dp[-1].item() - g_1[-1].item()) / abs(g_1[-1].item()),
+               'elbo_dp': g_dp[-1].item(), 'elbo_single': g_1[-1].item(), 'entries': int(live.numel()),
+               'what': 'dp%d (row shards + one all-reduce of the packed bucket) vs the same %d-row global minibatch on '
+                       'rank 0 alone' % (world, Bg)}
+        model.drop_engine(eng1)
+        del eng1
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return out
 
 
 def reference_iteration_timing(cfg, X, Y, torch, iters=20, warm=3):
@@ -521,7 +625,7 @@ def ncu_traffic(config, kernel):
         return None
 
 
-def kernel_timings(eng, capi, LIB, torch, reps=5):
+def kernel_timings(eng, capi, LIB, torch, peak_tf, reps=5):
     """Times gp_rows_fwd_kernel, gp_tile_bwd_kernel and gp_reduce_bwd_kernel of the widest inner GP layer alone, on the
     buffers the last step left behind.  Algorithmic flops per launch:
       rows_fwd : T[(1+R)M^2 + 2M(D+2R+1)]           tile_bwd : T[(1+R)M^2 + 2M(3D+R+1)]
@@ -530,7 +634,7 @@ def kernel_timings(eng, capi, LIB, torch, reps=5):
     only skipped at 8x8x4 granularity), so 1.0 is not reachable."""
     gps = [r for r in eng.recs if r['type'] == 'gp']
     r = max(gps, key=lambda q: q['R'] * q['M'] * q['M'])
-    n_like = len(gps)
+    n_like = sum(1 for q in gps if (q['R'], q['M']) == (r['R'], r['M']))   # layers of the timed shape (the R=1 final layer is cheaper)
     T, M, D, R = eng.T, r['M'], r['D'], r['R']
     NB = r['Mp'] // 64
     flat, layer, base, feat = eng.flat, r['layer'], r['base'], r['feat']
@@ -576,7 +680,7 @@ def kernel_timings(eng, capi, LIB, torch, reps=5):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         out.append({'kernel': name, 'layer': 'M=%d D=%d R=%d T=%d' % (M, D, R, T), 'ms': ms, 'gflop': fl / 1e9,
-                    'tflops': fl / (ms * 1e-3) / 1e12, 'frac_of_fp64_dmma_peak': fl / (ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                    'tflops': fl / (ms * 1e-3) / 1e12, 'frac_of_fp64_dmma_peak': fl / (ms * 1e-3) / 1e12 / peak_tf,
                     'launches_per_step': n_like})
     return out
 

@@ -221,3 +221,9 @@ def adam_step(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr, beta1, beta2, e
     L.check(L.load().iwvi_adam_step(_ptr(x), _ptr(grad_elbo), _ptr(m), _ptr(v), _ptr(mask), _ptr(theta_pos), int(n),
                                     int(n_pos), float(lr), float(beta1), float(beta2), float(eps), int(t), _stream()),
             'iwvi_adam_step')
+
+
+def probe_dmma(out, blocks, warps, iters):
+    """Measurement utility: register-only DMMA issue loop (csrc/probe.cu); 2*256*8*iters*warps*blocks flops."""
+    L.check(L.load().iwvi_probe_dmma(_ptr(out), int(blocks), int(warps), int(iters), _stream()), 'iwvi_probe_dmma')
+    return 2.0 * 256 * 8 * iters * warps * blocks

@@ -137,10 +137,16 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
   double* Lmb = p.aux + al.off_lmb;   // block-major padded copies: L(i,k) for i > k, inverted diagonal blocks at (k,k)
   // Dataflow schedule: CTA i owns block row i and forms its blocks (i,0) .. (i,i) left to right.  prog[r] counts the
   // blocks row r has published; block (i,k) needs L(k,j), j < k (prog[k] >= j + 1) and, off the diagonal, the inverted
-  // diagonal block of row k (prog[k] >= k + 1).  All NB <= 8 CTAs are co-resident, and row i only ever waits for rows
-  // above it, so the waits cannot deadlock.  The critical path is the chain of diagonal blocks, not a serial sweep.
+  // diagonal block of row k (prog[k] >= k + 1).  Row i only ever waits for rows above it, and block rows are handed out by
+  // an atomic TICKET (prog[15], zeroed by the pack kernel) rather than by blockIdx: the CTA that owns row k has started
+  // before any CTA that could wait on it, whatever order the hardware dispatches blocks in and however few of the NB <= 8
+  // CTAs are resident at once (each needs ~211 KB of shared memory, so it never shares an SM), so the waits cannot deadlock.
+  // The critical path is the chain of diagonal blocks, not a serial sweep.
   int* prog = reinterpret_cast<int*>(p.aux + al.off_prog);
-  const int i = blockIdx.x;
+  __shared__ int s_row;
+  if (threadIdx.x == 0) s_row = atomicAdd(prog + 15, 1);
+  __syncthreads();
+  const int i = s_row;
   auto wait_row = [&](int row, int need) {
     if (tid == 0) while (ld_acquire(prog + row) < need) {}
     __syncthreads();

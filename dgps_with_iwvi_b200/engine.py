@@ -173,6 +173,15 @@ class Engine:
                 D = D_cur
                 assert feat.Z.shape == (M, D), 'inducing inputs %s do not match layer input width %d' % (feat.Z.shape, D)
                 mfk = layer.mean_function.kind
+                if mode == 'iw' and not last and not mix:
+                    # reference models.py:118-125 asks plain-kernel inner layers for full_cov=True over K, a branch whose
+                    # sampler (temp_workaround.py:92-96) cannot execute as written; this plan draws independently over K.
+                    import warnings
+                    warnings.warn('DGP_IWVI: inner GP layer %d has a plain kernel (no SharedMixedMok): the reference would '
+                                  'request a joint draw over the K importance samples (models.py:118-125, a branch that '
+                                  'fails in the reference itself); this plan samples independently over K.  The joint '
+                                  'draw is available at the operator level (multisample_sample_conditional(full_cov=True)).'
+                                  % li, RuntimeWarning, stacklevel=3)
                 sample = not last   # the final layer's sample is never consumed (models.py:133-150, :96-97)
                 flags = (LIB.FLAG_SAMPLE if sample else 0) | (LIB.FLAG_SAVE if self.train else 0)
                 d = capi.gp_desc(T, M, D, R, P, base.kind, mix, mfk, flags, layer.jitter)

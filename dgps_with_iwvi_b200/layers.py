@@ -35,8 +35,9 @@ class GPLayer(Parameterized):
         self.jitter = settings.jitter
 
     def propagate(self, F, full_cov=False, eps=None, **kwargs):
-        """F [..., D_in] CUDA float64 tensor -> (samples, mean, cov, kl); differentiable (torch autograd) with
-        respect to F and the layer's parameters.  `eps` injects the N(0,1) draw of temp_workaround.py:89."""
+        """F [..., D_in] CUDA float64 tensor -> (samples, mean, cov, kl); differentiable (torch autograd) with respect
+        to F, and to the layer's parameters once they are marked as leaves (`layer.requires_grad_()`; a Parameter's
+        storage does not require grad by default).  `eps` injects the N(0,1) draw of temp_workaround.py:89."""
         from . import temp_workaround as tw
         samples, mean, cov = tw.multisample_sample_conditional(
             F, self.feature, self.kern, self.q_mu, full_cov=full_cov, q_sqrt=self.q_sqrt, white=True,

@@ -59,12 +59,49 @@ class DGP_VI(Parameterized):
         self.noise_seed = 0
         self._evals = 0
 
+    # ---- layer loop (reference models.py:30-46) -------------------------------------------------
+    def propagate(self, X, full_cov=False, inference_amorization_inputs=None, is_sampled_local_regularizer=False,
+                  eps=None):
+        """reference models.py:30-46: the sequential layer loop over the operator-level layers, returning
+        (samples, means, covs, kls, kl_types) with one entry per layer.  X [..., Dx] (the reference passes the tiled
+        [S*N, Dx] / [N, K, Dx] / [S, N, Dx] inputs) as a CUDA float64 tensor or array.  Every layer runs through its
+        own `propagate` (C ABI -> CUDA, torch autograd for gradients); `eps` optionally injects the N(0,1) draws, one
+        entry per layer (None = drawn with torch.randn).  Whole-model objectives do not come through here but through
+        engine.Engine (same kernels, no autograd graph)."""
+        X = torch.as_tensor(np.asarray(X, dtype=np.float64) if not torch.is_tensor(X) else X,
+                            dtype=settings.float_type).to(self.X.device)
+        samples, means, covs, kls, kl_types = [X], [], [], [], []
+        for i, layer in enumerate(self.layers):
+            sample, mean, cov, kl = layer.propagate(samples[-1], full_cov=full_cov,
+                                                    inference_amorization_inputs=inference_amorization_inputs,
+                                                    is_sampled_local_regularizer=is_sampled_local_regularizer,
+                                                    eps=None if eps is None else eps[i])
+            samples.append(sample)
+            means.append(mean)
+            covs.append(cov)
+            kls.append(kl)
+            kl_types.append(layer.regularizer_type)
+        return samples[1:], means, covs, kls, kl_types
+
     # ---- plans ------------------------------------------------------------------------------
+    MAX_ENGINES = 4       # plans own every buffer of a pass (c3: 1 GB of saved panels per training plan, c4: 27 GB)
+
     def engine(self, B, K, mode=None, world_size=1, rank=0):
-        key = (int(B), int(K), mode or self._mode, int(world_size), int(rank))
-        if key not in self._engines:
-            self._engines[key] = Engine(self, key[0], key[1], key[2], world_size, rank)
-        return self._engines[key]
+        """The execution plan for (B, K, mode, world, rank, num_data); least-recently-used plans beyond MAX_ENGINES are
+        dropped (their device buffers are freed) so that evaluating many different batch / test-set sizes cannot
+        accumulate memory.  num_data is part of the key: the ELBO scale num_data / B is fixed inside a plan."""
+        key = (int(B), int(K), mode or self._mode, int(world_size), int(rank), int(self.num_data))
+        eng = self._engines.pop(key, None)
+        if eng is None:
+            eng = Engine(self, key[0], key[1], key[2], world_size, rank)
+        self._engines[key] = eng                      # dicts keep insertion order: last = most recently used
+        while len(self._engines) > self.MAX_ENGINES:
+            self._engines.pop(next(iter(self._engines)))
+        return eng
+
+    def drop_engine(self, eng):
+        for k in [k for k, v in self._engines.items() if v is eng]:
+            del self._engines[k]
 
     def _next_batch(self):
         if self.minibatch is None:

@@ -140,3 +140,12 @@ class Parameterized:
     def set_trainable(self, flag):
         for _, p in self.named_parameters():
             p.set_trainable(flag)
+
+    def requires_grad_(self, flag=True):
+        """Operator-level autograd (layer.propagate / model.propagate composed with torch): marks every parameter's
+        unconstrained storage as a differentiable leaf, so that `.value` carries gradients back to it (through the
+        transform) and `p.unconstrained.grad` is filled by backward().  Whole-model training does not need this: it runs
+        through engine.Engine, whose hand-written backward writes the flat gradient bucket."""
+        for _, p in self.named_parameters():
+            p.unconstrained.requires_grad_(flag)
+        return self

@@ -14,8 +14,9 @@ Extra keyword arguments the reference gets implicitly: `eps` (the N(0,1) draw of
 drawn with torch.randn when omitted), `mean_function` and `jitter` (the reference adds the mean function in
 GPLayer.propagate, layers.py:46-48; here it is fused into the per-point kernel).
 
-Not on the hot path and therefore not in CUDA (raise NotImplementedError): white=False (:63-65, never taken,
-layers.py:42) and full_output_cov=True.  q_sqrt=None (:174-184, SGHMC) and the 2-D diagonal q_sqrt (:72-73) are mapped
+Not on the hot path and therefore not in CUDA (raises NotImplementedError): full_output_cov=True.  white=False (:63-65,
+never taken by GPLayer, layers.py:42) is served by the same per-point kernels after an M x M change of variables
+(Lm^-1 f, Lm^-1 tril(q_sqrt)), see independent_multisample_sample_conditional.  q_sqrt=None (:174-184, SGHMC) and the 2-D diagonal q_sqrt (:72-73) are mapped
 onto the same kernels (zero / diagonal Cholesky factors).  full_cov=True
 (:55-57,82-83, whose joint sampler :92-96 has a shape bug and is dead code in training) is served
 by iwvi_gp_fullcov_fwd / _bwd (csrc/gp_fullcov.cu: DMMA Gram products on the saved A / U panels, shared-memory
@@ -185,6 +186,45 @@ class _GPFullCov(torch.autograd.Function):
         return dX, dZ, dls, dv.reshape(ctx.var_shape), dqm, dqs, dA, db, None, None
 
 
+class _KuuCholesky(torch.autograd.Function):
+    """Lm = chol(Kuu + jitter I) [M, M] as a differentiable function of (Z, lengthscales, variance):
+    iwvi_gp_prologue_fwd (temp_workaround.py:39,48) forward, iwvi_gp_prologue_bwd (Cholesky + gram adjoint) backward."""
+
+    @staticmethod
+    def forward(ctx, Z, ls, variance, meta):
+        LIB.load()
+        dev = Z.device
+        M, D = Z.shape
+        d = capi.gp_desc(0, M, D, 1, 1, meta['kern'], False, 'Zero', 0, meta['jitter'])
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        Mp = capi.gp_mp(M)
+        Lm, aux, kl = z(Mp, Mp), z(capi.gp_aux_doubles(d)), z(1)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        Zc, lsc, vc = _c(Z), _c(ls), _c(variance).reshape(1)
+        q_mu, q_sqrt = z(M, 1), torch.eye(M, dtype=F64, device=dev)[None].contiguous()
+        capi.gp_prologue_fwd(d, Zc, lsc, vc, q_mu, q_sqrt, Lm, aux, kl, info)
+        i = int(info.item())
+        if i:
+            raise RuntimeError('Cholesky of Kuu failed: leading minor of order %d is not positive definite' % i)
+        ctx.d, ctx.saved, ctx.var_shape = d, (Zc, lsc, vc, q_mu, q_sqrt, Lm, aux), variance.shape
+        return Lm[:M, :M].contiguous()
+
+    @staticmethod
+    def backward(ctx, dL):
+        Zc, lsc, vc, q_mu, q_sqrt, Lm, aux = ctx.saved
+        d = ctx.d
+        dev = Zc.device
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
+        M, D = Zc.shape
+        Mp = Lm.shape[0]
+        dLm = z(Mp, Mp)
+        dLm[:M, :M] = torch.tril(dL)
+        dZ, dls, dv = z(M, D), z(D), z(1)
+        capi.gp_prologue_bwd(capi.with_flags(d, LIB.FLAG_SKIP_KL), Lm, aux, Zc, lsc, vc, q_mu, q_sqrt, dLm, z(1),
+                             dZ, dls, dv, z(M, 1), z(1, M, M), z(capi.gp_pbwd_ws_doubles(d)))
+        return dZ, dls, dv.reshape(ctx.var_shape), None
+
+
 def _kern_parts(kern):
     mix = hasattr(kern, 'W')
     base = kern.kernel if mix else kern
@@ -195,8 +235,6 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
                                                eps=None, mean_function=None, jitter=1e-6, W=None, sample=True):
     """Reference temp_workaround.py:12-98.  Xnew [S, N, D] (or [T, D]); f = q_mu [M, R]; q_sqrt [R, M, M].
     Returns sample, mean [S, N, P], var [S, N, P] (full_cov=False) or [S, R, N, N] (full_cov=True, forward only)."""
-    if not white:
-        raise NotImplementedError('white=False (temp_workaround.py:63-65) is never taken by GPLayer (layers.py:42)')
     X = _t(Xnew)
     lead = X.shape[:-1]
     D = X.shape[-1]
@@ -217,6 +255,18 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
             raise ValueError('Bad dimension for q_sqrt: %s' % str(q_sq.dim()))
     ls, variance = _t(kern.lengthscales), _t(kern.variance)
     ls_vec = ls.expand(D) if ls.dim() == 0 or ls.numel() == 1 else ls
+    if not white:
+        # temp_workaround.py:63-65: A <- Lm^-T A before the mean (:68) and the q_sqrt projection (:78), the prior
+        # variance term (:59) keeping the first A.  With Lm lower-triangular,
+        #     (Lm^-T A)^T f = A^T (Lm^-1 f)   and   tril(q_sqrt)^T Lm^-T A = (Lm^-1 tril(q_sqrt))^T A,
+        # and Lm^-1 tril(q_sqrt) is itself lower-triangular: the unwhitened conditional IS the whitened one at
+        # (Lm^-1 f, Lm^-1 tril(q_sqrt)).  That change of variables is M x M work once per layer (two triangular solves,
+        # library TRSM), differentiable through Lm (its adjoint reaches Z and the kernel parameters through
+        # iwvi_gp_prologue_bwd); the per-point kernels run unchanged.
+        Lm = _KuuCholesky.apply(Z, ls_vec, variance, dict(kern=kern.kind, jitter=float(jitter)))
+        q_mu = torch.linalg.solve_triangular(Lm, q_mu, upper=False)
+        if q_sqrt is not None:
+            q_sq = torch.linalg.solve_triangular(Lm, torch.tril(q_sq), upper=False)
     Wt = _t(W)
     mf_kind = mean_function.kind if mean_function is not None else 'Zero'
     mfA = _t(mean_function.A) if mf_kind == 'Linear' else None
@@ -286,19 +336,32 @@ class _GaussKL(torch.autograd.Function):
         return dqm, dqs
 
 
-def gauss_kl(q_mu, q_sqrt, K=None):
-    """Reference temp_workaround.py:167-188 with q_sqrt given: gpflow's whitened gauss_kl (K must be None, as at
-    layers.py:44)."""
-    if K is not None:
-        raise NotImplementedError('GPLayer uses the whitened KL (K=None, layers.py:44)')
+def gauss_kl(q_mu, q_sqrt, K=None, jitter=1e-6):
+    """Reference temp_workaround.py:167-188.  K=None (what GPLayer passes, layers.py:44): gpflow's whitened gauss_kl on
+    the CUDA kernel.  K given (the unwhitened prior N(0, K), never used by the layers): with L = chol(K),
+    KL[N(q_mu, Lq Lq^T) || N(0, K)] equals the whitened KL at (L^-1 q_mu, L^-1 tril(q_sqrt)) -- an M x M change of variables
+    (library Cholesky + TRSM, once per call), then the same kernel.  q_sqrt=None (:174-184, SGHMC): minus the log density
+    of q_mu under N(0, K + jitter I) (or N(0, I)), summed over outputs."""
+    qm = _t(q_mu)
     if q_sqrt is None:
-        # temp_workaround.py:174-184: minus the log density of q_mu under N(0, I), summed over outputs
-        qm = _t(q_mu)
-        return 0.5 * (qm * qm).sum() + 0.5 * qm.numel() * float(np.log(2.0 * np.pi))
+        M = qm.shape[0]
+        if K is None:
+            alpha, logdet = qm, 0.0
+        else:
+            Kt = _t(K)
+            L = torch.linalg.cholesky(Kt + jitter * torch.eye(M, dtype=F64, device=Kt.device))     # :182
+            alpha = torch.linalg.solve_triangular(L, qm, upper=False)
+            logdet = torch.log(torch.diagonal(L)).sum()
+        # -sum_r log N(q_mu_r; 0, L L^T)   (gpflow.logdensities.multivariate_normal, :184)
+        return 0.5 * (alpha * alpha).sum() + qm.shape[1] * (0.5 * M * float(np.log(2.0 * np.pi)) + logdet)
     q_sq = _t(q_sqrt)
     if q_sq.dim() == 2:
         q_sq = torch.diag_embed(q_sq.t())      # gpflow gauss_kl's diagonal form [M, R]
-    return _GaussKL.apply(_t(q_mu), q_sq)
+    if K is not None:
+        L = torch.linalg.cholesky(_t(K))
+        qm = torch.linalg.solve_triangular(L, qm, upper=False)
+        q_sq = torch.linalg.solve_triangular(L, torch.tril(q_sq), upper=False)
+    return _GaussKL.apply(qm, q_sq)
 
 
 # ------------------------------------------------------------------------------------------------------------------

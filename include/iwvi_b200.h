@@ -282,6 +282,12 @@ int iwvi_adam_step_counter(double* x, const double* grad_elbo, double* m, double
                            double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1, double beta2,
                            double eps, int64_t* state, void* stream);
 
+/* ---- measurement utility (no reference counterpart) ----
+ * Register-only mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) issue loop: blocks x warps warps, 8 independent accumulator pairs
+ * each, `iters` iterations -> 2*256*8*iters*warps*blocks flops.  bench.py times it with CUDA events to state the FP64
+ * tensor-pipe roofline denominator from the run itself.  out: blocks*warps*32 doubles (written, never read). */
+int iwvi_probe_dmma(double* out, int32_t blocks, int32_t warps, int32_t iters, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

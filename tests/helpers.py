@@ -83,3 +83,32 @@ def assert_grads_close(got, want, rtol, label=''):
         scale = max(np.abs(w).max(), 1e-12)
         err = np.abs(g - w).max() / scale
         assert err < rtol, '%s grad %s: max err / max|ref| = %.3e' % (label, k, err)
+
+
+def grad_report(got, want, rtol=1e-8, atol_rel=1e-12):
+    """Per gradient tensor: the normwise error max|got - want| / max|want| AND the elementwise check north_star words
+    as "gradients within rtol 1e-8": |got - want| <= rtol |want| + atol_rel max|want| entry by entry (the absolute floor
+    is what float64 summation over thousands of points leaves on entries many orders below the tensor's largest).
+    Returns {name: dict(normwise, n, n_fail, worst (largest |err| / allowed), worst_index)}."""
+    got = {canon(k): np.asarray(v) for k, v in got.items()}
+    out = {}
+    for k, w in want.items():
+        w = np.asarray(w, dtype=np.float64)
+        g = got[k].reshape(w.shape)
+        scale = max(np.abs(w).max(), 1e-300) if w.size else 1.0
+        err = np.abs(g - w)
+        allowed = rtol * np.abs(w) + atol_rel * scale
+        ratio = err / allowed
+        i = int(np.argmax(ratio)) if w.size else 0
+        out[k] = dict(normwise=float(err.max() / scale) if w.size else 0.0, n=int(w.size),
+                      n_fail=int((ratio > 1.0).sum()), worst=float(ratio.reshape(-1)[i]) if w.size else 0.0,
+                      worst_index=i, max_abs=float(scale))
+    return out
+
+
+def assert_grads_close_elementwise(got, want, rtol=1e-8, atol_rel=1e-12, label=''):
+    rep = grad_report(got, want, rtol, atol_rel)
+    bad = {k: v for k, v in rep.items() if v['n_fail']}
+    assert not bad, '%s: entries outside rtol %.0e + %.0e max|ref|: %s' % (
+        label, rtol, atol_rel, {k: (v['n_fail'], v['n'], '%.2fx' % v['worst']) for k, v in bad.items()})
+    return rep

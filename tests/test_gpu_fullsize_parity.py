@@ -1,0 +1,67 @@
+"""CUDA path against the oracle AT BASELINE.json's own sizes (not only at toy shapes): the full c2 and c3 minibatches,
+the c5 shape (D=8 `L1_G5_G5`) and a 32-row slice of c4 (M=512, K=256 -- every per-point quantity of c4 at full M and K;
+the oracle's materialised [B,R,M,K] tensors bound the row count).  ELBO within rtol 1e-8; every gradient tensor both
+normwise (max|err| / max|ref| < 1e-8) and ELEMENTWISE (|err| <= 1e-8 |ref| + 1e-12 max|ref|, entry by entry --
+north_star's "gradients within rtol 1e-8" with the absolute floor float64 summation over 25 600 points leaves).
+The oracle evaluates these in 0.1-3 s on the host.  A report of every tensor's figures is written to
+gpurun_out/parity_fullsize_<case>.json (committed copies: profiles/parity_fullsize_r02.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import iwvi_oracle as O
+from oracle import synthetic as S
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+ATOL_REL = 1e-12
+
+CASES = {
+    # name: (BASELINE config, rows, inner q_sqrt scale).  1e-5 is the reference's initialisation (build_models.py:275-278)
+    'c2_full': ('c2', 512, 1e-5),
+    'c2_full_wide_q': ('c2', 512, 0.3),
+    'c3_full': ('c3', 512, 1e-5),
+    'c3_full_wide_q': ('c3', 512, 0.3),
+    'c5_shape_full': ('c5', 512, 1e-5),
+    'c4_slice32': ('c4', 32, 1e-5),
+    'c1_full': ('c1', 200, 1e-5),
+}
+
+
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_fullsize_oracle_parity(case):
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    cname, B, qs = CASES[case]
+    c = S.CONFIGS[cname]
+    Nd = min(c['N'], 20000)                               # rows beyond the minibatch only feed Z / the SVD of make_spec
+    if cname == 'c1':
+        X, Y = S.demo_data(seed=0)
+    else:
+        X, Y = S.make_data(Nd, c['D'], seed=0)
+    spec = S.make_spec(X, c['configuration'], c['M'], c['K'], lik_variance=c['lik_variance'], seed=0, perturb=0.1,
+                       inner_q_sqrt_scale=qs)
+    spec['num_data'] = c['N']
+    K = c['K']
+    Xb, Yb = X[:B], Y[:B]
+    eps = S.make_noise(spec, (B, K), seed=1)
+    e_ref, g_ref = O.iw_elbo_and_grads(spec, Xb, Yb, eps, reference_style=True)
+    e_ref = e_ref.item()
+    want = {k: v.numpy() for k, v in g_ref.items()}
+    m = model_from_spec(spec, X, Y)
+    e, g = m.compute_log_likelihood_and_grads(Xb, Yb, eps)
+    rep = H.grad_report(g, want, RTOL, ATOL_REL)
+    out = dict(case=case, config=cname, rows=B, K=K, M=c['M'], inner_q_sqrt_scale=qs, elbo=e, elbo_oracle=e_ref,
+               elbo_rel_err=abs(e - e_ref) / abs(e_ref), rtol=RTOL, atol_rel=ATOL_REL, tensors=rep)
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, 'parity_fullsize_%s.json' % case), 'w') as f:
+            json.dump(out, f, indent=1)
+    except OSError:
+        pass
+    assert abs(e - e_ref) < RTOL * abs(e_ref), (e, e_ref)
+    H.assert_grads_close(g, want, RTOL, case)
+    H.assert_grads_close_elementwise(g, want, RTOL, ATOL_REL, case)

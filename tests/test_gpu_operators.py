@@ -84,8 +84,22 @@ def test_gauss_kl_operator():
     k = tw.gauss_kl(ag, bg)
     (2.5 * k).backward()
     close('kl', k, ko); close('dq_mu', ag.grad, 2.5 * a.grad); close('dq_sqrt', bg.grad, 2.5 * torch.tril(b.grad))
-    with pytest.raises(NotImplementedError):
-        tw.gauss_kl(ag, bg, K=torch.eye(M, dtype=torch.float64).cuda())   # only the whitened KL is on the path
+    # K given (unwhitened prior N(0, K), temp_workaround.py:188 -> gpflow gauss_kl(q_mu, q_sqrt, K)): the textbook form
+    A = rng.standard_normal((M, M)); Kp = A @ A.T / M + np.eye(M)
+    ag2, bg2 = T64(q_mu).cuda().requires_grad_(True), T64(q_sqrt).cuda().requires_grad_(True)
+    k2 = tw.gauss_kl(ag2, bg2, K=T64(Kp).cuda())
+    want = 0.0
+    Ki = np.linalg.inv(Kp)
+    for r in range(R):
+        Sr = np.tril(q_sqrt[r]) @ np.tril(q_sqrt[r]).T
+        want += 0.5 * (np.trace(Ki @ Sr) + q_mu[:, r] @ Ki @ q_mu[:, r] - M + np.linalg.slogdet(Kp)[1]
+                       - np.linalg.slogdet(Sr)[1])
+    assert abs(k2.item() - want) < 1e-9 * abs(want)
+    k2.backward()
+    close('dq_mu (K)', ag2.grad, T64(Ki @ q_mu), rtol=1e-7)
+    # q_sqrt = None (:174-184): minus the log density of q_mu under N(0, K + jitter I)
+    k3 = tw.gauss_kl(T64(q_mu).cuda(), None, K=T64(Kp).cuda())
+    close('nlp (K)', k3, O.gauss_kl(T64(q_mu), None, K=T64(Kp)))
 
 
 @pytest.mark.parametrize('sampled,amortised', [(True, True), (False, True), (True, False)])
@@ -162,9 +176,6 @@ def test_full_cov_branch_and_predict_f_full_cov():
     with pytest.raises(NotImplementedError):
         tw.multisample_sample_conditional(T64(F2).cuda(), layer.feature, layer.kern, layer.q_mu, full_cov=True,
                                           q_sqrt=layer.q_sqrt, white=True)
-    with pytest.raises(NotImplementedError):
-        tw.multisample_sample_conditional(T64(F).cuda(), layer.feature, layer.kern, layer.q_mu, q_sqrt=layer.q_sqrt,
-                                          white=False)
 
 
 @pytest.mark.parametrize('form', ['none', 'diag'])
@@ -278,3 +289,89 @@ def test_full_cov_joint_draw_autograd(conf, which, kern, S_, N):
     if not mok:
         close('dA', layer.mean_function.A.unconstrained.grad, leaves[pre + 'mf.A'].grad)
         close('db', layer.mean_function.b.unconstrained.grad, leaves[pre + 'mf.b'].grad)
+
+
+@pytest.mark.parametrize('conf,which,kern,form', [('L1_G3', 1, 'RBF', 'full'), ('G2', 0, 'Matern52', 'full'),
+                                                  ('L1_G3', 2, 'RBF', 'diag'), ('G2', 0, 'RBF', 'none')])
+def test_conditional_unwhitened(conf, which, kern, form):
+    """white=False (reference temp_workaround.py:63-65: A <- Lm^-T A before the mean and the q_sqrt projection), values
+    and every gradient -- including the extra dependence on Z / lengthscales / variance through Lm -- against the oracle."""
+    from dgps_with_iwvi_b200 import temp_workaround as tw
+    layer, ol, leaves, pre = _layer_pair(conf, 4, 45, kern=kern, which=which)
+    Din = ol.Z.shape[1]
+    rng = np.random.default_rng(9)
+    Sn, N = 3, 11
+    M, R = ol.q_mu.shape
+    F = rng.standard_normal((Sn, N, Din)); eps = rng.standard_normal((Sn, N, R))
+    if form == 'full':
+        qo, qg = ol.q_sqrt, layer.q_sqrt
+    elif form == 'diag':
+        qd = np.abs(rng.standard_normal((M, R))) + 0.2
+        qo, qg = T64(qd).requires_grad_(True), T64(qd).cuda().requires_grad_(True)
+    else:
+        qo = qg = None
+    for _, p in layer.named_parameters():
+        p.unconstrained.requires_grad_(True)
+    Fo = T64(F).requires_grad_(True)
+    so, mo, vo = O.multisample_sample_conditional(Fo, ol.Z, ol.kern, ol.q_mu, q_sqrt=qo, white=False, eps=T64(eps))
+    Fg = T64(F).cuda().requires_grad_(True)
+    s, m, v = tw.multisample_sample_conditional(Fg, layer.feature, layer.kern, layer.q_mu, q_sqrt=qg, white=False,
+                                                eps=T64(eps).cuda(), jitter=layer.jitter)
+    close('sample', s, so); close('mean', m, mo); close('var', v, vo)
+    cs, cm, cv = [T64(rng.standard_normal(so.shape)) for _ in range(3)]
+    (so * cs).sum().add((mo * cm).sum()).add((vo * cv).sum()).backward()
+    (s * cs.cuda()).sum().add((m * cm.cuda()).sum()).add((v * cv.cuda()).sum()).backward()
+    mix = hasattr(layer.kern, 'W')
+    base = layer.kern.kernel if mix else layer.kern
+    feat = layer.feature.feat if hasattr(layer.feature, 'feat') else layer.feature
+    sig = lambda p: torch.sigmoid(p.unconstrained.detach())
+    close('dF', Fg.grad, Fo.grad)
+    close('dZ', feat.Z.unconstrained.grad, leaves[pre + 'Z'].grad)
+    close('dq_mu', layer.q_mu.unconstrained.grad, leaves[pre + 'q_mu'].grad)
+    close('dls', base.lengthscales.unconstrained.grad / sig(base.lengthscales), leaves[pre + 'kern.lengthscales'].grad)
+    close('dvariance', base.variance.unconstrained.grad / sig(base.variance), leaves[pre + 'kern.variance'].grad)
+    if form == 'full':
+        close('dq_sqrt', layer.q_sqrt.unconstrained.grad, torch.tril(leaves[pre + 'q_sqrt'].grad))
+    elif form == 'diag':
+        close('dq_sqrt', qg.grad, qo.grad)
+
+
+def test_model_propagate_matches_oracle_layer_loop():
+    """DGP_VI.propagate (reference models.py:30-46): (samples, means, covs, kls, kl_types), one entry per layer, on the
+    IW layout [N, K, .] with the sampled local regulariser and on the prediction layout (no amortisation inputs),
+    against oracle.DGP.propagate; gradient of a scalar of the outputs w.r.t. a first-layer parameter through autograd."""
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    from dgps_with_iwvi_b200.layers import RegularizerType
+    N, D, M, K = 9, 3, 20, 4
+    X, Y = S.make_data(40, D, seed=13)
+    spec = S.make_spec(X, 'L1_G3_G2', M, K, seed=13, perturb=0.3, inner_q_sqrt_scale=0.3)
+    model = model_from_spec(spec, X, Y)
+    omodel, leaves = O.build_from_spec(spec, requires_grad=True)
+    eps = S.make_noise(spec, (N, K), seed=14, final_noise=True)
+    Xt = np.repeat(X[:N, None, :], K, 1); XY = np.concatenate([Xt, np.repeat(Y[:N, None, :], K, 1)], -1)
+    outs_o = omodel.propagate(T64(Xt), [T64(e) for e in eps], inference_amorization_inputs=T64(XY),
+                              is_sampled_local_regularizer=True)
+    model.requires_grad_()
+    outs = model.propagate(Xt, inference_amorization_inputs=T64(XY).cuda(), is_sampled_local_regularizer=True,
+                           eps=[T64(e).cuda() for e in eps])
+    assert len(outs) == 5 and [len(o) for o in outs] == [4] * 5
+    for name, got, want in zip(['samples', 'means', 'covs', 'kls'], outs[:4], outs_o[:4]):
+        for i, (a, b) in enumerate(zip(got, want)):
+            close('%s[%d]' % (name, i), a, b)
+    assert outs[4] == [RegularizerType.LOCAL] + [RegularizerType.GLOBAL] * 3
+    assert [t == O.LOCAL for t in outs_o[4]] == [t is RegularizerType.LOCAL for t in outs[4]]
+    c = T64(np.random.default_rng(15).standard_normal(outs_o[1][-1].shape))
+    (outs_o[1][-1] * c).sum().add(outs_o[0][1].sum()).backward()
+    (outs[1][-1] * c.cuda()).sum().add(outs[0][1].sum()).backward()
+    close('dW0', model.layers[0].encoder.Ws[0].unconstrained.grad, leaves['layers.0.encoder.Ws.0'].grad)
+    close('dZ1', model.layers[1].feature.feat.Z.unconstrained.grad, leaves['layers.1.Z'].grad)
+    # prediction layout [S, N, .]: LV layers sample from the prior (layers.py:73-81), closed-form KL
+    Sn = 5
+    eps_p = S.make_noise(spec, (Sn, N), seed=16, final_noise=True)
+    Xp = np.repeat(X[None, :N, :], Sn, 0)
+    with torch.no_grad():
+        po = omodel.propagate(T64(Xp), [T64(e) for e in eps_p])
+        pg = model.propagate(Xp, eps=[T64(e).cuda() for e in eps_p])
+    for name, got, want in zip(['samples', 'means', 'covs', 'kls'], pg[:4], po[:4]):
+        for i, (a, b) in enumerate(zip(got, want)):
+            close('predict %s[%d]' % (name, i), a, b)

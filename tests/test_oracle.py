@@ -276,3 +276,60 @@ def test_joint_draw_reduces_to_diagonal_draw():
                                                               white=True, eps_joint=z)
     L = torch.linalg.cholesky(vj)
     assert torch.allclose((sj - mj).transpose(1, 2)[..., None], L @ z[..., None], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize('conf,kern,N,D,M,K', [('L1_G3_G2', 'RBF', 5, 3, 11, 4), ('L2_G2', 'Matern52', 4, 2, 9, 3),
+                                               ('G2_L1_G3', 'Matern32', 3, 2, 8, 5), ('L1', 'RBF', 6, 1, 7, 4)])
+def test_iw_bound_against_pointwise_scipy_loop(conf, kern, N, D, M, K):
+    """Second, structurally independent IW bound (oracle/iw_pointwise_np.py: a Python loop over every (n, k) with the
+    unwhitened textbook posterior, scipy.stats.norm.logpdf densities and scipy logsumexp) against the op-for-op oracle:
+    pins the [N, K] tiling (models.py:113-116), the sampled local regulariser (layers.py:98-100), Mok mixing, the
+    mean-function adds and reduce_logsumexp - log K (models.py:148) -- the IW-specific lines no reference test pins."""
+    from oracle import iw_pointwise_np as PW
+    X, Y = S.make_data(N, D, seed=5)
+    spec = S.make_spec(X, conf, M, K, seed=5, perturb=0.3, inner_q_sqrt_scale=0.3, kern=kern, lik_variance=0.05)
+    spec['num_data'] = 37                                     # scale = num_data / N != 1
+    eps = S.make_noise(spec, (N, K), seed=6)
+    model, _ = O.build_from_spec(spec)
+    want, parts = model.iw_likelihood(T(X), T(Y), [None if e is None else T(e) for e in eps], reference_style=True,
+                                      return_parts=True)
+    got, L_NK = PW.iw_bound(spec, X, Y, eps)
+    # the explicit Kuu^-1 of the unwhitened form costs a few digits (cond(Kuu) ~ 1e6 with jitter 1e-6)
+    np.testing.assert_allclose(L_NK, parts['L_NK'].numpy(), rtol=1e-7, atol=1e-7)
+    assert abs(got - want.item()) < 1e-7 * abs(want.item())
+
+
+def test_adam_oracle_against_torch_optim():
+    """Pins oracle/adam_oracle.py (TF AdamOptimizer on GPflow's unconstrained variables, build_models.py:289-295) against
+    torch.optim.Adam driving the same objective through autograd on softplus(x) + 1e-6.  torch puts epsilon inside the
+    bias-corrected denominator (sqrt(v / bc2) + eps) where TF uses sqrt(v) + eps ("epsilon hat"): identical for eps = 0,
+    and within eps-sized relative differences otherwise."""
+    from oracle import adam_oracle as AO
+    rng = np.random.default_rng(3)
+    n, n_pos = 12, 5
+    x0 = rng.standard_normal(n)
+    A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n)
+    c = rng.standard_normal(n)
+
+    def elbo_and_grad(theta):          # a concave quadratic "ELBO" of the CONSTRAINED values
+        return -0.5 * theta @ A @ theta + c @ theta, -A @ theta + c
+
+    for eps, tol in ((0.0, 1e-13), (1e-8, 1e-6)):
+        xt = torch.tensor(x0, requires_grad=True)
+        opt = torch.optim.Adam([xt], lr=1.0, betas=(0.9, 0.999), eps=eps)
+        x, m, v = x0.copy(), np.zeros(n), np.zeros(n)
+        for t in range(998, 1003):     # crosses the staircase boundary at global_step 1000
+            lr = AO.staircase_decay(5e-3, t, 1000, 0.98)
+            theta = np.concatenate([AO.positive_forward(x[:n_pos]), x[n_pos:]])
+            _, g = elbo_and_grad(theta)
+            x, m, v = AO.adam_step(x, g, m, v, t - 997, lr, n_pos, eps=eps)
+            for grp in opt.param_groups:
+                grp['lr'] = lr
+            opt.zero_grad()
+            th = torch.cat([torch.nn.functional.softplus(xt[:n_pos]) + 1e-6, xt[n_pos:]])
+            loss = 0.5 * th @ T(A) @ th - T(c) @ th
+            loss.backward()
+            opt.step()
+            np.testing.assert_allclose(x, xt.detach().numpy(), rtol=tol, atol=tol)
+    assert AO.staircase_decay(1.0, 999) == 1.0 and AO.staircase_decay(1.0, 1000) == 0.98 and \
+        abs(AO.staircase_decay(1.0, 2000) - 0.98 ** 2) < 1e-16
