@@ -110,6 +110,7 @@ struct BwdParams {
   BwdWs wl;
   int ntiles, grid_tile;
   int q_lo;      // reduce kernel: first matrix index of this launch (0 .. R; R == dLm)
+  int q_n;       // reduce kernel: number of matrices of this launch
   int fin_part;  // finalize kernel: 0 = everything, 1 = part A outputs, 2 = part B outputs
 };
 
@@ -924,11 +925,15 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // decode the work item
-  int item = blockIdx.x + p.q_lo * wl.S * wl.npairs;
+  // decode the work item.  Rasterisation: the block pair runs fastest, then the matrix q, the point range s slowest, so
+  // that the CTAs resident at any time (blockIdx order) all stream the SAME range of points: a 64-point chunk of A, U_r
+  // or Bbar is then fetched from DRAM once and served to the other (up to 2 NB (R+1)) readers of it from L2.  With q
+  // slowest (round 1) a wave held the ranges of 2-3 matrices only and A was streamed from DRAM once per wave
+  // (652 MB per launch against 390 MB of operands at c3, ncu).
+  int item = blockIdx.x;
   const int pair = item % wl.npairs; item /= wl.npairs;
-  const int s = item % wl.S;
-  const int q = item / wl.S;                                     // q < R: dLq_q ; q == R: dLm
+  const int q = p.q_lo + item % p.q_n;                           // q < R: dLq_q ; q == R: dLm
+  const int s = item / p.q_n;
   int bi = 0, acc_pairs = 0;
   while (acc_pairs + bi + 1 <= pair) { acc_pairs += bi + 1; bi++; }
   const int bj = pair - acc_pairs;                               // bj <= bi
@@ -1199,7 +1204,7 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
   cudaStream_t st = (cudaStream_t)stream;
   const int only = d->flags & IWVI_FLAG_ONLY_MASK;
-  p.q_lo = 0; p.fin_part = 0;
+  p.q_lo = 0; p.q_n = d->R + 1; p.fin_part = 0;
 
   if (!only || (only & IWVI_FLAG_ONLY_EPI)) {
     gp_epi_bwd_kernel<<<p.wl.n_epi, 256, 0, st>>>(p);
@@ -1223,6 +1228,7 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
     const int per_q = p.wl.S * p.wl.npairs;
     p.q_lo = (do_a && !do_b) ? d->R : 0;
     const int nq = (do_a && do_b) ? d->R + 1 : (do_a ? 1 : d->R);
+    p.q_n = nq;
     gp_reduce_bwd_kernel<<<nq * per_q, RED_THREADS, red_smem, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
