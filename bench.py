@@ -472,8 +472,7 @@ def main():
     dp_parity = dp_parity_check(trainer, model, Xd, Yd, B, K, world, rank, torch, dist) if world > 1 else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown(trainer, world, torch, dist)
         return
 
     # ---- per-kernel timing of the three DMMA kernels of one GP layer (CUDA events on the launching stream) ----
@@ -538,8 +537,25 @@ def main():
     if world == 1 and not args.no_reference_iteration:
         out['reference_iteration'] = reference_iteration_timing(cfg, X, Y, torch)
     emit(out)
-    if world > 1:
+    teardown(trainer, world, torch, dist)
+
+
+def teardown(trainer, world, torch, dist):
+    """Leaves the process group in order.  The step graph holds captured NCCL kernels: it is released before the
+    communicator is destroyed, and because a rank may wait in ncclCommDestroy for a peer that is still measuring (rank 0
+    times kernels after the other ranks are done), a watchdog ends the process -- the JSON line is already out -- if the
+    teardown has not finished within 20 s."""
+    if world <= 1:
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    trainer._graphs = None
+    torch.cuda.synchronize()
+    try:
         dist.destroy_process_group()
+    finally:
+        os._exit(0)
 
 
 def dp_parity_check(trainer, model, Xd, Yd, B, K, world, rank, torch, dist):

@@ -241,19 +241,20 @@ struct BwdSeq {
   int64_t u_stride;
   int64_t tile_off;   // offset of this tile's rows inside block 0 of its 64-point chunk (block-major saved arrays)
   int ph, r, i, j;
+  bool a_turn;        // first block column of r == 0 only: the saved A block i goes ahead of tril(q_sqrt_0) block (i, 0)
   __device__ __forceinline__ void init(int n0) {
-    ph = -1; r = 0; i = 0; j = 0;
+    ph = 0; r = 0; i = -1; j = 0; a_turn = false;
     tile_off = (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
   }
   __device__ __forceinline__ bool done() const { return ph == 3; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
     b.bytes = IWVI_STAGE_DOUBLES * 8;
-    if (ph == -1) {          // saved A, m-block i, rows of this tile (contiguous)
-      b.src = A_T + tile_off + (int64_t)i * IWVI_STAGE_DOUBLES; b.bytes = (uint32_t)tp_bytes;
-    } else if (ph == 0) {
+    if (ph == 0) {
       if (i < j) {           // saved U_r, m-block j, rows of this tile
         b.src = U_T + (int64_t)r * u_stride + tile_off + (int64_t)j * IWVI_STAGE_DOUBLES; b.bytes = (uint32_t)tp_bytes;
+      } else if (a_turn) {   // saved A, m-block i, rows of this tile (contiguous)
+        b.src = A_T + tile_off + (int64_t)i * IWVI_STAGE_DOUBLES; b.bytes = (uint32_t)tp_bytes;
       } else {               // tril(q_sqrt_r) block (row block i, col block j), i >= j
         b.src = Lqb + ((size_t)r * npairs + iwvi_pair(i, j)) * IWVI_STAGE_DOUBLES;
       }
@@ -265,10 +266,10 @@ struct BwdSeq {
     return b;
   }
   __device__ __forceinline__ void advance() {
-    if (ph == -1) {
-      if (++i == NB) { ph = 0; r = 0; j = 0; i = -1; }
-    } else if (ph == 0) {
+    if (ph == 0) {
+      if (a_turn) { a_turn = false; return; }
       if (++i == NB) { ++j; i = j - 1; if (j == NB) { ++r; j = 0; i = -1; if (r == R) { ph = 1; i = NB - 1; j = NB; } } }
+      a_turn = (ph == 0 && r == 0 && j == 0 && i >= 0);
     } else if (ph == 1) {
       if (j < NB) ++j;
       else { --i; j = i + 1; if (i < 0) { ph = 2; i = 0; } }
@@ -470,31 +471,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     named_bar_sync(BAR_ALL, 256);
     PHASE_MARK(0);
 
-    // ---- Abar / 2, part 1: (q_mu gmean_bar^T) / 2 - A gsum.  (The factor 2 of part 2 is exact in binary floating
-    //      point, so the panel carries Abar / 2 until the back substitution writes 2 x its result.)  The saved A arrives block by block through the ring (the
-    //      producer warp prefetches it while the previous tile finishes), never through synchronous global loads.
-    {
-      const int mm = tid & 63;          // this thread's inducing index inside every block; its points: tid/64 + 4*q
-      for (int mb = 0; mb < NB; mb++) {
-        const double* q = qmu + (size_t)(mb * IWVI_BLK + mm) * IWVI_MAX_R;
-        double qr[IWVI_MAX_R];
-#pragma unroll
-        for (int r = 0; r < IWVI_MAX_R; r++) qr[r] = q[r];
-        const double* st = pipe.wait();
-        for (int n = tid >> 6; n < TP; n += 4) {
-          double v = 0.0;
-#pragma unroll
-          for (int r = 0; r < IWVI_MAX_R; r++) v += qr[r] * gmb_s[r * TP + n];
-          panel[mb * PSTR + n * IWVI_LDS + mm] = 0.5 * v - st[n * IWVI_LDS + mm] * gsum_s[n];   // Abar / 2
-        }
-        pipe.release(lane);
-      }
-    }
-    named_bar_sync(BAR_ALL, 256);
     PHASE_MARK(1);
 
-    // ---- Abar, part 2: += 2 tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register B-fragments per k-block j
-    //      (the saved U_r block comes through the ring too, ahead of the tril(q_sqrt) blocks that multiply it)
+    // ---- Abar / 2 = (q_mu gmean_bar^T) / 2 - A gsum  +  sum_r tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register
+    //      B-fragments per k-block j (the saved U_r block comes through the ring, ahead of the tril(q_sqrt) blocks that
+    //      multiply it).  The factor 2 of the second term is exact in binary floating point, so the panel carries Abar / 2
+    //      until it is restored where Bbar is consumed.  The first term is never written on its own: every thread forms
+    //      it for the accumulator entries it owns when block row i is first touched (r == 0, j == 0), from the saved A block
+    //      that the producer warp slots into the ring right before tril(q_sqrt_0) block (i, 0) -- its latency hides behind
+    //      the previous product instead of being exposed in a streaming pass of its own, and the panel is neither
+    //      written nor re-read for it.
     for (int r = 0; r < R; r++) {
       for (int j = 0; j < NB; j++) {
         double vb[16][2];
@@ -513,13 +499,48 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         for (int i = j; i < NB; i++) {
           // the accumulators start from this thread's own panel entries (exclusive owner): no read-modify-write pass
           double acc[C::TM][2][2];
+          if (r == 0 && j == 0) {
+            // (q_mu gmean_bar^T) first, r outermost so that only the accumulators stay live (q_mu in aux is padded to
+            // [Mp, 8], gmean_bar to 8 columns, zeros beyond R / M); then the saved A block, which by now has arrived
+            acc_zero<C::TM, 2>(acc);
 #pragma unroll
-          for (int a_ = 0; a_ < C::TM; a_++)
+            for (int rr = 0; rr < IWVI_MAX_R; rr++) {
+              double qa[C::TM], gb[2][2];
+#pragma unroll
+              for (int a_ = 0; a_ < C::TM; a_++)
+                qa[a_] = __ldg(qmu + (size_t)(i * IWVI_BLK + wr0 + a_ * MR + g) * IWVI_MAX_R + rr);
+#pragma unroll
+              for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) gb[b][c] = gmb_s[rr * TP + wn0 + b * 8 + 2 * t + c];
+#pragma unroll
+              for (int a_ = 0; a_ < C::TM; a_++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                  for (int c = 0; c < 2; c++) acc[a_][b][c] += qa[a_] * gb[b][c];
+            }
+            const double* sa = pipe.wait();   // saved A, m-block i: sa[n * IWVI_LDS + m]
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
-              for (int c = 0; c < 2; c++)
-                acc[a_][b][c] = panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a_ * MR + g];
+              for (int c = 0; c < 2; c++) {
+                const int n = wn0 + b * 8 + 2 * t + c;
+                const double gs_n = gsum_s[n];
+#pragma unroll
+                for (int a_ = 0; a_ < C::TM; a_++)
+                  acc[a_][b][c] = 0.5 * acc[a_][b][c] - sa[n * IWVI_LDS + wr0 + a_ * MR + g] * gs_n;   // Abar / 2, first term
+              }
+            pipe.release(lane);
+          } else {
+#pragma unroll
+            for (int a_ = 0; a_ < C::TM; a_++)
+#pragma unroll
+              for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+                  acc[a_][b][c] = panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a_ * MR + g];
+          }
           const double* st = pipe.wait();
           const double* ap = st + (wr0 + g) * IWVI_LDS + t;
           if (i == j) {   // diagonal block of tril(q_sqrt_r): the structural zeros are skipped (compile-time pattern per wmi)

@@ -230,6 +230,10 @@ class Engine:
         self.ev_part_b = torch.cuda.Event()
         self.ev_elbo, self.ev_loss = torch.cuda.Event(), torch.cuda.Event()
         self._loss_pending = False
+        # data-parallel training: called as grad_hook(tag) on the stream where the gradients named by `tag` have just been
+        # completed -- ('gp', gi): every parameter of GP layer gi > 0; ('gp_q', 0): q_mu / q_sqrt of the first GP layer --
+        # so that their all-reduce overlaps with the rest of the backward pass (training.Trainer); None: no hook
+        self.grad_hook = None
         self.X_tiled = None
         if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
             self.X_tiled = z(T, self.Dx)
@@ -446,6 +450,8 @@ class Engine:
                     with torch.cuda.stream(self.side_b):
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_B), *args)
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_ONLY_KL), *pargs)
+                        if self.grad_hook is not None:
+                            self.grad_hook(('gp_q', 0))
                         self.ev_part_b.record(self.side_b)
                 else:
                     with torch.cuda.stream(side):
@@ -453,6 +459,8 @@ class Engine:
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), *pargs)
                         if not r['ard']:
                             torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                        if self.grad_hook is not None:
+                            self.grad_hook(('gp', gi))
                         self.ev_pbwd[gi].record(side)
                 d_next = r['dX']
             else:

@@ -25,14 +25,18 @@ def staircase_decay(base, step, decay_steps=1000, rate=0.98):
 
 
 class GradBucket:
-    """The exchange step of data-parallel training: ONE all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) of
-    the PACKED gradient bucket.  What crosses the wire: trainable entries only (frozen W / mean-function / kernel-variance
+    """The exchange step of data-parallel training: all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) of the
+    PACKED gradient bucket.  What crosses the wire: trainable entries only (frozen W / mean-function / kernel-variance
     slots never form a gradient, build_models.py:209,213,225-227); of every LowerTriangular parameter only the lower
     triangle (GPflow stores q_sqrt packed; the strict upper triangle of the dense [R, M, M] storage gets an exactly-zero
     gradient); `always_reduce` parameters whatever their flag (the NatGrad half needs the last layer's q_mu / q_sqrt
-    gradients, which Adam's mask excludes); and the ELBO slot.  At c3: 0.37 M doubles instead of the dense 0.74 M."""
+    gradients, which Adam's mask excludes); and the ELBO slot.  At c3: 0.37 M doubles instead of the dense 0.74 M.
 
-    def __init__(self, flat, always_reduce=(), process_group=None):
+    `groups` = [(tag, [parameters])]: the packed buffer is laid out segment by segment in that order, the remaining
+    parameters and the ELBO slot last (tag 'final'), so that a segment can be all-reduced on its own as soon as the backward
+    pass has completed it (allreduce(tag)) -- or the whole bucket in one call (allreduce())."""
+
+    def __init__(self, flat, always_reduce=(), process_group=None, groups=()):
         from .params import LowerTriangular
         self.flat, self.pg = flat, process_group
         flat.refresh_mask()
@@ -45,29 +49,53 @@ class GradBucket:
                 _, o, sz, shape, _ = flat.entries[id(p)]
                 tri = torch.ones(shape[-2:], dtype=torch.bool, device=flat.device).tril().expand(shape).reshape(-1)
                 keep[o:o + sz] &= tri
-        idx = torch.nonzero(keep).flatten()
-        self.index = torch.cat([idx, torch.tensor([flat.n], dtype=idx.dtype, device=flat.device)]).contiguous()
+        seg_of = torch.full((flat.n,), len(groups), dtype=torch.int64, device=flat.device)     # default: 'final'
+        for gi, (_, params) in enumerate(groups):
+            for p in params:
+                _, o, sz, _, _ = flat.entries[id(p)]
+                seg_of[o:o + sz] = gi
+        parts, self.segments, off = [], {}, 0
+        for gi, tag in enumerate([t for t, _ in groups] + ['final']):
+            idx = torch.nonzero(keep & (seg_of == gi)).flatten()
+            if tag == 'final':
+                idx = torch.cat([idx, torch.tensor([flat.n], dtype=idx.dtype, device=flat.device)])
+            parts.append(idx)
+            self.segments[tag] = (off, off + idx.numel())
+            off += idx.numel()
+        self.index = torch.cat(parts).contiguous()
         self.buf = torch.zeros(self.index.numel(), dtype=torch.float64, device=flat.device)
 
-    def allreduce(self):
-        """pack -> all_reduce(SUM) -> unpack, in stream order on the current stream."""
-        g = self.flat.g
-        torch.index_select(g, 0, self.index, out=self.buf)
-        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.pg)
-        g.index_copy_(0, self.index, self.buf)
+    def allreduce(self, tag=None):
+        """pack -> all_reduce(SUM) -> unpack of one segment (or of the whole bucket), in stream order on the current
+        stream."""
+        a, b = (0, self.index.numel()) if tag is None else self.segments[tag]
+        if a == b:
+            return
+        g, idx, buf = self.flat.g, self.index[a:b], self.buf[a:b]
+        torch.index_select(g, 0, idx, out=buf)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+        g.index_copy_(0, idx, buf)
 
 
 class Trainer:
-    """use_graph=True (default): after two eager steps the whole step -- noise, forward, backward, optimiser -- is
-    captured ONCE as a CUDA graph and replayed; the step count and learning rate live in device memory
+    """use_graph=True (default): after two eager steps the whole step -- noise, forward, backward, gradient exchange,
+    optimiser -- is captured ONCE as a CUDA graph and replayed; the step count and learning rate live in device memory
     (iwvi_normal_fill_counter / iwvi_adam_step_counter) so every replay draws fresh noise and applies the right bias
-    correction.  With several ranks the NCCL all-reduce stays an eager call between two graphs."""
+    correction.
+
+    Several ranks: the packed gradient bucket is exchanged in segments, each all-reduced (NCCL) on the side stream that
+    completed it while the backward pass of the layers below is still running (overlap_comm): the upper GP layers as
+    soon as their Cholesky / gram adjoints are done, the first GP layer's q_mu / q_sqrt while its own adjoint chain runs;
+    only the small remainder (first-layer Z / kernel parameters, encoder, likelihood variance, ELBO slot) is exchanged
+    after the backward pass.  The NCCL calls are captured into the step graph (graph_comm); if the capture is refused
+    the all-reduce falls back to ONE eager call of the whole bucket between two graphs."""
 
     def __init__(self, model, B_local, lr=5e-3, lr_decay=0.98, beta1=0.9, beta2=0.999, eps=1e-8, seed=0,
-                 process_group=None, use_graph=True, always_reduce=None):
+                 process_group=None, use_graph=True, always_reduce=None, overlap_comm=True, graph_comm=True,
+                 distributed=None):
         self.model = model
         self.pg = process_group
-        self.distributed = dist.is_available() and dist.is_initialized()
+        self.distributed = (dist.is_available() and dist.is_initialized()) if distributed is None else bool(distributed)
         self.world_size = dist.get_world_size(process_group) if self.distributed else 1
         self.rank = dist.get_rank(process_group) if self.distributed else 0
         self.B_local = int(B_local)
@@ -76,6 +104,9 @@ class Trainer:
         self.flat.refresh_mask()
         self._trainable = tuple(p.trainable for p in self.flat.params)
         self.always_reduce = list(always_reduce or [])
+        self.graph_comm = bool(graph_comm)
+        # segments are issued from side streams inside the backward pass: with CUDA graphs that needs the capture
+        self.overlap_comm = bool(overlap_comm) and self.world_size > 1 and (self.graph_comm or not use_graph)
         self._build_bucket()
         self.m = torch.zeros_like(self.flat.x)
         self.v = torch.zeros_like(self.flat.x)
@@ -95,11 +126,27 @@ class Trainer:
 
     # ---- the exchange step: ONE all-reduce of the PACKED gradient bucket ----
     def _build_bucket(self):
-        self.gbucket = GradBucket(self.flat, self.always_reduce, self.pg)
+        groups = []
+        if self.overlap_comm:
+            gps = [r for r in self.engine.recs if r['type'] == 'gp']
+            for r in reversed(gps):                      # the order in which the backward pass completes them
+                layer, base, feat = r['layer'], r['base'], r['feat']
+                if r['gi'] == 0:
+                    groups.append((('gp_q', 0), [layer.q_mu, layer.q_sqrt]))
+                    continue
+                ps = [feat.Z, base.lengthscales, base.variance, layer.q_mu, layer.q_sqrt]
+                if r['mix']:
+                    ps.append(layer.kern.W)
+                if r['mf'] == 'Linear':
+                    ps += [layer.mean_function.A, layer.mean_function.b]
+                groups.append((('gp', r['gi']), ps))
+        self.gbucket = GradBucket(self.flat, self.always_reduce, self.pg, groups)
+        self.engine.grad_hook = self.gbucket.allreduce if self.overlap_comm else None
 
     def allreduce_grads(self):
+        """What is left to exchange after backward(): everything, or with overlap_comm the 'final' segment."""
         if self.world_size > 1:
-            self.gbucket.allreduce()
+            self.gbucket.allreduce('final' if self.overlap_comm else None)
 
     # ---- the two halves of a step, written against device-side state only (capturable) ----
     def _fwd_bwd(self, row0):
@@ -115,12 +162,35 @@ class Trainer:
     def _capture(self, row0):
         l0 = capi.LAUNCHES
         torch.cuda.synchronize()
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga):
-            self._fwd_bwd(row0)
-        with torch.cuda.graph(gb, pool=ga.pool()):
-            self._update()
-        self._graphs = (ga, gb)
+        self._graphs = None
+        if self.world_size == 1 or self.graph_comm:
+            # the whole step, exchange included, as ONE graph
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fwd_bwd(row0)
+                    self.allreduce_grads()
+                    self._update()
+                self._graphs = (g, None)
+            except RuntimeError as e:          # NCCL refused the capture: two graphs around an eager all-reduce
+                if self.world_size == 1:
+                    raise
+                import warnings
+                warnings.warn('dgps_with_iwvi_b200: NCCL all-reduce could not be captured into the step graph (%s); '
+                              'falling back to an eager all-reduce between two graphs' % str(e).splitlines()[0])
+                torch.cuda.synchronize()
+                self.graph_comm = False
+                if self.overlap_comm:          # segments issued from side streams need the capture: one bucket instead
+                    self.overlap_comm = False
+                    self._build_bucket()
+                capi.LAUNCHES = l0
+        if self._graphs is None:
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._fwd_bwd(row0)
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._update()
+            self._graphs = (ga, gb)
         self._graph_launches = capi.LAUNCHES - l0
         self._graph_row0 = row0
         capi.LAUNCHES = l0             # capture launched nothing; replays are counted in step_device
@@ -145,6 +215,10 @@ class Trainer:
         graph = self.use_graph and self.t > self.eager_steps_before_capture
         if graph and (self._graphs is None or self._graph_row0 != row0):
             self._capture(row0)
+        if graph and self._graphs[1] is None:          # one graph: noise, forward, backward, exchange, optimiser
+            self._graphs[0].replay()
+            capi.LAUNCHES += self._graph_launches
+            return self.flat.loss_slot
         if graph:
             self._graphs[0].replay()
         else:

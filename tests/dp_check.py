@@ -45,6 +45,39 @@ def main():
         print('dp%d vs single: bucket max err / max = %.3e, elbo rel err = %.3e' % (world, err, rel_elbo), flush=True)
         ok = err < 1e-10 and rel_elbo < 1e-12
     dist.barrier()
+    # ---- the Trainer's step: segmented all-reduce overlapped with the backward pass, captured into ONE CUDA graph (steps
+    #      3+), against a single-process Trainer fed the same global minibatches; and the eager one-bucket exchange
+    from dgps_with_iwvi_b200.training import Trainer
+    import warnings
+    B = (r1 - r0)
+    finals = {}
+    for mode in ('overlap_graph', 'one_bucket_two_graphs'):
+        m2 = build_model(X, Y, 'L1_G4_G3', M=M, num_IW_samples=K, minibatch_size=Bg, mode='IWAE', seed=3)
+        with warnings.catch_warnings():
+            warnings.simplefilter('error')            # a refused NCCL capture must not pass silently here
+            tr = Trainer(m2, B, lr=1e-2, seed=4, overlap_comm=(mode == 'overlap_graph'), graph_comm=(mode == 'overlap_graph'))
+            assert tr.overlap_comm == (mode == 'overlap_graph')
+            for i in range(6):
+                gi_ = np.random.default_rng(100 + i).permutation(N)[:Bg]
+                loss = tr.step_device(torch.as_tensor(X[gi_[r0:r1]]).cuda(), torch.as_tensor(Y[gi_[r0:r1]]).cuda())
+        torch.cuda.synchronize()
+        assert tr._graphs is not None and (tr._graphs[1] is None) == (mode == 'overlap_graph')
+        finals[mode] = (FlatParams.of(m2).x.clone(), float(loss.item()))
+        tr.engine.check_info()
+    if rank == 0:
+        m1 = build_model(X, Y, 'L1_G4_G3', M=M, num_IW_samples=K, minibatch_size=Bg, mode='IWAE', seed=3)
+        tr1 = Trainer(m1, Bg, lr=1e-2, seed=4, distributed=False)
+        for i in range(6):
+            gi_ = np.random.default_rng(100 + i).permutation(N)[:Bg]
+            loss1 = tr1.step_device(torch.as_tensor(X[gi_]).cuda(), torch.as_tensor(Y[gi_]).cuda())
+        x1 = FlatParams.of(m1).x
+        for mode, (x2, l2) in finals.items():
+            err = (x2 - x1).abs().max().item() / x1.abs().max().item()
+            lerr = abs(l2 - float(loss1.item())) / abs(float(loss1.item()))
+            print('Trainer dp%d [%s] vs single after 6 steps: x max err / max = %.3e, elbo rel err = %.3e'
+                  % (world, mode, err, lerr), flush=True)
+            ok = ok and err < 1e-8 and lerr < 1e-9
+    dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -47,7 +47,10 @@ def num(r, k):
     i = idx[k]
     if i is None or not r[i]:
         return None
-    v = float(r[i].replace(',', ''))
+    try:
+        v = float(r[i].replace(',', ''))
+    except ValueError:      # 'no data'
+        return None
     u = units[i]
     if k.endswith('_bytes') and u in ('Kbyte', 'Mbyte', 'Gbyte'):
         v *= {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
