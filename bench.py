@@ -403,8 +403,7 @@ def main():
     idx_all = torch.as_tensor(np.stack([next_idx() for _ in range(n_res)]), device=dev)
 
     def step_resident(i):
-        idx = idx_all[i]
-        return trainer.step_device(Xd[idx], Yd[idx])
+        return trainer.step_indices(idx_all[i])          # rows gathered on the device by iwvi_batch_gather
 
     # The clock sampler is constructed and started BEFORE the warm-up, on rank 0, so that nothing host-side happens on
     # any rank between the pre-timing barrier and ev0.record(): a rank that reaches its first all-reduce while another

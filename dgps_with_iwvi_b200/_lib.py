@@ -68,6 +68,7 @@ SIGNATURES = {
     'iwvi_normal_fill_counter': (C.c_int, [P, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int64, P, P]),
     'iwvi_adam_step_counter': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, P, C.c_double, C.c_double, C.c_double, P, P]),
     'iwvi_positive_fwd': (C.c_int, [P, P, C.c_int64, P]),
+    'iwvi_batch_gather': (C.c_int, [P, P, P, C.c_int32, C.c_int32, C.c_int32, P, P, P, P]),
     'iwvi_probe_dmma': (C.c_int, [P, C.c_int32, C.c_int32, C.c_int32, P]),
     'iwvi_adam_step': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int64, P]),

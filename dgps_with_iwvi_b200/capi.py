@@ -227,3 +227,9 @@ def probe_dmma(out, blocks, warps, iters):
     """Measurement utility: register-only DMMA issue loop (csrc/probe.cu); 2*256*8*iters*warps*blocks flops."""
     L.check(L.load().iwvi_probe_dmma(_ptr(out), int(blocks), int(warps), int(iters), _stream()), 'iwvi_probe_dmma')
     return 2.0 * 256 * 8 * iters * warps * blocks
+
+
+def batch_gather(X, Y, idx, B, Dx, Dy, Xb, Yb, XYb):
+    _count(1)
+    L.check(L.load().iwvi_batch_gather(_ptr(X), _ptr(Y), _ptr(idx), int(B), int(Dx), int(Dy), _ptr(Xb), _ptr(Yb),
+                                       _ptr(XYb), _stream()), 'iwvi_batch_gather')

@@ -27,6 +27,7 @@ struct LvParams {
   const double *F, *enc_in, *params, *eps, *mu_in, *sigma_in, *d_samples, *d_kl, *d_mu, *d_sigma;
   double *samples, *kl, *mu, *sigma, *d_params, *dF, *ws;
   int n_params, n_groups;
+  int rb;   // forward kernel: encoder rows per block iteration (<= LV_RB), chosen by the host so that the grid fills the SMs
 };
 
 // encoder forward for one row held by one warp.  acts: [n_layers+1][LV_W] of this warp (all layers kept).
@@ -52,16 +53,21 @@ __device__ __forceinline__ void encoder_row(const iwvi_lv_desc& d, const double*
 }
 
 __global__ void __launch_bounds__(256) lv_fwd_kernel(const LvParams p) {
+  // Per block iteration: `rb` encoder rows (one warp each evaluates the MLP), then all 256 threads write the rows'
+  // Kt points -- [F, W] and the local regulariser -- with consecutive threads on consecutive doubles of the row-major
+  // outputs (fully coalesced 8-byte accesses; rows are Df + Lw doubles wide, odd at c3, so wider vectors would straddle
+  // rows) and 32-bit index arithmetic.  rb is chosen by the host so that the grid covers the SMs: at c3 (512 rows) 8 rows
+  // per block left 64 CTAs on 148 SMs.
   __shared__ double acts[LV_RB][(IWVI_MAX_ENC_LAYERS + 1) * LV_W];
   __shared__ double mu_s[LV_RB][IWVI_MAX_LW], sg_s[LV_RB][IWVI_MAX_LW];
   const iwvi_lv_desc& d = p.d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Lw = d.Lw, Df = d.Df, Kt = d.Kt, C = Df + Lw;
+  const int Lw = d.Lw, Df = d.Df, Kt = d.Kt, C = Df + Lw, rb = p.rb;
   for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-    const int n0 = grp * LV_RB;
+    const int n0 = grp * rb;
     const int n = n0 + warp;
     __syncthreads();
-    if (n < d.Be) {
+    if (warp < rb && n < d.Be) {
       if (d.prior) {
         if (lane < Lw) { mu_s[warp][lane] = d.prior_mu; sg_s[warp][lane] = d.prior_sigma; }
       } else {
@@ -78,28 +84,29 @@ __global__ void __launch_bounds__(256) lv_fwd_kernel(const LvParams p) {
       }
     }
     __syncthreads();
-    const int rows = min(LV_RB, d.Be - n0);
-    const int64_t p0 = (int64_t)n0 * Kt;
-    const int64_t ne = (int64_t)rows * Kt * C;
-    for (int64_t e = tid; e < ne; e += 256) {
-      const int64_t pl = e / C;
-      const int c = (int)(e - pl * C);
-      const int nl = (int)(pl / Kt);
-      const int64_t pt = p0 + pl;
+    const int rows = min(rb, d.Be - n0);
+    const size_t p0 = (size_t)n0 * Kt;
+    const double* Fsrc = d.f_bcast ? p.F + (size_t)n0 * Df : p.F + p0 * Df;
+    const double* eps = p.eps + p0 * Lw;
+    double* smp = p.samples + p0 * C;
+    double* klp = p.kl ? p.kl + p0 * Lw : nullptr;
+    const int ne = rows * Kt * C;                       // <= 8 * Kt * C: 32-bit arithmetic throughout
+    for (int e = tid; e < ne; e += 256) {
+      const int pl = e / C, c = e - pl * C;
+      const int nl = pl / Kt;
       double v;
       if (c < Df) {
-        v = d.f_bcast ? p.F[(size_t)(n0 + nl) * Df + c] : p.F[(size_t)pt * Df + c];
+        v = Fsrc[(d.f_bcast ? nl : pl) * Df + c];
       } else {
         const int j = c - Df;
-        const double m = mu_s[nl][j], s = sg_s[nl][j];
-        const double z = p.eps[(size_t)pt * Lw + j];
-        v = m + z * s;
-        if (p.kl) {
-          p.kl[(size_t)pt * Lw + j] = d.sampled ? -0.5 * z * z - log(s) + 0.5 * v * v
-                                                 : 0.5 * m * m + 0.5 * (s * s - 1.0 - log(s * s));
-        }
+        const double m = mu_s[nl][j], sg = sg_s[nl][j];
+        const double z = eps[pl * Lw + j];
+        v = m + z * sg;
+        if (klp)
+          klp[pl * Lw + j] = d.sampled ? -0.5 * z * z - log(sg) + 0.5 * v * v
+                                       : 0.5 * m * m + 0.5 * (sg * sg - 1.0 - log(sg * sg));
       }
-      p.samples[(size_t)pt * C + c] = v;
+      smp[e] = v;
     }
   }
 }
@@ -421,6 +428,22 @@ __global__ void adam_kernel(double* x, const double* g_elbo, double* m, double* 
   }
 }
 __global__ void step_counter_inc_kernel(int64_t* state) { state[0] += 1; }
+
+// Minibatch assembly: rows idx[b] (idx == NULL: row b) of the resident data arrays into the plan's X, Y and [X, Y] buffers
+// in one launch (Xb / Yb may be NULL when they are the sources themselves).
+__global__ void batch_gather_kernel(const double* __restrict__ X, const double* __restrict__ Y,
+                                    const int64_t* __restrict__ idx, int B, int Dx, int Dy, double* __restrict__ Xb,
+                                    double* __restrict__ Yb, double* __restrict__ XYb) {
+  const int W = Dx + Dy;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * W; e += gridDim.x * blockDim.x) {
+    const int b = e / W, c = e - b * W;
+    const int64_t row = idx ? idx[b] : b;
+    const double v = c < Dx ? X[row * Dx + c] : Y[row * Dy + (c - Dx)];
+    if (XYb) XYb[e] = v;
+    if (c < Dx) { if (Xb) Xb[(size_t)b * Dx + c] = v; }
+    else if (Yb) Yb[(size_t)b * Dy + (c - Dx)] = v;
+  }
+}
 __global__ void positive_fwd_kernel(const double* x, double* theta, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     theta[i] = softplus_d(x[i]) + 1e-6;
@@ -451,7 +474,14 @@ extern "C" int iwvi_lv_fwd(const iwvi_lv_desc* d, const double* F, const double*
   p.d = *d; p.F = F; p.enc_in = enc_in; p.params = params; p.eps = eps;
   p.samples = samples; p.kl = kl; p.mu = mu; p.sigma = sigma;
   p.n_params = lv_nparams(d);
-  p.n_groups = (d->Be + LV_RB - 1) / LV_RB;
+  // rows per block: as many as keep >= 2 x 148 blocks in flight (8 at most: one warp per row), and few enough that the
+  // 32-bit element count of a block iteration (rows * Kt * (Df + Lw)) cannot overflow
+  int rb = LV_RB;
+  while (rb > 1 && (d->Be + rb - 1) / rb < 2 * 148) rb >>= 1;
+  while (rb > 1 && (int64_t)rb * d->Kt * (d->Df + d->Lw) > (int64_t)1 << 30) rb >>= 1;
+  if ((int64_t)rb * d->Kt * (d->Df + d->Lw) > (int64_t)1 << 30) return IWVI_ERR_UNSUPPORTED;
+  p.rb = rb;
+  p.n_groups = (d->Be + rb - 1) / rb;
   const int grid = p.n_groups < 4 * LV_MAX_GRID ? p.n_groups : 4 * LV_MAX_GRID;
   lv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   IWVI_CHECK_LAUNCH();
@@ -553,6 +583,19 @@ extern "C" int iwvi_normal_fill_counter(double* out, int64_t n_points, int32_t C
   int64_t nb = (pairs + 255) / 256;
   if (nb > 4 * 148) nb = 4 * 148;
   normal_fill_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(out, first_point * C, n, seed_base, state, step_add, layer);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
+
+extern "C" int iwvi_batch_gather(const double* X, const double* Y, const int64_t* idx, int32_t B, int32_t Dx, int32_t Dy,
+                                 double* Xb, double* Yb, double* XYb, void* stream) {
+  if (!X || !Y) return IWVI_ERR_NULL;
+  if (B < 0 || Dx < 1 || Dy < 1) return IWVI_ERR_BAD_DESC;
+  if (B == 0) return IWVI_OK;
+  const int n = B * (Dx + Dy);
+  int nb = (n + 255) / 256;
+  if (nb > 4 * 148) nb = 4 * 148;
+  batch_gather_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(X, Y, idx, B, Dx, Dy, Xb, Yb, XYb);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }

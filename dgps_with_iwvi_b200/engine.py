@@ -268,8 +268,13 @@ class Engine:
         if Y is not None:
             Y = torch.as_tensor(Y, dtype=F64)
             self.Y.copy_(Y.reshape(self.B, self.Dy), non_blocking=True)
-            self.XY[:, :self.Dx].copy_(self.X)
-            self.XY[:, self.Dx:].copy_(self.Y)
+            capi.batch_gather(self.X, self.Y, None, self.B, self.Dx, self.Dy, None, None, self.XY)
+
+    def set_batch_indices(self, Xdata, Ydata, idx):
+        """The minibatch as row indices (int64 device tensor [B]) into device-resident data arrays X [N, Dx], Y [N, Dy]
+        (gpflow.params.Minibatch, models.py:25-26): X, Y and [X, Y] are gathered in ONE launch."""
+        assert idx.dtype == torch.int64 and idx.numel() == self.B
+        capi.batch_gather(Xdata, Ydata, idx, self.B, self.Dx, self.Dy, self.X, self.Y, self.XY)
 
     def _tile(self, A, out):
         if self.mode == 'iw':      # data-major: point = n*K + k

@@ -113,10 +113,15 @@ class DGP_VI(Parameterized):
     def _build_likelihood(self, X=None, Y=None, eps=None):
         """ELBO on the next minibatch (or the given one) as a 1-element device tensor; reference models.py:49-86
         (VI) / :112-150 (IW).  `eps`: optional injected noise, one entry per layer, point-major."""
-        if X is None:
-            X, Y = self._next_batch()
-        eng = self.engine(len(X), self.num_samples)
-        eng.set_batch(X, Y)
+        if X is None and self.minibatch is not None:
+            idx = torch.as_tensor(self.minibatch.next(), device=self.X.device)
+            eng = self.engine(len(idx), self.num_samples)
+            eng.set_batch_indices(self.X, self.Y, idx)       # one gather launch (gpflow Minibatch, models.py:25-26)
+        else:
+            if X is None:
+                X, Y = self.X, self.Y
+            eng = self.engine(len(X), self.num_samples)
+            eng.set_batch(X, Y)
         self._evals += 1
         eng.draw_noise(eps, seed=self.noise_seed, step=self._evals)
         self._last_engine = eng

@@ -195,7 +195,12 @@ class Trainer:
         self._graph_row0 = row0
         capi.LAUNCHES = l0             # capture launched nothing; replays are counted in step_device
 
-    def step_device(self, X_local, Y_local, row0_global=None):
+    def step_indices(self, idx_local, row0_global=None):
+        """step_device with this rank's minibatch rows given as int64 device indices into the model's resident data
+        (model.X, model.Y): the gather is one launch instead of torch indexing + copies."""
+        return self.step_device(None, None, row0_global, idx=idx_local)
+
+    def step_device(self, X_local, Y_local, row0_global=None, idx=None):
         """One training step on this rank's rows; returns the global ELBO as a 1-element device tensor (no sync)."""
         self.t += 1
         row0 = self.rank * self.B_local if row0_global is None else row0_global
@@ -211,7 +216,10 @@ class Trainer:
         if lr != self._lr_host:
             self.lr_dev.fill_(lr)
             self._lr_host = lr
-        self.engine.set_batch(X_local, Y_local)
+        if idx is not None:
+            self.engine.set_batch_indices(self.model.X, self.model.Y, idx)
+        else:
+            self.engine.set_batch(X_local, Y_local)
         graph = self.use_graph and self.t > self.eager_steps_before_capture
         if graph and (self._graphs is None or self._graph_row0 != row0):
             self._capture(row0)

@@ -265,6 +265,13 @@ int iwvi_normal_fill(double* out, int64_t n_points, int32_t C, int64_t first_poi
 int iwvi_normal_fill_counter(double* out, int64_t n_points, int32_t C, int64_t first_point, uint64_t seed_base,
                              int32_t layer, int64_t step_add, const int64_t* state, void* stream);
 
+/* ---- minibatch assembly (gpflow.params.Minibatch feeding X / Y, models.py:25-26; the [X, Y] concatenation of
+ * models.py:53,116) ----
+ * Rows idx[b] (int64 device indices; NULL: row b) of the resident data X [N,Dx], Y [N,Dy] into Xb [B,Dx], Yb [B,Dy] and
+ * XYb [B,Dx+Dy] (any of the three outputs may be NULL) in one launch. */
+int iwvi_batch_gather(const double* X, const double* Y, const int64_t* idx, int32_t B, int32_t Dx, int32_t Dy,
+                      double* Xb, double* Yb, double* XYb, void* stream);
+
 /* ---- optimiser step either side of the path (experiments/build_models.py:284-295) ----
  * gpflow.transforms.positive (Log1pe): theta = softplus(x) + 1e-6 for the first n entries. */
 int iwvi_positive_fwd(const double* x, double* theta, int64_t n, void* stream);

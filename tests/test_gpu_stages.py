@@ -430,3 +430,22 @@ def test_rows_fwd_range_equals_whole_call(T, M):
     assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, 0, cut + 1, stream) == -1
     assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, cut, T + 1, stream) == -1
     assert lib.iwvi_gp_rows_fwd_range(C.byref(df), *ptrs, cut, cut, stream) == 0        # empty range: nothing to do
+
+
+def test_batch_gather_one_launch():
+    """iwvi_batch_gather: rows idx[b] of resident X / Y into X_b, Y_b and [X_b, Y_b] (gpflow Minibatch + the concatenation
+    of models.py:53,116), bit-exact; idx = NULL copies row b (the host-batch path's [X, Y] assembly)."""
+    from dgps_with_iwvi_b200 import capi
+    rng = np.random.default_rng(3)
+    N, B, Dx, Dy = 1000, 77, 5, 2
+    X, Y = rng.standard_normal((N, Dx)), rng.standard_normal((N, Dy))
+    idx = rng.integers(0, N, B)
+    dev = torch.device('cuda')
+    Xd, Yd, idxd = torch.as_tensor(X, device=dev), torch.as_tensor(Y, device=dev), torch.as_tensor(idx, device=dev)
+    Xb, Yb, XYb = (torch.zeros(B, c, dtype=torch.float64, device=dev) for c in (Dx, Dy, Dx + Dy))
+    capi.batch_gather(Xd, Yd, idxd, B, Dx, Dy, Xb, Yb, XYb)
+    assert np.array_equal(Xb.cpu().numpy(), X[idx]) and np.array_equal(Yb.cpu().numpy(), Y[idx])
+    assert np.array_equal(XYb.cpu().numpy(), np.concatenate([X[idx], Y[idx]], 1))
+    XY2 = torch.zeros_like(XYb)
+    capi.batch_gather(Xb, Yb, None, B, Dx, Dy, None, None, XY2)
+    assert torch.equal(XY2, XYb)
