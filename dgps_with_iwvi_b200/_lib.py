@@ -53,8 +53,9 @@ SIGNATURES = {
     'iwvi_gp_tile_points': (C.c_int, [C.POINTER(GpDesc)]),
     'iwvi_gp_rows_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 23),
     'iwvi_gp_prologue_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 16),
-    'iwvi_gp_fullcov_fwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 5 + [C.c_double] + [P] * 4),
-    'iwvi_gp_fullcov_bwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 4 + [C.c_double] + [P] * 6),
+    'iwvi_gp_fullcov_fwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 5 + [C.c_double] + [P] * 5),
+    'iwvi_gp_fullcov_ws_doubles': (C.c_int64, [C.POINTER(GpDesc), C.c_int32, C.c_int32]),
+    'iwvi_gp_fullcov_bwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 4 + [C.c_double] + [P] * 7),
     'iwvi_gauss_kl_fwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 4),
     'iwvi_gauss_kl_bwd': (C.c_int, [C.c_int32, C.c_int32] + [P] * 6),
     'iwvi_lv_param_doubles': (C.c_int64, [C.POINTER(LvDesc)]),

@@ -140,18 +140,25 @@ def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls
             'iwvi_gp_prologue_bwd')
 
 
-def gp_fullcov_fwd(d, S, N, aux, X, save, mean, eps, chol_jitter, cov, sample, info):
+def gp_fullcov_ws_doubles(d, S, N):
+    n = L.load().iwvi_gp_fullcov_ws_doubles(C.byref(d), int(S), int(N))
+    if n < 0:
+        raise RuntimeError('iwvi_gp_fullcov_ws_doubles: bad descriptor')
+    return int(n)
+
+
+def gp_fullcov_fwd(d, S, N, aux, X, save, mean, eps, chol_jitter, cov, sample, info, ws=None):
     _count(1)
     L.check(L.load().iwvi_gp_fullcov_fwd(C.byref(d), int(S), int(N), _ptr(aux), _ptr(X), _ptr(save), _ptr(mean),
-                                         _ptr(eps), float(chol_jitter), _ptr(cov), _ptr(sample), _ptr(info), _stream()),
-            'iwvi_gp_fullcov_fwd')
+                                         _ptr(eps), float(chol_jitter), _ptr(cov), _ptr(sample), _ptr(info), _ptr(ws),
+                                         _stream()), 'iwvi_gp_fullcov_fwd')
 
 
-def gp_fullcov_bwd(d, S, N, aux, X, save, eps, chol_jitter, d_sample, d_cov, save2, dX_knn, part):
+def gp_fullcov_bwd(d, S, N, aux, X, save, eps, chol_jitter, d_sample, d_cov, save2, dX_knn, part, ws=None):
     _count(1)
     L.check(L.load().iwvi_gp_fullcov_bwd(C.byref(d), int(S), int(N), _ptr(aux), _ptr(X), _ptr(save), _ptr(eps),
                                          float(chol_jitter), _ptr(d_sample), _ptr(d_cov), _ptr(save2), _ptr(dX_knn),
-                                         _ptr(part), _stream()), 'iwvi_gp_fullcov_bwd')
+                                         _ptr(part), _ptr(ws), _stream()), 'iwvi_gp_fullcov_bwd')
 
 
 def gauss_kl_fwd(M, R, q_mu, q_sqrt, kl):

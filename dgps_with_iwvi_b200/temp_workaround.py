@@ -20,7 +20,8 @@ never taken by GPLayer, layers.py:42) is served by the same per-point kernels af
 onto the same kernels (zero / diagonal Cholesky factors).  full_cov=True
 (:55-57,82-83, whose joint sampler :92-96 has a shape bug and is dead code in training) is served
 by iwvi_gp_fullcov_fwd / _bwd (csrc/gp_fullcov.cu: DMMA Gram products on the saved A / U panels, shared-memory
-Cholesky and its adjoint, corrected joint draw), differentiable for groups of up to 64 points."""
+Cholesky and its adjoint, corrected joint draw; batched blocked Cholesky over global memory beyond 64 points), differentiable for groups of up to
+256 points (BASELINE config c4: K = 256)."""
 import numpy as np
 import torch
 
@@ -135,7 +136,9 @@ class _GPFullCov(torch.autograd.Function):
         capi.gp_rows_fwd(d, Lm, aux, Xc, None, Ac, bc, None, None, mean, var, save)
         cov = zr(S_, R, N, N)
         smp = zr(T, R) if zc is not None else None
-        capi.gp_fullcov_fwd(d, S_, N, aux, Xc, save, mean, zc, meta['chol_jitter'], cov, smp, info[1:])
+        n_ws = capi.gp_fullcov_ws_doubles(d, S_, N)
+        ws = zr(n_ws) if n_ws else None
+        capi.gp_fullcov_fwd(d, S_, N, aux, Xc, save, mean, zc, meta['chol_jitter'], cov, smp, info[1:], ws)
         i0, i1 = (int(v) for v in info.tolist())
         if i0:
             raise RuntimeError('Cholesky of Kuu failed: leading minor of order %d is not positive definite' % i0)
@@ -152,8 +155,8 @@ class _GPFullCov(torch.autograd.Function):
         Xc, Zc, lsc, vc, qmc, qsc, Ac, bc, zc, Lm, aux, save = ctx.saved
         d, meta = ctx.d, ctx.meta
         S_, N = meta['S'], meta['N']
-        if N > 64:
-            raise NotImplementedError('the adjoint of the covariance over the inner axis is built for at most 64 points '
+        if N > 256:
+            raise NotImplementedError('the adjoint of the covariance over the inner axis is built for at most 256 points '
                                       'per group (N = %d)' % N)
         dev = Xc.device
         zr = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
@@ -162,7 +165,9 @@ class _GPFullCov(torch.autograd.Function):
         Mp = Lm.shape[0]
         ds = _c(d_sample) if (zc is not None and d_sample is not None and d_sample.numel()) else None
         save2, dXk, part = torch.zeros_like(save), zr(T, D), zr(S_, 40)
-        capi.gp_fullcov_bwd(d, S_, N, aux, Xc, save, zc, meta['chol_jitter'], ds, _c(d_cov), save2, dXk, part)
+        n_ws = capi.gp_fullcov_ws_doubles(d, S_, N)
+        capi.gp_fullcov_bwd(d, S_, N, aux, Xc, save, zc, meta['chol_jitter'], ds, _c(d_cov), save2, dXk, part,
+                            zr(n_ws) if n_ws else None)
         gm = zr(T, R) if d_mean is None else d_mean.detach().clone()
         if ds is not None:
             gm += ds
@@ -284,8 +289,8 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
         raise NotImplementedError('the Mok branch forces full_cov=False (temp_workaround.py:125-129)')
     S_ = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
     N = lead[-1]
-    if sample and N > 64:
-        raise NotImplementedError('the joint draw is built for inner axes of at most 64 points (N = %d); the covariance '
+    if sample and N > 256:
+        raise NotImplementedError('the joint draw is built for inner axes of at most 256 points (N = %d); the covariance '
                                   'itself (sample=False) has no such limit' % N)
     z = None
     if sample:

@@ -170,18 +170,20 @@ int iwvi_gp_prologue_bwd(const iwvi_gp_desc* d, const double* Lm, const double* 
  * Covariance over the inner axis and the joint draw, forward, for plain-kernel layers: the full_cov=True branch of
  * independent_multisample_sample_conditional (temp_workaround.py:45, :55-57, :82-83) and the joint sampler intended at
  * :92-96 (the reference's own lines add an [S,N,R] mean to an [S,R,N,1] draw and never execute).  Runs after
- * iwvi_gp_rows_fwd with IWVI_FLAG_SAVE on the same descriptor (d->T == S*N, d->mix == 0; sample needs N <= 64):
+ * iwvi_gp_rows_fwd with IWVI_FLAG_SAVE on the same descriptor (d->T == S*N, d->mix == 0; the draw serves N <= 256, the
+ * covariance any N).  ws: iwvi_gp_fullcov_ws_doubles(d, S, N) doubles (0 for N <= 64: may be NULL):
  *   X [S*N,D]; save (A, U_r panels); mean [S*N,R] as written by iwvi_gp_rows_fwd; eps [S,R,N] (the [S,R,N,1] draw of :94)
  *   out: cov [S,R,N,N] = k(X_s,X_s) - A_s^T A_s + U_rs^T U_rs (or NULL);
  *        sample [S*N,R] = mean + chol(cov + chol_jitter I) eps (or NULL); info [1] (int32, first failing leading minor).
  */
 int iwvi_gp_fullcov_fwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const double* aux, const double* X,
                         const double* save, const double* mean, const double* eps, double chol_jitter,
-                        double* cov, double* sample, int32_t* info, void* stream);
+                        double* cov, double* sample, int32_t* info, double* ws, void* stream);
+int64_t iwvi_gp_fullcov_ws_doubles(const iwvi_gp_desc* d, int32_t S, int32_t N);   /* workspace of _fwd / _bwd (doubles) */
 
 /*
  * Adjoint of iwvi_gp_fullcov_fwd (tf.gradients through temp_workaround.py:45,55-57,82-83 and the joint draw; Cholesky
- * adjoint as in TF's CholeskyGrad, symmetrised), N <= 64.  Cotangents d_sample [S*N,R] and d_cov [S,R,N,N] (either may
+ * adjoint as in TF's CholeskyGrad, symmetrised), N <= 256 (ws as for the forward call).  Cotangents d_sample [S*N,R] and d_cov [S,R,N,N] (either may
  * be NULL).  It prepares what iwvi_gp_rows_bwd needs to finish the job with its existing kernels:
  *   save2 (same size as save, zero-initialised by the caller): save2.A = A_s (sum_r H_r) / R, save2.U_r = U_rs H_r, with
  *         H_r the symmetric N x N cotangent of C_r.  Run iwvi_gp_rows_bwd(IWVI_FLAG_ONLY_EPI | ONLY_TILE | NO_KDIAG) on
@@ -192,7 +194,7 @@ int iwvi_gp_fullcov_fwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const doubl
  */
 int iwvi_gp_fullcov_bwd(const iwvi_gp_desc* d, int32_t S, int32_t N, const double* aux, const double* X,
                         const double* save, const double* eps, double chol_jitter, const double* d_sample,
-                        const double* d_cov, double* save2, double* dX_knn, double* part, void* stream);
+                        const double* d_cov, double* save2, double* dX_knn, double* part, double* ws, void* stream);
 
 /*
  * Whitened KL[q(u)||p(u)] on its own, for callers of the operator-level gauss_kl(q_mu, q_sqrt) (temp_workaround.py:167-188

@@ -164,7 +164,7 @@ def test_full_cov_branch_and_predict_f_full_cov():
                                                   q_sqrt=layer.q_sqrt, white=True, sample=False)
     close('mean3', mg, mo); close('cov3', vg, vo)
     assert vg.shape == (3, 1, 11, 11)
-    # more than 64 points per group: covariance in 64 x 64 blocks; the joint draw is limited to one block
+    # more than 64 points per group: covariance in 64 x 64 blocks; the joint draw is built for up to 256 points
     F2 = rng.standard_normal((2, 97, D))
     _, mo2, vo2 = O.independent_multisample_sample_conditional(T64(F2), omodel.layers[0].Z, omodel.layers[0].kern,
                                                               omodel.layers[0].q_mu, full_cov=True,
@@ -173,8 +173,9 @@ def test_full_cov_branch_and_predict_f_full_cov():
                                                     q_sqrt=layer.q_sqrt, white=True, sample=False)
     close('mean3b', mg2, mo2); close('cov3b', vg2, vo2)
     assert torch.equal(vg2, vg2.transpose(-1, -2))
+    F3 = rng.standard_normal((1, 257, D))
     with pytest.raises(NotImplementedError):
-        tw.multisample_sample_conditional(T64(F2).cuda(), layer.feature, layer.kern, layer.q_mu, full_cov=True,
+        tw.multisample_sample_conditional(T64(F3).cuda(), layer.feature, layer.kern, layer.q_mu, full_cov=True,
                                           q_sqrt=layer.q_sqrt, white=True)
 
 
@@ -213,7 +214,9 @@ def test_conditional_q_sqrt_none_and_diagonal(form):
 
 
 @pytest.mark.parametrize('S_,N,M,kern', [(5, 50, 100, 'RBF'), (3, 64, 37, 'Matern52'), (7, 8, 64, 'Matern32'),
-                                         (4, 1, 29, 'RBF'), (2, 20, 130, 'Matern12')])
+                                         (4, 1, 29, 'RBF'), (2, 20, 130, 'Matern12'),
+                                         # beyond one 64-point block: batched blocked Cholesky over global memory
+                                         (3, 65, 40, 'RBF'), (2, 150, 100, 'Matern52'), (2, 256, 70, 'RBF')])
 def test_full_cov_joint_draw(S_, N, M, kern):
     """iwvi_gp_fullcov_fwd: covariance over the inner axis [S, R, N, N] (temp_workaround.py:55-57,82-83) and the joint
     draw the reference intends at :92-96 (noise in its [S, R, N, 1] order), against the oracle; groups straddle the
@@ -230,7 +233,9 @@ def test_full_cov_joint_draw(S_, N, M, kern):
     gkern = layer.kern.kernel if hasattr(layer.kern, 'W') else layer.kern
     R = ol.q_mu.shape[1]
     rng = np.random.default_rng(5)
-    F = rng.standard_normal((S_, N, D)); z = rng.standard_normal((S_, R, N))
+    # (large groups: points spread out, so that the N x N covariance of a smooth kernel stays well conditioned -- the
+    #  reference factorises it without jitter, temp_workaround.py:95)
+    F = rng.standard_normal((S_, N, D)) * (4.0 if N > 64 else 1.0); z = rng.standard_normal((S_, R, N))
     so, mo, vo = O.independent_multisample_sample_conditional(T64(F), ol.Z, okern, ol.q_mu, full_cov=True,
                                                               q_sqrt=ol.q_sqrt, white=True, eps_joint=T64(z))
     s, m, v = tw.independent_multisample_sample_conditional(T64(F).cuda(), layer.feature, gkern, layer.q_mu,
@@ -246,7 +251,9 @@ def test_full_cov_joint_draw(S_, N, M, kern):
 
 
 @pytest.mark.parametrize('conf,which,kern,S_,N', [('G2', 0, 'RBF', 3, 20), ('L1_G3', 2, 'Matern52', 2, 50),
-                                                  ('G3', 0, 'Matern32', 2, 64), ('G2', 1, 'RBF', 5, 1)])
+                                                  ('G3', 0, 'Matern32', 2, 64), ('G2', 1, 'RBF', 5, 1),
+                                                  ('G2', 0, 'RBF', 2, 100), ('L1_G3', 2, 'Matern52', 3, 129),
+                                                  ('G2', 0, 'Matern32', 1, 256)])
 def test_full_cov_joint_draw_autograd(conf, which, kern, S_, N):
     """Gradients through the covariance over the inner axis and the joint draw (iwvi_gp_fullcov_bwd + the per-point
     backward kernels) against torch autograd on the oracle (Cholesky adjoint included): cotangents on the sample, the
@@ -260,7 +267,7 @@ def test_full_cov_joint_draw_autograd(conf, which, kern, S_, N):
     gmf = None if mok else layer.mean_function
     Din, R = ol.Z.shape[1], ol.q_mu.shape[1]
     rng = np.random.default_rng(4)
-    F = rng.standard_normal((S_, N, Din)); z = rng.standard_normal((S_, R, N))
+    F = rng.standard_normal((S_, N, Din)) * (4.0 if N > 64 else 1.0); z = rng.standard_normal((S_, R, N))
     Fo = T64(F).requires_grad_(True)
     so, mo, vo = O.independent_multisample_sample_conditional(Fo, ol.Z, okern, ol.q_mu, full_cov=True, q_sqrt=ol.q_sqrt,
                                                               white=True, eps_joint=T64(z))

@@ -380,9 +380,12 @@ def test_fullcov_stage_info_and_errors():
     lib = LIB.load()
     stream = torch.cuda.current_stream().cuda_stream
     args = [g['aux'].data_ptr(), X.data_ptr(), save.data_ptr(), mean.data_ptr(), z.data_ptr(), 0.0, cov.data_ptr(),
-            smp.data_ptr(), info.data_ptr(), stream]
+            smp.data_ptr(), info.data_ptr(), None, stream]
     assert lib.iwvi_gp_fullcov_fwd(C.byref(df), S_, N + 1, *args) == -1           # S*N != T
-    assert lib.iwvi_gp_fullcov_fwd(C.byref(capi.with_flags(df, df.flags, T=65 * 2)), 2, 65, *args) == -2   # N > 64
+    assert lib.iwvi_gp_fullcov_fwd(C.byref(capi.with_flags(df, df.flags, T=257 * 2)), 2, 257, *args) == -2   # N > 256
+    assert lib.iwvi_gp_fullcov_fwd(C.byref(capi.with_flags(df, df.flags, T=65 * 2)), 2, 65, *args) == -4   # N > 64: no ws
+    assert capi.gp_fullcov_ws_doubles(df, S_, N) == 0
+    assert capi.gp_fullcov_ws_doubles(capi.with_flags(df, df.flags, T=65 * 2), 2, 65) >= 2 * R * 65 * 65
     mixed = capi.gp_desc(T, M, D, R, 4, 'RBF', True, 'Zero', LIB.FLAG_SAVE, 1e-6)
     assert lib.iwvi_gp_fullcov_fwd(C.byref(mixed), S_, N, *args) == -1            # the Mok branch forces full_cov=False
 
