@@ -12,6 +12,7 @@ MAX_ENC_LAYERS = 8
 
 KERN_IDS = {'RBF': 0, 'Matern12': 1, 'Matern32': 2, 'Matern52': 3}
 MF_IDS = {'Zero': 0, 'Identity': 1, 'Linear': 2}
+ACT_IDS = {'tanh': 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3, 'elu': 4, 'identity': 5}
 FLAG_SAMPLE, FLAG_SAVE, FLAG_ACCUM = 1, 2, 4
 FLAG_ONLY_EPI, FLAG_ONLY_TILE, FLAG_ONLY_REDUCE, FLAG_ONLY_FINAL = 16, 32, 64, 128
 FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
@@ -29,7 +30,8 @@ class GpDesc(C.Structure):
 class LvDesc(C.Structure):
     _fields_ = [('Be', C.c_int32), ('Kt', C.c_int32), ('Df', C.c_int32), ('Dxy', C.c_int32), ('Lw', C.c_int32),
                 ('n_layers', C.c_int32), ('dims', C.c_int32 * (MAX_ENC_LAYERS + 1)), ('sampled', C.c_int32),
-                ('f_bcast', C.c_int32), ('prior', C.c_int32), ('prior_mu', C.c_double), ('prior_sigma', C.c_double)]
+                ('f_bcast', C.c_int32), ('prior', C.c_int32), ('act', C.c_int32), ('reserved', C.c_int32),
+                ('prior_mu', C.c_double), ('prior_sigma', C.c_double)]
 
 
 class ElboDesc(C.Structure):

@@ -20,7 +20,7 @@ def model_from_spec(spec, X, Y, mode='iw', minibatch_size=None):
     for ls in spec['layers']:
         if ls['type'] == 'lv':
             dims = [w.shape[0] for w in ls['Ws']] + [ls['Ws'][-1].shape[1]]
-            enc = Encoder(ls['latent_dim'], dims[0], dims[1:-1], seed=0)
+            enc = Encoder(ls['latent_dim'], dims[0], dims[1:-1], activation_func=ls.get('activation'), seed=0)
             for p, w in zip(enc.Ws, ls['Ws']):
                 p.assign(w)
             for p, b in zip(enc.bs, ls['bs']):
@@ -30,7 +30,9 @@ def model_from_spec(spec, X, Y, mode='iw', minibatch_size=None):
             M, D = ls['Z'].shape
             R = ls['q_mu'].shape[1]
             lsc = np.asarray(ls['lengthscales'], dtype=np.float64)
-            kern = KERNELS[ls['kern']](D, variance=float(ls['variance']), lengthscales=lsc, ARD=lsc.ndim > 0 and lsc.size > 1)
+            adims = ls.get('active_dims')
+            kern = KERNELS[ls['kern']](D if adims is None else len(adims), variance=float(ls['variance']), lengthscales=lsc,
+                                       ARD=lsc.ndim > 0 and lsc.size > 1, active_dims=adims)
             feat = InducingPoints(ls['Z'])
             if ls.get('W') is not None:
                 kern = SharedMixedMok(kern, ls['W'])
@@ -123,10 +125,11 @@ def spec_from_model(model):
                                q_mu=layer.q_mu.read_value(), q_sqrt=layer.q_sqrt.read_value(),
                                W=layer.kern.W.read_value() if mix else None, mf=mf.kind,
                                mf_A=mf.A.read_value() if mf.kind == 'Linear' else None,
-                               mf_b=mf.b.read_value() if mf.kind == 'Linear' else None, jitter=layer.jitter))
+                               mf_b=mf.b.read_value() if mf.kind == 'Linear' else None, jitter=layer.jitter,
+                               active_dims=getattr(base, 'active_dims', None)))
         else:
             enc = layer.encoder
             layers.append(dict(type='lv', latent_dim=layer.latent_dim, Ws=[w.read_value() for w in enc.Ws],
-                               bs=[b.read_value() for b in enc.bs]))
+                               bs=[b.read_value() for b in enc.bs], activation=enc.activation_func))
     return dict(num_data=model.num_data, num_samples=model.num_samples,
                 lik_variance=model.likelihood.variance.read_value(), layers=layers)

@@ -43,13 +43,14 @@ def with_flags(d, flags, T=None):
     return L.GpDesc(d.T if T is None else int(T), d.M, d.D, d.R, d.P, d.kern, d.mix, d.mf, int(flags), 0, d.jitter)
 
 
-def lv_desc(Be, Kt, Df, Dxy, Lw, dims, sampled, f_bcast, prior=False, prior_mu=0.0, prior_sigma=1.0):
+def lv_desc(Be, Kt, Df, Dxy, Lw, dims, sampled, f_bcast, prior=False, prior_mu=0.0, prior_sigma=1.0, act='tanh'):
     arr = (C.c_int32 * (L.MAX_ENC_LAYERS + 1))()
     dims = list(dims or [])
     for i, v in enumerate(dims):
         arr[i] = int(v)
     return L.LvDesc(int(Be), int(Kt), int(Df), int(Dxy), int(Lw), max(len(dims) - 1, 0), arr, int(bool(sampled)),
-                    int(bool(f_bcast)), int(bool(prior)), float(prior_mu), float(prior_sigma))
+                    int(bool(f_bcast)), int(bool(prior)), L.ACT_IDS[act] if isinstance(act, str) else int(act), 0,
+                    float(prior_mu), float(prior_sigma))
 
 
 def elbo_desc(B, K, Dy, Lw, iw, data_major, scale):

@@ -21,6 +21,28 @@ namespace {
 
 __device__ __forceinline__ double softplus_d(double x) { return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
 __device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+// Encoder non-linearity (IWVI_ACT_*) and its derivative expressed through the OUTPUT t = act(a), which is what the backward
+// pass has at hand (it recomputes the activations, not the pre-activations)
+__device__ __forceinline__ double act_fwd(int act, double a) {
+  switch (act) {
+    case IWVI_ACT_TANH: return tanh(a);
+    case IWVI_ACT_RELU: return a > 0.0 ? a : 0.0;
+    case IWVI_ACT_SIGMOID: return sigmoid_d(a);
+    case IWVI_ACT_SOFTPLUS: return softplus_d(a);
+    case IWVI_ACT_ELU: return a > 0.0 ? a : expm1(a);
+    default: return a;
+  }
+}
+__device__ __forceinline__ double act_grad_from_output(int act, double t) {
+  switch (act) {
+    case IWVI_ACT_TANH: return 1.0 - t * t;
+    case IWVI_ACT_RELU: return t > 0.0 ? 1.0 : 0.0;
+    case IWVI_ACT_SIGMOID: return t * (1.0 - t);
+    case IWVI_ACT_SOFTPLUS: return -expm1(-t);          // sigmoid(a) = 1 - exp(-softplus(a))
+    case IWVI_ACT_ELU: return t > 0.0 ? 1.0 : t + 1.0;
+    default: return 1.0;
+  }
+}
 
 struct LvParams {
   iwvi_lv_desc d;
@@ -43,7 +65,7 @@ __device__ __forceinline__ void encoder_row(const iwvi_lv_desc& d, const double*
     for (int u = lane; u < dout; u += 32) {
       double a = b[u];
       for (int i = 0; i < din; i++) a += h[i] * W[i * dout + u];
-      if (l < d.n_layers - 1) a = tanh(a);
+      if (l < d.n_layers - 1) a = act_fwd(d.act, a);
       if (din == dout) a += h[u];
       o[u] = a;
     }
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(256) lv_bwd_kernel(const LvParams p) {
       __syncwarp();
       for (int u = lane; u < dout; u += 32) {
         double g = dout_s[warp][u];
-        if (l < d.n_layers - 1) { const double t = o[u] - (skip ? h[u] : 0.0); g *= 1.0 - t * t; }
+        if (l < d.n_layers - 1) { const double t = o[u] - (skip ? h[u] : 0.0); g *= act_grad_from_output(d.act, t); }
         dpre_s[warp][u] = g;
       }
       __syncthreads();
@@ -234,6 +256,7 @@ int lv_check(const iwvi_lv_desc* d) {
   if (!d) return IWVI_ERR_NULL;
   if (d->Be < 0 || d->Kt < 1 || d->Df < 0 || d->Lw < 1 || d->Lw > IWVI_MAX_LW) return IWVI_ERR_BAD_DESC;
   if (!d->prior) {
+    if (d->act < 0 || d->act > IWVI_ACT_IDENTITY) return IWVI_ERR_BAD_DESC;
     if (d->n_layers < 1 || d->n_layers > IWVI_MAX_ENC_LAYERS) return IWVI_ERR_UNSUPPORTED;
     if (d->dims[0] != d->Dxy || d->dims[d->n_layers] != 2 * d->Lw) return IWVI_ERR_BAD_DESC;
     for (int l = 0; l <= d->n_layers; l++)

@@ -140,7 +140,8 @@ class Engine:
                 enc = layer.encoder
                 d = capi.lv_desc(Be, Kt, D_cur, self.Dx + self.Dy, Lw, None if prior else enc.layer_dims,
                                  sampled=(mode == 'iw'), f_bcast=bcast, prior=prior,
-                                 prior_mu=layer.prior_mu, prior_sigma=layer.prior_sigma)
+                                 prior_mu=layer.prior_mu, prior_sigma=layer.prior_sigma,
+                                 act=getattr(enc, 'activation_func', 'tanh'))
                 r = dict(type='lv', layer=layer, d=d, idx=li, Lw=Lw, Df=D_cur, bcast=bcast, Be=Be, first=first,
                          samples=z(T, D_cur + Lw), kl=z(T, Lw), eps=z(T, Lw), mu=z(Be, Lw), sigma=z(Be, Lw),
                          enc_in=None if (bcast or prior) else z(T, self.Dx + self.Dy))
@@ -172,6 +173,7 @@ class Engine:
                 P = kern.W.shape[0] if mix else R
                 D = D_cur
                 assert feat.Z.shape == (M, D), 'inducing inputs %s do not match layer input width %d' % (feat.Z.shape, D)
+                assert base.input_dim <= D, 'kernel input_dim %d exceeds the layer input width %d' % (base.input_dim, D)
                 mfk = layer.mean_function.kind
                 if mode == 'iw' and not last and not mix:
                     # reference models.py:118-125 asks plain-kernel inner layers for full_cov=True over K, a branch whose
@@ -186,12 +188,19 @@ class Engine:
                 flags = (LIB.FLAG_SAMPLE if sample else 0) | (LIB.FLAG_SAVE if self.train else 0)
                 d = capi.gp_desc(T, M, D, R, P, base.kind, mix, mfk, flags, layer.jitter)
                 Mp = capi.gp_mp(M)
+                # lengthscales reach the kernels as a width-D vector: the parameter itself when it already is one (ARD over all
+                # D columns, or D == 1), else an expanded copy (a shared lengthscale; +inf outside the kernel's active_dims)
+                direct = (base.ARD or D == 1) and getattr(base, 'active_dims', None) is None and base.input_dim == D
+                adims = getattr(base, 'active_dims', None)
+                if adims is None and base.input_dim != D:
+                    adims = list(range(base.input_dim))
                 r = dict(type='gp', layer=layer, d=d, idx=li, gi=gi, M=M, R=R, P=P, D=D, mix=mix, mf=mfk, Mp=Mp,
-                         sampled=sample, base=base, feat=feat, ard=base.ARD or D == 1,
+                         sampled=sample, base=base, feat=feat, ard=direct, adims=adims,
+                         adims_t=None if adims is None else torch.as_tensor(adims, dtype=torch.int64, device=dev),
                          Lm=z(Mp, Mp), aux=z(capi.gp_aux_doubles(d)), kl=self.kls[gi:gi + 1],
                          info=self.infos[gi:gi + 1], mean=z(T, P), var=z(T, P),
                          sample=z(T, P) if sample else None, eps=z(T, R) if sample else None,
-                         ls_vec=None if (base.ARD or D == 1) else z(D))
+                         ls_vec=None if direct else z(D))
                 if self.train:
                     r['save'] = z(capi.gp_save_doubles(d))
                     r['dLm'] = z(Mp, Mp)
@@ -319,7 +328,7 @@ class Engine:
                 if r['ard']:
                     ls = self._cv(base.lengthscales)
                 else:
-                    r['ls_vec'].copy_(self._cv(base.lengthscales).expand(r['D']))
+                    r['ls_vec'].copy_(base.full_lengthscales(self._cv(base.lengthscales).reshape(-1), r['D']))
                     ls = r['ls_vec']
                 r['ls'] = ls
                 capi.gp_prologue_fwd(r['d'], self._cv(feat.Z), ls, self._cv(base.variance), self._cv(layer.q_mu),
@@ -393,6 +402,16 @@ class Engine:
             self._join_loss()
         return flat.loss_slot
 
+    def _fold_dls(self, r):
+        """Gradient of the width-D lengthscale vector the kernels saw -> gradient of the lengthscale parameter: the sum for
+        a shared lengthscale, the active columns for an ARD kernel restricted by active_dims (inactive columns carry an
+        exact zero: their 1 / lengthscale is 0)."""
+        base, g = r['base'], self.flat.gview(r['base'].lengthscales)
+        if base.ARD:
+            torch.index_select(r['dls_vec'], 0, r['adims_t'], out=g)
+        else:
+            torch.sum(r['dls_vec'], 0, keepdim=True, out=g)
+
     def _join_loss(self):
         if self._loss_pending:
             torch.cuda.current_stream().wait_event(self.ev_loss)
@@ -449,7 +468,7 @@ class Engine:
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_A), *args)
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), *pargs)
                         if not r['ard']:
-                            torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                            self._fold_dls(r)
                         self.ev_pbwd[gi].record(side)
                     self.side_b.wait_event(self.ev_rows[gi])
                     with torch.cuda.stream(self.side_b):
@@ -463,7 +482,7 @@ class Engine:
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red), *args)
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), *pargs)
                         if not r['ard']:
-                            torch.sum(r['dls_vec'], 0, keepdim=True, out=flat.gview(base.lengthscales))
+                            self._fold_dls(r)
                         if self.grad_hook is not None:
                             self.grad_hook(('gp', gi))
                         self.ev_pbwd[gi].record(side)

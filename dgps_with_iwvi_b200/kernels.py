@@ -13,8 +13,12 @@ class Stationary(Parameterized):
     def __init__(self, input_dim, variance=1.0, lengthscales=None, active_dims=None, ARD=None, name=None):
         Parameterized.__init__(self, name=name)
         self.input_dim = int(input_dim)
-        if active_dims is not None and list(active_dims) != list(range(self.input_dim)):
-            raise NotImplementedError('only the default active_dims (first input_dim columns) are on the path')
+        # gpflow: the kernel acts on the columns `active_dims` of its inputs (default: the first input_dim columns).  The
+        # CUDA path consumes 1 / lengthscale per input column, so a restricted kernel is the full-width ARD kernel with
+        # 1 / lengthscale = 0 on the inactive columns (engine / temp_workaround expand the lengthscales accordingly).
+        self.active_dims = None if active_dims is None else [int(a) for a in active_dims]
+        if self.active_dims is not None and len(self.active_dims) != self.input_dim:
+            raise ValueError('active_dims must name input_dim = %d columns' % self.input_dim)
         if lengthscales is None:
             lengthscales = np.ones(self.input_dim) if ARD else 1.0
         lengthscales = np.asarray(lengthscales, dtype=np.float64)
@@ -25,6 +29,25 @@ class Stationary(Parameterized):
         self.ARD = bool(ARD)
         self.variance = Parameter(np.asarray(variance, dtype=np.float64).reshape(()), transform=positive)
         self.lengthscales = Parameter(lengthscales if self.ARD else lengthscales.reshape(()), transform=positive)
+
+
+    def full_lengthscales(self, ls, D):
+        """Constrained lengthscales `ls` (tensor: scalar or [input_dim]) as a width-D vector for the kernels: +inf on
+        columns the kernel does not act on."""
+        import torch
+        if self.active_dims is None and (ls.dim() == 0 or ls.numel() == 1):
+            return ls.expand(D) if self.input_dim == D else self._scatter(ls.expand(self.input_dim), list(range(self.input_dim)), D)
+        if self.active_dims is None and ls.numel() == D:
+            return ls
+        dims = self.active_dims if self.active_dims is not None else list(range(self.input_dim))
+        return self._scatter(ls.expand(len(dims)) if ls.numel() == 1 else ls, dims, D)
+
+    @staticmethod
+    def _scatter(vals, dims, D):
+        import torch
+        out = torch.full((D,), float('inf'), dtype=vals.dtype, device=vals.device)
+        idx = torch.as_tensor(dims, dtype=torch.int64, device=vals.device)
+        return out.index_copy(0, idx, vals.reshape(-1))
 
 
 class RBF(Stationary):

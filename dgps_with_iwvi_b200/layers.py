@@ -47,13 +47,22 @@ class GPLayer(Parameterized):
 
 
 class Encoder(Parameterized):
-    """reference layers.py:108-152: tanh MLP [input_dim, *network_dims, 2*latent_dim], skip connection after the
-    activation where widths match, sigma = softplus(raw - 3).  Xavier-normal weights, zero biases (:129-131)."""
+    """reference layers.py:108-152: MLP [input_dim, *network_dims, 2*latent_dim] with `activation_func` between the
+    layers (default tanh, :122), skip connection after the activation where widths match, sigma = softplus(raw - 3).
+    Xavier-normal weights, zero biases (:129-131).  The reference takes a TensorFlow op; here the non-linearity is named:
+    'tanh' | 'relu' | 'sigmoid' | 'softplus' | 'elu' | 'identity', or a callable whose __name__ is one of those
+    (torch.tanh, torch.relu, torch.nn.functional.softplus, ...) -- the fused encoder kernel evaluates it on the device."""
+    ACTIVATIONS = ('tanh', 'relu', 'sigmoid', 'softplus', 'elu', 'identity')
 
     def __init__(self, latent_dim, input_dim, network_dims, activation_func=None, name=None, seed=None):
         Parameterized.__init__(self, name=name)
-        if activation_func not in (None, 'tanh'):
-            raise NotImplementedError('the fused encoder kernel implements the reference default (tanh)')
+        act = activation_func if activation_func is not None else 'tanh'
+        if not isinstance(act, str):
+            act = getattr(act, '__name__', str(act)).lower()
+        if act not in self.ACTIVATIONS:
+            raise NotImplementedError('Encoder(activation_func=%r): the fused encoder kernel implements %s'
+                                      % (activation_func, ', '.join(self.ACTIVATIONS)))
+        self.activation_func = act
         self.latent_dim = latent_dim
         self.layer_dims = [input_dim, *network_dims, latent_dim * 2]
         rng = np.random if seed is None else np.random.default_rng(seed)

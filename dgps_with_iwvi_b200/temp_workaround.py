@@ -259,7 +259,7 @@ def independent_multisample_sample_conditional(Xnew, feat, kern, f, *, full_cov=
         elif q_sq.dim() != 3:
             raise ValueError('Bad dimension for q_sqrt: %s' % str(q_sq.dim()))
     ls, variance = _t(kern.lengthscales), _t(kern.variance)
-    ls_vec = ls.expand(D) if ls.dim() == 0 or ls.numel() == 1 else ls
+    ls_vec = kern.full_lengthscales(ls, D)      # width D; +inf (1 / lengthscale = 0) outside the kernel's active_dims
     if not white:
         # temp_workaround.py:63-65: A <- Lm^-T A before the mean (:68) and the q_sqrt projection (:78), the prior
         # variance term (:59) keeping the first A.  With Lm lower-triangular,
@@ -384,7 +384,7 @@ class _LVPropagate(torch.autograd.Function):
         prior = enc_in is None
         d = capi.lv_desc(T, 1, Df, 0 if prior else enc_in.shape[1], Lw, None if prior else meta['dims'],
                          sampled=meta['sampled'], f_bcast=False, prior=prior, prior_mu=meta.get('prior_mu', 0.0),
-                         prior_sigma=meta.get('prior_sigma', 1.0))
+                         prior_sigma=meta.get('prior_sigma', 1.0), act=meta.get('act', 'tanh'))
         z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
         samples, kl, mu, sigma = z(T, Df + Lw), z(T, Lw), z(T, Lw), z(T, Lw)
         Fc, Ec, Pc, ec = _c(F), _c(enc_in), _c(params), _c(eps)
@@ -419,7 +419,7 @@ def encoder_forward(enc, Z):
     lead = Zt.shape[:-1]
     Z2 = Zt.reshape(-1, Zt.shape[-1])
     eps0 = torch.zeros(Z2.shape[0], enc.latent_dim, dtype=F64, device=Z2.device)
-    meta = dict(dims=enc.layer_dims, sampled=False)
+    meta = dict(dims=enc.layer_dims, sampled=False, act=getattr(enc, 'activation_func', 'tanh'))
     _, _, mu, sigma = _LVPropagate.apply(None, Z2, _packed_encoder_params(enc), eps0, meta)
     return mu.reshape(*lead, enc.latent_dim), sigma.reshape(*lead, enc.latent_dim)
 
@@ -440,6 +440,7 @@ def latent_variable_propagate(layer, F, inference_amorization_inputs=None, is_sa
     else:
         XY = _t(inference_amorization_inputs)
         meta['dims'] = layer.encoder.layer_dims
+        meta['act'] = getattr(layer.encoder, 'activation_func', 'tanh')
         samples, kl, mu, sigma = _LVPropagate.apply(F2, XY.reshape(T, XY.shape[-1]),
                                                     _packed_encoder_params(layer.encoder), e, meta)
     mean = torch.cat([F2, mu], 1)

@@ -59,6 +59,14 @@ extern "C" {
 #define IWVI_MF_IDENTITY 1
 #define IWVI_MF_LINEAR   2
 
+/* encoder non-linearities: tf.nn.tanh (the reference default, layers.py:122) / relu / sigmoid / softplus / elu / identity */
+#define IWVI_ACT_TANH     0
+#define IWVI_ACT_RELU     1
+#define IWVI_ACT_SIGMOID  2
+#define IWVI_ACT_SOFTPLUS 3
+#define IWVI_ACT_ELU      4
+#define IWVI_ACT_IDENTITY 5
+
 /* flags */
 #define IWVI_FLAG_SAMPLE 1  /* eps given: produce sample = mean + eps*sqrt(var) (temp_workaround.py:89-91) */
 #define IWVI_FLAG_SAVE   2  /* keep A, U, latent mean/var for the backward pass */
@@ -217,6 +225,8 @@ typedef struct iwvi_lv_desc {
   int32_t sampled;   /* 1: log q(W) - log p(W) per sample (layers.py:98-100); 0: closed-form KL (:103) */
   int32_t f_bcast;   /* 1: F is [Be,Df], broadcast over Kt; 0: F is [Be*Kt,Df]             */
   int32_t prior;     /* 1: no encoder, q_mu/q_sqrt = prior_mu/prior_sigma (layers.py:73-81) */
+  int32_t act;       /* IWVI_ACT_*: Encoder(activation_func=...) between the layers (layers.py:109,122,144; default tanh) */
+  int32_t reserved;
   double  prior_mu, prior_sigma;
 } iwvi_lv_desc;
 

@@ -35,7 +35,8 @@ def adam_step(x, g_elbo_constrained, m, v, t, lr, n_pos, mask=None, b1=0.9, b2=0
     t = 1, 2, ...; lr already decayed.  Returns (x, m, v) new arrays."""
     x, m, v = np.array(x, dtype=np.float64), np.array(m, dtype=np.float64), np.array(v, dtype=np.float64)
     g = -np.asarray(g_elbo_constrained, dtype=np.float64).copy()
-    g[:n_pos] *= 1.0 / (1.0 + np.exp(-x[:n_pos]))
+    with np.errstate(over='ignore'):                        # exp(745) -> inf -> sigmoid 0, as intended
+        g[:n_pos] *= 1.0 / (1.0 + np.exp(-x[:n_pos]))
     live = np.ones_like(x, dtype=bool) if mask is None else (np.asarray(mask) != 0)
     g = np.where(live, g, 0.0)
     m = b1 * m + (1.0 - b1) * g

@@ -84,12 +84,16 @@ class Kern:
     """Stationary kernel descriptor: kind in {'RBF','Matern52','Matern32','Matern12'};
     variance scalar tensor, lengthscales scalar or [D] tensor (constrained values)."""
 
-    def __init__(self, kind, variance, lengthscales):
+    def __init__(self, kind, variance, lengthscales, active_dims=None):
         self.kind = kind
         self.variance = variance
         self.lengthscales = lengthscales
+        self.active_dims = active_dims      # gpflow Kern._slice: the kernel acts on these input columns only
 
     def K(self, X, X2=None):
+        if self.active_dims is not None:
+            X = X[..., self.active_dims]
+            X2 = None if X2 is None else X2[..., self.active_dims]
         r2 = square_dist(X, X2, self.lengthscales)
         if self.kind == 'RBF':
             return self.variance * torch.exp(-r2 / 2.0)
@@ -334,8 +338,12 @@ class GPLayer:
 class Encoder:
     """layers.py:108-152. Ws[i] [d_i, d_{i+1}], bs[i] [d_{i+1}]; tanh; skip when dims match; softplus(.-3)."""
 
-    def __init__(self, Ws, bs, latent_dim):
+    ACTS = {'tanh': torch.tanh, 'relu': torch.relu, 'sigmoid': torch.sigmoid,
+            'softplus': torch.nn.functional.softplus, 'elu': torch.nn.functional.elu, 'identity': lambda z: z}
+
+    def __init__(self, Ws, bs, latent_dim, activation='tanh'):
         self.Ws, self.bs, self.latent_dim = Ws, bs, latent_dim
+        self.activation = self.ACTS[activation]             # layers.py:122: activation_func or tf.nn.tanh
 
     def __call__(self, Z):
         n = len(self.bs)
@@ -344,7 +352,7 @@ class Encoder:
             Z0 = Z
             Z = Z @ W + b                                   # :141
             if i < n - 1:
-                Z = torch.tanh(Z)                           # :143-144
+                Z = self.activation(Z)                      # :143-144
             if dim_out == dim_in:
                 Z = Z + Z0                                  # :146-147 skip AFTER the activation
         means, log_chol_diag = torch.split(Z, self.latent_dim, dim=-1)    # :149
@@ -507,10 +515,11 @@ def build_from_spec(spec, requires_grad=False):
         if ls['type'] == 'lv':
             Ws = [leaf(p + 'encoder.Ws.%d' % j, w) for j, w in enumerate(ls['Ws'])]
             bs = [leaf(p + 'encoder.bs.%d' % j, b) for j, b in enumerate(ls['bs'])]
-            layers.append(LatentVariableLayer(ls['latent_dim'], Encoder(Ws, bs, ls['latent_dim'])))
+            layers.append(LatentVariableLayer(ls['latent_dim'], Encoder(Ws, bs, ls['latent_dim'],
+                                                                        ls.get('activation', 'tanh'))))
         else:
             kern = Kern(ls['kern'], leaf(p + 'kern.variance', ls['variance']),
-                        leaf(p + 'kern.lengthscales', ls['lengthscales']))
+                        leaf(p + 'kern.lengthscales', ls['lengthscales']), ls.get('active_dims'))
             if ls.get('W') is not None:
                 kern = Mok(kern, leaf(p + 'kern.W', ls['W']))
             mf = MeanFunction(ls['mf'], leaf(p + 'mf.A', ls.get('mf_A')), leaf(p + 'mf.b', ls.get('mf_b')))

@@ -39,7 +39,7 @@ def test_version_and_struct_layout(lib):
     assert lib.iwvi_version() == 100
     assert C.sizeof(_lib.GpDesc) == 48 and C.sizeof(_lib.ElboDesc) == 32
     assert _lib.GpDesc.jitter.offset == 40 and _lib.ElboDesc.scale.offset == 24
-    assert C.sizeof(_lib.LvDesc) == 4 * 6 + 4 * 9 + 4 * 3 + 16
+    assert C.sizeof(_lib.LvDesc) == 4 * 6 + 4 * 9 + 4 * 5 + 16
 
 
 def test_size_helpers_on_host(lib):

@@ -382,3 +382,93 @@ def test_model_propagate_matches_oracle_layer_loop():
     for name, got, want in zip(['samples', 'means', 'covs', 'kls'], pg[:4], po[:4]):
         for i, (a, b) in enumerate(zip(got, want)):
             close('predict %s[%d]' % (name, i), a, b)
+
+
+@pytest.mark.parametrize('act', ['relu', 'sigmoid', 'softplus', 'elu', 'identity'])
+def test_encoder_activation_functions(act):
+    """Encoder(activation_func=...) (reference layers.py:109,122,144): the non-default non-linearities of the fused
+    encoder kernel -- layer-level values and gradients, and the whole-model IW-ELBO + gradients through the engine."""
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    import helpers as H
+    D, N, K = 3, 12, 4
+    X, Y = S.make_data(30, D, seed=5)
+    spec = S.make_spec(X, 'L2_G2', 10, K, seed=5, perturb=0.3, inner_q_sqrt_scale=0.3)
+    spec['layers'][0]['activation'] = act
+    model = model_from_spec(spec, X, Y)
+    layer = model.layers[0]
+    assert layer.encoder.activation_func == act
+    omodel, leaves = O.build_from_spec(spec, requires_grad=True)
+    olayer = omodel.layers[0]
+    rng = np.random.default_rng(6)
+    F = rng.standard_normal((N, K, D)); XY = rng.standard_normal((N, K, D + 1)); eps = rng.standard_normal((N, K, 2))
+    Fo = T64(F).requires_grad_(True)
+    outs_o = olayer.propagate(Fo, T64(XY), True, eps=T64(eps))
+    Fg = T64(F).cuda().requires_grad_(True)
+    for _, p in layer.named_parameters():
+        p.unconstrained.requires_grad_(True)
+    outs = layer.propagate(Fg, inference_amorization_inputs=T64(XY).cuda(), is_sampled_local_regularizer=True,
+                           eps=T64(eps).cuda())
+    cots = [T64(rng.standard_normal(o.shape)) for o in outs_o]
+    for n, a, b in zip(['samples', 'mean', 'cov', 'kl'], outs, outs_o):
+        close(n, a, b)
+    sum((o * c).sum() for o, c in zip(outs_o, cots)).backward()
+    sum((o * c.cuda()).sum() for o, c in zip(outs, cots)).backward()
+    for j, (W, b) in enumerate(zip(layer.encoder.Ws, layer.encoder.bs)):
+        close('dW%d' % j, W.unconstrained.grad, leaves['layers.0.encoder.Ws.%d' % j].grad)
+        close('db%d' % j, b.unconstrained.grad, leaves['layers.0.encoder.bs.%d' % j].grad)
+    # whole model through the engine
+    m2 = model_from_spec(spec, X, Y)
+    eps_m = S.make_noise(spec, (N, K), seed=7)
+    e_ref, g_ref = O.iw_elbo_and_grads(spec, X[:N], Y[:N], eps_m)
+    e, g = m2.compute_log_likelihood_and_grads(X[:N], Y[:N], eps_m)
+    assert abs(e - e_ref.item()) < RTOL * abs(e_ref.item())
+    H.assert_grads_close(g, {k: v.numpy() for k, v in g_ref.items()}, RTOL, act)
+    with pytest.raises(NotImplementedError):
+        from dgps_with_iwvi_b200.layers import Encoder
+        Encoder(1, 3, [4], activation_func='swish')
+
+
+@pytest.mark.parametrize('ard', [True, False])
+def test_kernel_active_dims(ard):
+    """gpflow kernels restricted by `active_dims` (Kern._slice): a Mok layer whose base kernel acts on 3 of its 5 input
+    columns, ARD and shared lengthscale -- the operator-level conditional (values, gradients) and the whole-model
+    IW-ELBO + gradients through the engine, against the oracle evaluating the sliced kernel."""
+    from dgps_with_iwvi_b200 import temp_workaround as tw
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    import helpers as H
+    D, N, K, M = 4, 14, 3, 17
+    X, Y = S.make_data(40, D, seed=9)
+    spec = S.make_spec(X, 'L1_G3', M, K, seed=9, perturb=0.3, inner_q_sqrt_scale=0.3)
+    g1 = spec['layers'][1]                                   # input width D + 1 = 5
+    g1['active_dims'] = [0, 2, 4]
+    g1['lengthscales'] = g1['lengthscales'][[0, 2, 4]] if ard else np.array(1.7)
+    model = model_from_spec(spec, X, Y)
+    layer = model.layers[1]
+    assert layer.kern.kernel.active_dims == [0, 2, 4] and layer.kern.kernel.ARD == ard
+    omodel, leaves = O.build_from_spec(spec, requires_grad=True)
+    ol = omodel.layers[1]
+    rng = np.random.default_rng(2)
+    F = rng.standard_normal((N, K, D + 1)); eps = rng.standard_normal((N, K, 3))
+    Fo = T64(F).requires_grad_(True)
+    so, mo, vo = O.multisample_sample_conditional(Fo, ol.Z, ol.kern, ol.q_mu, q_sqrt=ol.q_sqrt, white=True, eps=T64(eps))
+    Fg = T64(F).cuda().requires_grad_(True)
+    model.requires_grad_()
+    s, m, v = tw.multisample_sample_conditional(Fg, layer.feature, layer.kern, layer.q_mu, q_sqrt=layer.q_sqrt, white=True,
+                                                eps=T64(eps).cuda(), jitter=layer.jitter)
+    close('sample', s, so); close('mean', m, mo); close('var', v, vo)
+    c = T64(rng.standard_normal(so.shape))
+    ((so * c).sum() + (vo * c).sum()).backward()
+    ((s * c.cuda()).sum() + (v * c.cuda()).sum()).backward()
+    close('dF', Fg.grad, Fo.grad)
+    base = layer.kern.kernel
+    sig = torch.sigmoid(base.lengthscales.unconstrained.detach())
+    close('dls', (base.lengthscales.unconstrained.grad / sig).reshape(leaves['layers.1.kern.lengthscales'].shape),
+          leaves['layers.1.kern.lengthscales'].grad)
+    close('dZ', layer.feature.feat.Z.unconstrained.grad, leaves['layers.1.Z'].grad)
+    assert (layer.feature.feat.Z.unconstrained.grad[:, [1, 3]] == 0).all()      # inactive columns: exact zeros
+    m2 = model_from_spec(spec, X, Y)
+    eps_m = S.make_noise(spec, (N, K), seed=3)
+    e_ref, g_ref = O.iw_elbo_and_grads(spec, X[:N], Y[:N], eps_m)
+    e, g = m2.compute_log_likelihood_and_grads(X[:N], Y[:N], eps_m)
+    assert abs(e - e_ref.item()) < RTOL * abs(e_ref.item())
+    H.assert_grads_close(g, {k: v.numpy() for k, v in g_ref.items()}, RTOL, 'active_dims')
