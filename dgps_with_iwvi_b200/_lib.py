@@ -17,6 +17,7 @@ FLAG_SAMPLE, FLAG_SAVE, FLAG_ACCUM = 1, 2, 4
 FLAG_ONLY_EPI, FLAG_ONLY_TILE, FLAG_ONLY_REDUCE, FLAG_ONLY_FINAL = 16, 32, 64, 128
 FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
 FLAG_NO_KDIAG = 4096
+FLAG_TWO_CHAINS = 8192
 
 ERRORS = {-1: 'bad descriptor', -2: 'unsupported size', -3: 'CUDA launch failure', -4: 'null pointer'}
 
@@ -54,6 +55,8 @@ SIGNATURES = {
     'iwvi_gp_rows_fwd_range': (C.c_int, [C.POINTER(GpDesc)] + [P] * 11 + [C.c_int64, C.c_int64, P]),
     'iwvi_gp_tile_points': (C.c_int, [C.POINTER(GpDesc)]),
     'iwvi_gp_rows_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 23),
+    'iwvi_gp_rows_bwd_range': (C.c_int, [C.POINTER(GpDesc)] + [P] * 22 + [C.c_int64, C.c_int64, P]),
+    'iwvi_gp_bwd_tile_points': (C.c_int, [C.POINTER(GpDesc)]),
     'iwvi_gp_prologue_bwd': (C.c_int, [C.POINTER(GpDesc)] + [P] * 16),
     'iwvi_gp_fullcov_fwd': (C.c_int, [C.POINTER(GpDesc), C.c_int32, C.c_int32] + [P] * 5 + [C.c_double] + [P] * 5),
     'iwvi_gp_fullcov_ws_doubles': (C.c_int64, [C.POINTER(GpDesc), C.c_int32, C.c_int32]),

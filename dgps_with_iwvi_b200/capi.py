@@ -133,6 +133,24 @@ def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, 
                                       _ptr(dW), _ptr(dmfA), _ptr(dmfb), _ptr(ws), _stream()), 'iwvi_gp_rows_bwd')
 
 
+def gp_rows_bwd_range(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu,
+                      dq_sqrt, dLm, dW, dmfA, dmfb, ws, point_begin, point_end):
+    only = d.flags & 240
+    _count(bin(only).count('1'))
+    L.check(L.load().iwvi_gp_rows_bwd_range(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(save), _ptr(X), _ptr(W), _ptr(mfA),
+                                            _ptr(mfb), _ptr(eps), _ptr(d_sample), _ptr(d_mean), _ptr(d_var), _ptr(dX),
+                                            _ptr(dZ), _ptr(dls), _ptr(dvariance), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(dLm),
+                                            _ptr(dW), _ptr(dmfA), _ptr(dmfb), _ptr(ws), int(point_begin), int(point_end),
+                                            _stream()), 'iwvi_gp_rows_bwd_range')
+
+
+def gp_bwd_tile_points(d):
+    tp = L.load().iwvi_gp_bwd_tile_points(C.byref(d))
+    if tp < 0:
+        L.check(tp, 'iwvi_gp_bwd_tile_points')
+    return tp
+
+
 def gp_prologue_bwd(d, Lm, aux, Z, ls, variance, q_mu, q_sqrt, dLm, dkl, dZ, dls, dvariance, dq_mu, dq_sqrt, ws):
     _count(1 if d.flags & L.FLAG_ONLY_KL else (5 if d.flags & L.FLAG_SKIP_KL else 6))
     L.check(L.load().iwvi_gp_prologue_bwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(Z), _ptr(ls), _ptr(variance),

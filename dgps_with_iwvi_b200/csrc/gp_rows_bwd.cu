@@ -96,7 +96,7 @@ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   w.off_gmb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_gvb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_epi = o;  o += (int64_t)w.n_epi * EPI_STRIDE;
-  w.off_tile = o; o += (int64_t)w.grid_tile * w.tile_stride;
+  w.off_tile = o; o += (int64_t)2 * w.grid_tile * w.tile_stride;   // per-CTA partials of the tile kernel: two point chains (see iwvi_gp_rows_bwd_range)
   w.off_red = o;  o += (int64_t)(d.R + 1) * w.S * w.npairs * IWVI_BLK * IWVI_BLK;
   w.off_qred = o; o += (int64_t)w.S * al.NB * IWVI_BLK * IWVI_MAX_R;
   w.total = o;
@@ -109,6 +109,10 @@ struct BwdParams {
   double *dX, *dZ, *dls, *dvariance, *dq_mu, *dq_sqrt, *dLm, *dW, *dmfA, *dmfb, *ws;
   BwdWs wl;
   int ntiles, grid_tile;
+  int tile0, tile1;   // tile kernel: tiles [tile0, tile1) of this launch
+  int slot0;          // tile kernel: first per-CTA partial slot of this launch (0: first chain, nsm: second chain)
+  int n_slots;        // tile kernel: slots per chain; a ranged launch zeroes the slots of its chain that its grid does not own
+  int epi0;           // epilogue kernel: first 32-point CTA of this launch
   int q_lo;      // reduce kernel: first matrix index of this launch (0 .. R; R == dLm)
   int q_n;       // reduce kernel: number of matrices of this launch
   int fin_part;  // finalize kernel: 0 = everything, 1 = part A outputs, 2 = part B outputs
@@ -132,7 +136,8 @@ __global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
   double* gmb = p.ws + p.wl.off_gmb;
   double* gvb = p.ws + p.wl.off_gvb;
   const int tid = threadIdx.x;
-  const int p0 = blockIdx.x * EPI_PTS;
+  const int epi_cta = blockIdx.x + p.epi0;
+  const int p0 = epi_cta * EPI_PTS;
   const int npts = max(0, min(EPI_PTS, T - p0));     // real points of this CTA (the rest are zero padding)
   for (int idx = tid; idx < EPI_PTS * P; idx += 256) {
     const int n = idx / P, q = idx - n * P;
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
       p.dX[(size_t)p0 * D + idx] = (d.mf == IWVI_MF_IDENTITY) ? ds[n][k] + dm[n][k] : 0.0;
     }
   }
-  double* part = p.ws + p.wl.off_epi + (size_t)blockIdx.x * EPI_STRIDE;
+  double* part = p.ws + p.wl.off_epi + (size_t)epi_cta * EPI_STRIDE;
   // (the Kdiag term of dvariance: d fvar / d variance = 1 per point and output; absent when the caller handles the prior
   //  covariance k(X, X) itself, IWVI_FLAG_NO_KDIAG -- the full-covariance adjoint in gp_fullcov.cu)
   const double tot = block_sum(gv_sum, red);
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     const SaveLayout svp = iwvi_save_layout(T, M, R);
     seq.A_T = p.save + svp.off_a; seq.U_T = p.save + svp.off_u; seq.u_stride = svp.u_stride;
     seq.tp_bytes = TP * IWVI_LDS * 8;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
       seq.init(tile * TP);
       while (!seq.done()) { pipe.produce(seq.get(), lane); seq.advance(); }
     }
@@ -428,10 +433,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   const double* gmb = p.ws + p.wl.off_gmb;
   const double* gvb = p.ws + p.wl.off_gvb;
   double* bbar_T = p.ws + p.wl.off_bbar;
-  double* mypart = p.ws + p.wl.off_tile + (size_t)blockIdx.x * p.wl.tile_stride;
+  double* mypart = p.ws + p.wl.off_tile + (size_t)(p.slot0 + blockIdx.x) * p.wl.tile_stride;
 
   // this CTA's partial of dZ (accumulated across its tiles in global memory, exclusive owner) and dls
   for (int idx = tid; idx < p.wl.tile_stride; idx += 256) mypart[idx] = 0.0;
+  // one of two point chains (iwvi_gp_rows_bwd_range): the finalize kernel will sum ALL slots of both chains, and the slots
+  // of this chain beyond this launch's grid may hold partials of an earlier call -- clear them (no other launch touches
+  // this chain's slots before the finalize kernel reads them)
+  if (p.n_slots > 0)
+    for (int s2 = blockIdx.x + gridDim.x; s2 < p.n_slots; s2 += gridDim.x) {
+      double* other = p.ws + p.wl.off_tile + (size_t)(p.slot0 + s2) * p.wl.tile_stride;
+      for (int idx = tid; idx < p.wl.tile_stride; idx += 256) other[idx] = 0.0;
+    }
   dls_s[tid] = 0.0;
   double dvar_acc = 0.0;
   // lengthscale adjoint: sum_mn G_mn (x~_nd - z~_md)^2 = sum_n colsum_n x~_nd^2 + sum_m z~_md (rowsum_m z~_md - 2 (G x~)_md),
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   for (int b = 0; b < 4; b++) { dl_acc[b][0] = 0.0; dl_acc[b][1] = 0.0; }
 
   PHASE_DECL;
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  for (int tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
     const int n0 = tile * TP;
     named_bar_sync(BAR_ALL, 256);
     PHASE_MARK(7);
@@ -1151,7 +1164,8 @@ static int launch_tile_k(const BwdParams& p, int smem_bytes, cudaStream_t st) {
   if (!pool_ok) return IWVI_ERR_LAUNCH;
   if (cudaFuncSetAttribute(gp_tile_bwd_kernel<TP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return IWVI_ERR_LAUNCH;
-  gp_tile_bwd_kernel<TP, KIND><<<p.grid_tile, TILE_THREADS, smem_bytes, st>>>(p);
+  const int grid = (p.tile1 - p.tile0) < p.grid_tile ? (p.tile1 - p.tile0) : p.grid_tile;
+  gp_tile_bwd_kernel<TP, KIND><<<grid, TILE_THREADS, smem_bytes, st>>>(p);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
 }
@@ -1194,12 +1208,22 @@ extern "C" int64_t iwvi_gp_bwd_ws_doubles(const iwvi_gp_desc* d) {
   return bwd_ws_layout(*d, nsm).total;
 }
 
-extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
-                                const double* X, const double* W, const double* mfA, const double* mfb,
-                                const double* eps, const double* d_sample, const double* d_mean, const double* d_var,
-                                double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu,
-                                double* dq_sqrt, double* dLm, double* dW, double* dmfA, double* dmfb, double* ws,
-                                void* stream) {
+extern "C" int iwvi_gp_bwd_tile_points(const iwvi_gp_desc* d) {
+  if (iwvi_check_gp_desc(d) != IWVI_OK) return IWVI_ERR_BAD_DESC;
+  int nsm = 148, max_smem = 0;
+  if (device_info(&nsm, &max_smem) != IWVI_OK) return IWVI_ERR_LAUNCH;
+  const AuxLayout al = iwvi_aux_layout(d->M, d->D, d->R);
+  int smem_bytes = 0;
+  const int TP = pick_bwd_tp(iwvi_round_up(d->T, 128), al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
+  return TP < 0 ? IWVI_ERR_UNSUPPORTED : TP;
+}
+
+static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
+                         const double* X, const double* W, const double* mfA, const double* mfb,
+                         const double* eps, const double* d_sample, const double* d_mean, const double* d_var,
+                         double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu,
+                         double* dq_sqrt, double* dLm, double* dW, double* dmfA, double* dmfb, double* ws,
+                         int64_t point_begin, int64_t point_end, bool ranged, void* stream) {
   int rc = iwvi_check_gp_desc(d);
   if (rc != IWVI_OK) return rc;
   if (!Lm || !aux || !save || !X || !dX || !dZ || !dls || !dvariance || !dq_mu || !dq_sqrt || !dLm || !ws)
@@ -1226,9 +1250,27 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   cudaStream_t st = (cudaStream_t)stream;
   const int only = d->flags & IWVI_FLAG_ONLY_MASK;
   p.q_lo = 0; p.q_n = d->R + 1; p.fin_part = 0;
+  p.tile0 = 0; p.tile1 = p.ntiles; p.slot0 = 0; p.n_slots = 0; p.epi0 = 0;
+  int n_epi = p.wl.n_epi;
+  if (ranged) {
+    // one of the two point chains of the per-point half: [0, point_end) or [point_begin, T)
+    if (!only || (only & (IWVI_FLAG_ONLY_REDUCE | IWVI_FLAG_ONLY_FINAL))) return IWVI_ERR_BAD_DESC;
+    if (point_begin < 0 || point_end > d->T || point_begin >= point_end) return IWVI_ERR_BAD_DESC;
+    if (point_begin != 0 && point_end != d->T) return IWVI_ERR_BAD_DESC;
+    if (point_begin % TP || (point_end != d->T && point_end % TP)) return IWVI_ERR_BAD_DESC;
+    p.tile0 = (int)(point_begin / TP);
+    p.tile1 = point_end == d->T ? p.ntiles : (int)(point_end / TP);
+    p.epi0 = (int)(point_begin / EPI_PTS);
+    n_epi = (point_end == d->T ? p.wl.n_epi : (int)(point_end / EPI_PTS)) - p.epi0;
+    p.n_slots = nsm;
+    if (point_begin != 0) {
+      if (p.tile1 - p.tile0 > nsm) return IWVI_ERR_UNSUPPORTED;   // the second chain runs one tile per CTA, one slot each
+      p.slot0 = nsm;
+    }
+  }
 
   if (!only || (only & IWVI_FLAG_ONLY_EPI)) {
-    gp_epi_bwd_kernel<<<p.wl.n_epi, 256, 0, st>>>(p);
+    gp_epi_bwd_kernel<<<n_epi, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
 
@@ -1256,8 +1298,30 @@ extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const d
   if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {
     const FinalLayout fl = final_layout(*d, p.wl);
     p.fin_part = (do_a && do_b) ? 0 : (do_a ? 1 : 2);
+    // the per-CTA partials of the tile kernel: one chain's slots, or (IWVI_FLAG_TWO_CHAINS) both chains' slots
+    if (d->flags & IWVI_FLAG_TWO_CHAINS) p.grid_tile = 2 * nsm;
     gp_finalize_bwd_kernel<<<fl.grid_elem + fl.grid_warp, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }
   return IWVI_OK;
+}
+
+extern "C" int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
+                                const double* X, const double* W, const double* mfA, const double* mfb,
+                                const double* eps, const double* d_sample, const double* d_mean, const double* d_var,
+                                double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu,
+                                double* dq_sqrt, double* dLm, double* dW, double* dmfA, double* dmfb, double* ws,
+                                void* stream) {
+  return rows_bwd_impl(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu,
+                       dq_sqrt, dLm, dW, dmfA, dmfb, ws, 0, d ? d->T : 0, false, stream);
+}
+
+extern "C" int iwvi_gp_rows_bwd_range(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
+                                      const double* X, const double* W, const double* mfA, const double* mfb,
+                                      const double* eps, const double* d_sample, const double* d_mean,
+                                      const double* d_var, double* dX, double* dZ, double* dls, double* dvariance,
+                                      double* dq_mu, double* dq_sqrt, double* dLm, double* dW, double* dmfA, double* dmfb,
+                                      double* ws, int64_t point_begin, int64_t point_end, void* stream) {
+  return rows_bwd_impl(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu,
+                       dq_sqrt, dLm, dW, dmfA, dmfb, ws, point_begin, point_end, true, stream);
 }

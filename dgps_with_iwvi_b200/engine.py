@@ -252,6 +252,9 @@ class Engine:
         # chain of the full waves on the main stream and the chain of the remaining tiles on a second stream; the two
         # never exchange data before the likelihood, and the remainder's CTAs fill the SMs the other chain leaves free.
         self.split = None
+        self.split_bwd = None
+        self.ev_bwd0 = torch.cuda.Event()
+        self.ev_rows_b = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.side_f = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         gps = [r for r in self.recs if r['type'] == 'gp']
@@ -265,6 +268,16 @@ class Engine:
                 full = tiles // nsm * nsm
                 if full > 0 and tiles - full >= nsm // 8:
                     self.split = full * tp
+            # the same for the per-point half of the backward pass (its tile width may differ from the forward's)
+            if self.train:
+                tpb = {capi.gp_bwd_tile_points(r['d']) for r in gps}
+                if len(tpb) == 1:
+                    tp = tpb.pop()
+                    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+                    tiles = -(-T // tp)
+                    full = tiles // nsm * nsm
+                    if full > 0 and tiles - full >= nsm // 8:
+                        self.split_bwd = full * tp
 
     # ------------------------------------------------------------------------------------------
     def _cv(self, p):
@@ -423,6 +436,10 @@ class Engine:
         lik_p = self.model.likelihood.variance
         capi.iwelbo_bwd(self.ed, last['mean'], last['var'], self.Y, self._cv(lik_p), self.w, self.one, self.dmean,
                         self.dvar, self.dkl_local, flat.gview(lik_p), self.elbo_ws)
+        two = self.split_bwd is not None
+        if two:                # the remainder's chain of per-point launches starts here, on its own stream
+            self.ev_bwd0.record(torch.cuda.current_stream())
+            self.side_f.wait_event(self.ev_bwd0)
         d_next = None          # cotangent of the current layer's output samples
         lv_off = self.Lw_total
         for r in reversed(self.recs):
@@ -450,11 +467,25 @@ class Engine:
                         self.dmean if is_last else None, self.dvar if is_last else None,
                         r['dX'], outs[0], outs[1], outs[2], outs[3], outs[4], r['dLm'], gW, gA, gb, r['bwd_ws'])
                 fl = r['d'].flags
-                capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE), *args)
                 main = torch.cuda.current_stream()
                 gi = r['gi']
-                self.ev_rows[gi].record(main)
                 side = self.side[gi]
+                if two:
+                    # Points are independent through the backward chain of GP layers too: the full waves of tiles run on
+                    # the main stream, the remaining tiles (one per CTA) as a second chain whose CTAs fill the SMs the
+                    # last wave of every layer leaves idle; the parameter reductions wait for both.
+                    dpt = capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE)
+                    capi.gp_rows_bwd_range(dpt, *args, 0, self.split_bwd)
+                    with torch.cuda.stream(self.side_f):
+                        capi.gp_rows_bwd_range(dpt, *args, self.split_bwd, self.T)
+                        self.ev_rows_b[gi].record(self.side_f)
+                    fl |= LIB.FLAG_TWO_CHAINS
+                    side.wait_event(self.ev_rows_b[gi])
+                    if gi == 0:
+                        self.side_b.wait_event(self.ev_rows_b[gi])
+                else:
+                    capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE), *args)
+                self.ev_rows[gi].record(main)
                 side.wait_event(self.ev_rows[gi])
                 pargs = (r['Lm'], r['aux'], self._cv(feat.Z), r['ls'], self._cv(base.variance), self._cv(layer.q_mu),
                          self._cv(layer.q_sqrt), r['dLm'], self.dkl, outs[0], outs[1], outs[2], outs[3], outs[4],
@@ -488,6 +519,9 @@ class Engine:
                         self.ev_pbwd[gi].record(side)
                 d_next = r['dX']
             else:
+                if two:        # (a latent-variable layer only ever sits below the GP chain when the pass is split)
+                    torch.cuda.current_stream().wait_event(self.ev_rows_b[0])
+                    two = False
                 Lw = r['Lw']
                 lv_off -= Lw
                 if len(self.lv_recs) > 1:
@@ -504,6 +538,8 @@ class Engine:
                         o += p.size
                 d_next = r.get('dF')
         main = torch.cuda.current_stream()
+        if two:                # no latent-variable layer below the GP chain: join the remainder's chain here
+            main.wait_event(self.ev_rows_b[0])
         for ev in self.ev_pbwd:
             main.wait_event(ev)
         if self.n_gp:

@@ -88,6 +88,9 @@ extern "C" {
 #define IWVI_FLAG_PART_B   512
 #define IWVI_FLAG_SKIP_KL  1024
 #define IWVI_FLAG_ONLY_KL  2048
+/* iwvi_gp_rows_bwd (REDUCE / FINAL launches): the per-point half ran as two point chains (iwvi_gp_rows_bwd_range): sum the
+ * per-CTA partials of both. */
+#define IWVI_FLAG_TWO_CHAINS 8192
 /* iwvi_gp_rows_bwd: leave the Kdiag term (d var / d variance = 1 per point) out of dvariance -- set by callers that
  * differentiate the prior covariance k(X, X) themselves (iwvi_gp_fullcov_bwd). */
 #define IWVI_FLAG_NO_KDIAG 4096
@@ -161,6 +164,22 @@ int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux,
                      const double* d_sample, const double* d_mean, const double* d_var,
                      double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu, double* dq_sqrt,
                      double* dLm, double* dW, double* dmfA, double* dmfb, double* ws, void* stream);
+
+/*
+ * The per-point half of iwvi_gp_rows_bwd (flags: IWVI_FLAG_ONLY_EPI and / or IWVI_FLAG_ONLY_TILE) over one of TWO point
+ * chains: [0, point_end) or [point_begin, T), split on a multiple of iwvi_gp_bwd_tile_points(d).  Points are independent
+ * through the whole backward chain of GP layers as they are through the forward one, so the caller can run the chain of
+ * the full waves of tiles and the chain of the remainder on two streams (the remainder, at most one tile per SM, fills
+ * the SMs the last wave leaves idle); the parameter half (REDUCE / FINAL, which contracts over ALL points) then runs
+ * once both have finished, with IWVI_FLAG_TWO_CHAINS.  All pointers and the descriptor are those of the whole call.
+ */
+int iwvi_gp_rows_bwd_range(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* save,
+                           const double* X, const double* W, const double* mfA, const double* mfb, const double* eps,
+                           const double* d_sample, const double* d_mean, const double* d_var,
+                           double* dX, double* dZ, double* dls, double* dvariance, double* dq_mu, double* dq_sqrt,
+                           double* dLm, double* dW, double* dmfA, double* dmfb, double* ws,
+                           int64_t point_begin, int64_t point_end, void* stream);
+int iwvi_gp_bwd_tile_points(const iwvi_gp_desc* d);    /* points per tile of the backward tile kernel for d */
 
 /*
  * Adjoint of iwvi_gp_prologue_fwd: Cholesky adjoint (TF CholeskyGrad), gram adjoint of Kuu and the KL

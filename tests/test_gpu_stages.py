@@ -452,3 +452,61 @@ def test_batch_gather_one_launch():
     XY2 = torch.zeros_like(XYb)
     capi.batch_gather(Xb, Yb, None, B, Dx, Dy, None, None, XY2)
     assert torch.equal(XY2, XYb)
+
+
+@pytest.mark.parametrize('T,M,split', [(20000, 100, 296 * 64), (9700, 64, 148 * 64)])
+def test_rows_bwd_range_two_chains_equal_whole_call(T, M, split):
+    """iwvi_gp_rows_bwd_range: the per-point half (EPI | TILE) over [0, split) and [split, T) on two streams, then the
+    parameter half with IWVI_FLAG_TWO_CHAINS, against the whole call: dX and Bbar-dependent outputs bit for bit, the
+    gradients that go through per-CTA partials (dZ, dls, dvariance) to summation order; bad ranges are rejected."""
+    import ctypes as C
+    from dgps_with_iwvi_b200 import capi
+    from dgps_with_iwvi_b200 import _lib as LIB
+    D, R, P = 5, 3, 4
+    rng = np.random.default_rng(T + M + 1)
+    L = make_layer(rng, T, M, D, R, P, True, 'Linear', 'RBF')
+    g = run_prologue(L)
+    d = capi.with_flags(g['d'], LIB.FLAG_SAMPLE | LIB.FLAG_SAVE)
+    t = dev
+    X, W, mfA, mfb, eps = t(L['X']), t(L['W']), t(L['mfA']), t(L['mfb']), t(L['eps'])
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64, device='cuda')
+    smp, mean, var, save = z(T, P), z(T, P), z(T, P), z(capi.gp_save_doubles(d))
+    capi.gp_rows_fwd(d, g['Lm'], g['aux'], X, W, mfA, mfb, eps, smp, mean, var, save)
+    ds, dm, dv = (t(rng.standard_normal((T, P))) for _ in range(3))
+    Mp = capi.gp_mp(M)
+    tp = capi.gp_bwd_tile_points(d)
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    tiles = -(-T // tp)
+    assert tp in (32, 64) and split == tiles // nsm * nsm * tp
+
+    def outs():
+        return dict(dX=z(T, D), dZ=z(M, D), dls=z(D), dvar=z(1), dqm=z(M, R), dqs=z(R, M, M), dLm=z(Mp, Mp), dW=z(P, R),
+                    dA=z(D, P), db=z(P), ws=z(capi.gp_bwd_ws_doubles(d)))
+
+    def args(o):
+        return (g['Lm'], g['aux'], save, X, W, mfA, mfb, eps, ds, dm, dv, o['dX'], o['dZ'], o['dls'], o['dvar'], o['dqm'],
+                o['dqs'], o['dLm'], o['dW'], o['dA'], o['db'], o['ws'])
+    a, b = outs(), outs()
+    capi.gp_rows_bwd(d, *args(a))
+    pt = capi.with_flags(d, d.flags | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE)
+    s2 = torch.cuda.Stream()
+    ev0, ev1 = torch.cuda.Event(), torch.cuda.Event()
+    ev0.record()
+    capi.gp_rows_bwd_range(pt, *args(b), 0, split)
+    s2.wait_event(ev0)
+    with torch.cuda.stream(s2):
+        capi.gp_rows_bwd_range(pt, *args(b), split, T)
+        ev1.record(s2)
+    torch.cuda.current_stream().wait_event(ev1)
+    capi.gp_rows_bwd(capi.with_flags(d, d.flags | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL | LIB.FLAG_TWO_CHAINS), *args(b))
+    torch.cuda.synchronize()
+    for k in ('dX', 'dqm', 'dqs', 'dLm'):
+        assert torch.equal(a[k], b[k]), k
+    for k in ('dZ', 'dls', 'dvar', 'dW', 'dA', 'db'):
+        assert (a[k] - b[k]).abs().max().item() <= 1e-12 * a[k].abs().max().item(), k
+    lib = LIB.load()
+    ptrs = [x.data_ptr() if x is not None else None for x in args(b)]
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.iwvi_gp_rows_bwd_range(C.byref(pt), *ptrs, 0, 100, st) == -1            # not on a tile boundary
+    assert lib.iwvi_gp_rows_bwd_range(C.byref(pt), *ptrs, 64, 128, st) == -1           # neither [0, e) nor [b, T)
+    assert lib.iwvi_gp_rows_bwd_range(C.byref(d), *ptrs, 0, split, st) == -1           # parameter half cannot be ranged
