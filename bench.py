@@ -363,7 +363,13 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # the gradient segments are exchanged while compute kernels with hundreds of queued CTAs are running: NCCL's
+        # kernels go on a high-priority stream so that they are dispatched as soon as SMs free up
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), pg_options=opts)
+        except (AttributeError, TypeError):
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from dgps_with_iwvi_b200 import capi
     from dgps_with_iwvi_b200 import _lib as LIB
     from dgps_with_iwvi_b200.build_models import build_model, spec_from_model

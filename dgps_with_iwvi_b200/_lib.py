@@ -18,6 +18,7 @@ FLAG_ONLY_EPI, FLAG_ONLY_TILE, FLAG_ONLY_REDUCE, FLAG_ONLY_FINAL = 16, 32, 64, 1
 FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
 FLAG_NO_KDIAG = 4096
 FLAG_TWO_CHAINS = 8192
+FLAG_PRO_HYP, FLAG_PRO_Q = 16384, 32768
 
 ERRORS = {-1: 'bad descriptor', -2: 'unsupported size', -3: 'CUDA launch failure', -4: 'null pointer'}
 
@@ -73,8 +74,11 @@ SIGNATURES = {
     'iwvi_normal_fill': (C.c_int, [P, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, P]),
     'iwvi_normal_fill_counter': (C.c_int, [P, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int64, P, P]),
     'iwvi_adam_step_counter': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, P, C.c_double, C.c_double, C.c_double, P, P]),
+    'iwvi_adam_step_counter_part': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, P, C.c_double, C.c_double, C.c_double, P,
+                                               C.c_int32, P]),
     'iwvi_positive_fwd': (C.c_int, [P, P, C.c_int64, P]),
     'iwvi_batch_gather': (C.c_int, [P, P, P, C.c_int32, C.c_int32, C.c_int32, P, P, P, P]),
+    'iwvi_debug_stamp': (C.c_int, [P, C.c_int32, P]),
     'iwvi_probe_dmma': (C.c_int, [P, C.c_int32, C.c_int32, C.c_int32, P]),
     'iwvi_adam_step': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int64, P]),

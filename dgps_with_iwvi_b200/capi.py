@@ -237,6 +237,13 @@ def adam_step_counter(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr_dev, bet
                                             _stream()), 'iwvi_adam_step_counter')
 
 
+def adam_step_counter_part(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr_dev, beta1, beta2, eps, state, advance):
+    _count(2 if advance else 1)
+    L.check(L.load().iwvi_adam_step_counter_part(_ptr(x), _ptr(grad_elbo), _ptr(m), _ptr(v), _ptr(mask), _ptr(theta_pos),
+                                                 int(n), int(n_pos), _ptr(lr_dev), float(beta1), float(beta2), float(eps),
+                                                 _ptr(state), int(bool(advance)), _stream()), 'iwvi_adam_step_counter_part')
+
+
 def positive_fwd(x, theta, n):
     _count(1)
     L.check(L.load().iwvi_positive_fwd(_ptr(x), _ptr(theta), int(n), _stream()), 'iwvi_positive_fwd')

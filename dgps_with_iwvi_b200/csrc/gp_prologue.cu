@@ -25,6 +25,7 @@ struct ProParams {
   const double *Z, *ls, *variance, *q_mu, *q_sqrt;
   double *Lm, *aux, *kl;
   int32_t* info;
+  int mode;   // 0: everything; 1 (IWVI_FLAG_PRO_HYP): what depends on Z / kernel parameters; 2 (IWVI_FLAG_PRO_Q): on q_mu / q_sqrt
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -58,17 +59,28 @@ __global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
     }
   } else {
     const int gtid = blockIdx.x * 256 + threadIdx.x, gsz = IWVI_PACK_SMALL * 256;
-    // Zt = Z / ls
-    for (int e = gtid; e < Mp * ldz; e += gsz) {
-      const int m = e / ldz, k = e - m * ldz;
-      aux[al.off_zt + e] = (m < M && k < D) ? p.Z[(size_t)m * D + k] / p.ls[k] : 0.0;
+    if (p.mode != 2) {
+      // Zt = Z / ls
+      for (int e = gtid; e < Mp * ldz; e += gsz) {
+        const int m = e / ldz, k = e - m * ldz;
+        aux[al.off_zt + e] = (m < M && k < D) ? p.Z[(size_t)m * D + k] / p.ls[k] : 0.0;
+      }
+      for (int m = gtid; m < Mp; m += gsz) {
+        double s = 0.0;
+        if (m < M)
+          for (int k = 0; k < D; k++) { const double v = p.Z[(size_t)m * D + k] / p.ls[k]; s += v * v; }
+        aux[al.off_zn + m] = s;
+      }
+      if (gtid < 64) {
+        double v = 0.0;
+        if (gtid == IWVI_C_VARIANCE) v = p.variance[0];
+        else if (gtid >= IWVI_C_INVLS && gtid < IWVI_C_INVLS + D) v = 1.0 / p.ls[gtid - IWVI_C_INVLS];
+        aux[al.off_consts + gtid] = v;
+      }
+      if (gtid < 16) reinterpret_cast<int*>(aux + al.off_prog)[gtid] = 0;   // Cholesky hand-off counters
+      if (gtid == 0) p.info[0] = 0;
     }
-    for (int m = gtid; m < Mp; m += gsz) {
-      double s = 0.0;
-      if (m < M)
-        for (int k = 0; k < D; k++) { const double v = p.Z[(size_t)m * D + k] / p.ls[k]; s += v * v; }
-      aux[al.off_zn + m] = s;
-    }
+    if (p.mode == 1) return;      // the q_mu / q_sqrt dependent half (and its KL partials) belongs to the other call
     // q_mu padded to [Mp, 8]; mahalanobis term of the KL
     for (int e = gtid; e < Mp * IWVI_MAX_R; e += gsz) {
       const int m = e / IWVI_MAX_R, r = e - m * IWVI_MAX_R;
@@ -76,17 +88,21 @@ __global__ void __launch_bounds__(256) gp_pack_kernel(const ProParams p) {
       if (m < M && r < R) { v = p.q_mu[(size_t)m * R + r]; klp += v * v; }
       aux[al.off_qmu + e] = v;
     }
-    if (gtid < 64) {
-      double v = 0.0;
-      if (gtid == IWVI_C_VARIANCE) v = p.variance[0];
-      else if (gtid >= IWVI_C_INVLS && gtid < IWVI_C_INVLS + D) v = 1.0 / p.ls[gtid - IWVI_C_INVLS];
-      aux[al.off_consts + gtid] = v;
-    }
-    if (gtid < 16) reinterpret_cast<int*>(aux + al.off_prog)[gtid] = 0;   // Cholesky hand-off counters
-    if (gtid == 0) p.info[0] = 0;
   }
   const double tot = block_sum(klp, red);
   if (threadIdx.x == 0) aux[al.off_scratch + blockIdx.x] = tot;
+}
+
+// final KL sum in the fixed order of the pack launch's CTAs (what the last Cholesky row does when both halves run together)
+__global__ void gp_kl_sum_kernel(const ProParams p) {
+  const iwvi_gp_desc& d = p.d;
+  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    const int nparts = IWVI_PACK_SMALL + d.R * al.npairs;
+    for (int q = 0; q < nparts; q++) s += p.aux[al.off_scratch + q];
+    p.kl[0] = 0.5 * (s - (double)d.M * (double)d.R);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,7 +420,7 @@ __global__ void __launch_bounds__(256, 1) gp_chol_kernel(const ProParams p) {
     }
   }
   if (i == NB - 1) PHASE_FLUSH(2);
-  if (i == NB - 1 && tid == 0) {   // the last row depends on every other row: it finishes last
+  if (i == NB - 1 && tid == 0 && p.mode == 0) {   // the last row depends on every other row: it finishes last
     double s = 0.0;
     const int nparts = IWVI_PACK_SMALL + d.R * al.npairs;   // CTAs of this layer's pack launch
     for (int q = 0; q < nparts; q++) s += aux[al.off_scratch + q];
@@ -747,9 +763,18 @@ extern "C" int iwvi_gp_prologue_fwd(const iwvi_gp_desc* d, const double* Z, cons
   ProParams p;
   p.d = *d; p.Z = Z; p.ls = ls; p.variance = variance; p.q_mu = q_mu; p.q_sqrt = q_sqrt;
   p.Lm = Lm; p.aux = aux; p.kl = kl; p.info = info;
+  const bool hyp = (d->flags & IWVI_FLAG_PRO_HYP) != 0, qq = (d->flags & IWVI_FLAG_PRO_Q) != 0;
+  if (hyp && qq) return IWVI_ERR_BAD_DESC;
+  p.mode = hyp ? 1 : (qq ? 2 : 0);
   cudaStream_t st = (cudaStream_t)stream;
-  gp_pack_kernel<<<IWVI_PACK_SMALL + d->R * iwvi_aux_layout(d->M, d->D, d->R).npairs, 256, 0, st>>>(p);
+  const int pack_grid = hyp ? IWVI_PACK_SMALL : IWVI_PACK_SMALL + d->R * iwvi_aux_layout(d->M, d->D, d->R).npairs;
+  gp_pack_kernel<<<pack_grid, 256, 0, st>>>(p);
   IWVI_CHECK_LAUNCH();
+  if (qq) {
+    gp_kl_sum_kernel<<<1, 32, 0, st>>>(p);
+    IWVI_CHECK_LAUNCH();
+    return IWVI_OK;
+  }
   const int smem_bytes = (5 * IWVI_STAGE_DOUBLES + 2 * IWVI_BLK * 36) * 8;
   switch (d->kern) {
     case IWVI_KERN_RBF: return launch_chol<IWVI_KERN_RBF>(p, smem_bytes, st);

@@ -438,14 +438,16 @@ __global__ void adam_kernel(double* x, const double* g_elbo, double* m, double* 
     lr_t = lr_dev[0] * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // masked-out entries are not in the optimiser's var_list (set_trainable(False)) or belong to another segment of a
+    // step that updates the parameters segment by segment: value, moments and constrained copy stay as they are
+    if (mask && mask[i] == 0.0) continue;
     double xi = x[i];
     double g = -g_elbo[i];                         // the optimiser minimises -ELBO
     if (i < n_pos) g *= sigmoid_d(xi);             // d softplus(x) / dx
-    if (mask) g *= mask[i];
     const double mi = b1 * m[i] + (1.0 - b1) * g;
     const double vi = b2 * v[i] + (1.0 - b2) * g * g;
     m[i] = mi; v[i] = vi;
-    if (!mask || mask[i] != 0.0) xi -= lr_t * mi / (sqrt(vi) + eps);
+    xi -= lr_t * mi / (sqrt(vi) + eps);
     x[i] = xi;
     if (i < n_pos) theta_pos[i] = softplus_d(xi) + 1e-6;
   }
@@ -646,9 +648,9 @@ extern "C" int iwvi_adam_step(double* x, const double* grad_elbo, double* m, dou
   return IWVI_OK;
 }
 
-extern "C" int iwvi_adam_step_counter(double* x, const double* grad_elbo, double* m, double* v, const double* mask,
-                                      double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1,
-                                      double beta2, double eps, int64_t* state, void* stream) {
+extern "C" int iwvi_adam_step_counter_part(double* x, const double* grad_elbo, double* m, double* v, const double* mask,
+                                           double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1,
+                                           double beta2, double eps, int64_t* state, int32_t advance, void* stream) {
   if (!x || !grad_elbo || !m || !v || !lr || !state) return IWVI_ERR_NULL;
   if (n_pos > 0 && !theta_pos) return IWVI_ERR_NULL;
   if (n <= 0) return IWVI_ERR_BAD_DESC;
@@ -657,9 +659,17 @@ extern "C" int iwvi_adam_step_counter(double* x, const double* grad_elbo, double
   adam_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, 0.0, beta1, beta2,
                                                         eps, state, lr);
   IWVI_CHECK_LAUNCH();
-  step_counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
-  IWVI_CHECK_LAUNCH();
+  if (advance) {
+    step_counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    IWVI_CHECK_LAUNCH();
+  }
   return IWVI_OK;
+}
+
+extern "C" int iwvi_adam_step_counter(double* x, const double* grad_elbo, double* m, double* v, const double* mask,
+                                      double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1,
+                                      double beta2, double eps, int64_t* state, void* stream) {
+  return iwvi_adam_step_counter_part(x, grad_elbo, m, v, mask, theta_pos, n, n_pos, lr, beta1, beta2, eps, state, 1, stream);
 }
 
 #ifdef IWVI_PHASE_TIMING

@@ -21,7 +21,23 @@ __global__ void probe_dmma_kernel(double* out, int iters) {
   for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+__global__ void debug_stamp_kernel(unsigned long long* slots, int idx) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  slots[idx] = t;
+}
 }  // namespace
+
+// Measurement utility: writes the GPU's global nanosecond timer to slots[idx] when the stream reaches this point (a
+// one-thread kernel, capturable into a CUDA graph): tools/graph_timeline.py brackets every launch of a replayed training
+// step with these to see which chains are exposed.
+extern "C" int iwvi_debug_stamp(unsigned long long* slots, int32_t idx, void* stream) {
+  if (!slots) return IWVI_ERR_NULL;
+  if (idx < 0) return IWVI_ERR_BAD_DESC;
+  debug_stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slots, idx);
+  IWVI_CHECK_LAUNCH();
+  return IWVI_OK;
+}
 
 extern "C" int iwvi_probe_dmma(double* out, int32_t blocks, int32_t warps, int32_t iters, void* stream) {
   if (!out) return IWVI_ERR_NULL;

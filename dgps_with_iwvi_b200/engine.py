@@ -231,6 +231,12 @@ class Engine:
         # once-per-layer prologue stages (Cholesky, KL and their adjoints) depend only on the parameters: they run on
         # side streams, concurrently with each other and with the per-point stages of other layers
         self.side = [torch.cuda.Stream(device=dev) for _ in range(self.n_gp)]
+        # The latency chains (Cholesky of Kuu; Cholesky / gram adjoints; the trainer's segment update + next-step
+        # factorisation) are a few CTAs each and sit on the step's critical path, while the kernels they overlap with
+        # queue hundreds of CTAs: on a HIGH-PRIORITY stream their blocks are dispatched as soon as an SM frees up instead
+        # of after the last wave of whatever throughput kernel was launched before them.
+        self.hp = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(self.n_gp)]
+        self.ev_red = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.ev_start = torch.cuda.Event()
         self.ev_pro = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.ev_rows = [torch.cuda.Event() for _ in range(self.n_gp)]
@@ -239,9 +245,10 @@ class Engine:
         self.ev_part_b = torch.cuda.Event()
         self.ev_elbo, self.ev_loss = torch.cuda.Event(), torch.cuda.Event()
         self._loss_pending = False
-        # data-parallel training: called as grad_hook(tag) on the stream where the gradients named by `tag` have just been
-        # completed -- ('gp', gi): every parameter of GP layer gi > 0; ('gp_q', 0): q_mu / q_sqrt of the first GP layer --
-        # so that their all-reduce overlaps with the rest of the backward pass (training.Trainer); None: no hook
+        # training: called as grad_hook(tag) on the stream where the gradients named by `tag` have just been completed --
+        # ('gp', gi): every parameter of GP layer gi > 0; ('gp_h', 0): inducing inputs / kernel / mixing / mean-function
+        # parameters of the first GP layer; ('gp_q', 0): its q_mu / q_sqrt -- so that their all-reduce, their update and the
+        # next step's factorisation overlap with the rest of the backward pass (training.Trainer); None: no hook
         self.grad_hook = None
         self.X_tiled = None
         if self.recs[0]['type'] == 'gp' or not self.recs[0].get('bcast', False):
@@ -324,28 +331,39 @@ class Engine:
             else:
                 capi.normal_fill(buf, self.T, buf.shape[1], first, layer_seed(seed, step + step_add, r['idx']))
 
-    def forward(self, join=True):
+    def prologue_layer(self, r, part=0):
+        """Once-per-step stage of GP layer `r` on the CURRENT stream: scaled inducing inputs, Cholesky of Kuu, padded
+        variational parameters, KL.  part: 0 everything, LIB.FLAG_PRO_HYP / LIB.FLAG_PRO_Q one half (include/iwvi_b200.h)."""
+        base, feat, layer = r['base'], r['feat'], r['layer']
+        if r['ard']:
+            ls = self._cv(base.lengthscales)
+        else:
+            if part != LIB.FLAG_PRO_Q:
+                r['ls_vec'].copy_(base.full_lengthscales(self._cv(base.lengthscales).reshape(-1), r['D']))
+            ls = r['ls_vec']
+        r['ls'] = ls
+        d = r['d'] if not part else capi.with_flags(r['d'], r['d'].flags | part)
+        capi.gp_prologue_fwd(d, self._cv(feat.Z), ls, self._cv(base.variance), self._cv(layer.q_mu),
+                             self._cv(layer.q_sqrt), r['Lm'], r['aux'], r['kl'], r['info'])
+
+    def forward(self, join=True, prologue=True):
         """join=False: the two-kernel assembly of the loss slot (data term minus the global KLs) is left running on a side
-        stream and joined at the end of backward(), off the critical path between the forward and the backward pass."""
+        stream and joined at the end of backward(), off the critical path between the forward and the backward pass.
+        prologue=False: the once-per-layer stages (constrained values, Cholesky factors, KLs) are already in place for the
+        current parameters -- training.Trainer prepares them at the end of the previous step, as soon as each layer's
+        update is final, where they overlap with the rest of the backward pass instead of opening the next step."""
         flat = self.flat
-        flat.refresh_constrained()
         main = torch.cuda.current_stream()
-        self.ev_start.record(main)
+        if prologue:
+            flat.refresh_constrained()
+            self.ev_start.record(main)
         for r in self.recs:
-            if r['type'] != 'gp':
+            if r['type'] != 'gp' or not prologue:
                 continue
-            base, feat, layer = r['base'], r['feat'], r['layer']
-            side = self.side[r['gi']]
+            side = self.hp[r['gi']]
             side.wait_event(self.ev_start)
             with torch.cuda.stream(side):
-                if r['ard']:
-                    ls = self._cv(base.lengthscales)
-                else:
-                    r['ls_vec'].copy_(base.full_lengthscales(self._cv(base.lengthscales).reshape(-1), r['D']))
-                    ls = r['ls_vec']
-                r['ls'] = ls
-                capi.gp_prologue_fwd(r['d'], self._cv(feat.Z), ls, self._cv(base.variance), self._cv(layer.q_mu),
-                                     self._cv(layer.q_sqrt), r['Lm'], r['aux'], r['kl'], r['info'])
+                self.prologue_layer(r)
                 self.ev_pro[r['gi']].record(side)
         F = None
         if self.X_tiled is not None:
@@ -370,7 +388,8 @@ class Engine:
             else:
                 layer, base = r['layer'], r['base']
                 r['Fin'] = F
-                main.wait_event(self.ev_pro[r['gi']])
+                if prologue:
+                    main.wait_event(self.ev_pro[r['gi']])
                 args = (r['d'], r['Lm'], r['aux'], F,
                         self._cv(layer.kern.W) if r['mix'] else None,
                         self._cv(layer.mean_function.A) if r['mf'] == 'Linear' else None,
@@ -382,7 +401,8 @@ class Engine:
                     if r['gi'] == 0:          # the chain's inputs (latent-variable layer output, noise) are complete
                         self.ev_fork.record(main)
                         self.side_f.wait_event(self.ev_fork)
-                    self.side_f.wait_event(self.ev_pro[r['gi']])
+                    if prologue:
+                        self.side_f.wait_event(self.ev_pro[r['gi']])
                     capi.gp_rows_fwd_range(*args, 0, self.split)
                     with torch.cuda.stream(self.side_f):
                         capi.gp_rows_fwd_range(*args, self.split, self.T)
@@ -495,12 +515,21 @@ class Engine:
                     # The first GP layer comes last in the backward pass, so nothing is left to hide its Cholesky / gram
                     # adjoint chain behind -- except its own reductions: dLm first (part A), then the chain on this stream
                     # while dq_sqrt / dq_mu (part B) are formed on a second one; the KL adjoint adds into part B's outputs.
-                    with torch.cuda.stream(side):
+                    # Part A goes on the HIGH-PRIORITY stream: launched together with part B at equal priority its 140 CTAs
+                    # interleave with part B's 700 and finish when those do, which leaves the whole adjoint chain (and
+                    # the trainer's update + next-step factorisation behind it) exposed at the end of the step.
+                    hp = self.hp[gi]
+                    hp.wait_event(self.ev_rows[gi])
+                    if two:
+                        hp.wait_event(self.ev_rows_b[gi])
+                    with torch.cuda.stream(hp):
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_A), *args)
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), *pargs)
                         if not r['ard']:
                             self._fold_dls(r)
-                        self.ev_pbwd[gi].record(side)
+                        if self.grad_hook is not None:
+                            self.grad_hook(('gp_h', 0))
+                        self.ev_pbwd[gi].record(hp)
                     self.side_b.wait_event(self.ev_rows[gi])
                     with torch.cuda.stream(self.side_b):
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_B), *args)
@@ -509,14 +538,18 @@ class Engine:
                             self.grad_hook(('gp_q', 0))
                         self.ev_part_b.record(self.side_b)
                 else:
+                    hp = self.hp[gi]
                     with torch.cuda.stream(side):
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red), *args)
+                        self.ev_red[gi].record(side)
+                    hp.wait_event(self.ev_red[gi])
+                    with torch.cuda.stream(hp):
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM), *pargs)
                         if not r['ard']:
                             self._fold_dls(r)
                         if self.grad_hook is not None:
                             self.grad_hook(('gp', gi))
-                        self.ev_pbwd[gi].record(side)
+                        self.ev_pbwd[gi].record(hp)
                 d_next = r['dX']
             else:
                 if two:        # (a latent-variable layer only ever sits below the GP chain when the pass is split)

@@ -6,6 +6,7 @@ global row index so the result does not depend on the number of GPUs (up to summ
 import torch
 import torch.distributed as dist
 
+from . import _lib as LIB
 from . import capi
 from . import natgrad as NG
 from .engine import FlatParams
@@ -92,7 +93,7 @@ class Trainer:
 
     def __init__(self, model, B_local, lr=5e-3, lr_decay=0.98, beta1=0.9, beta2=0.999, eps=1e-8, seed=0,
                  process_group=None, use_graph=True, always_reduce=None, overlap_comm=True, graph_comm=True,
-                 distributed=None):
+                 distributed=None, pipeline=True):
         self.model = model
         self.pg = process_group
         self.distributed = (dist.is_available() and dist.is_initialized()) if distributed is None else bool(distributed)
@@ -107,9 +108,16 @@ class Trainer:
         self.graph_comm = bool(graph_comm)
         # segments are issued from side streams inside the backward pass: with CUDA graphs that needs the capture
         self.overlap_comm = bool(overlap_comm) and self.world_size > 1 and (self.graph_comm or not use_graph)
-        self._build_bucket()
+        # Segment-wise step: every segment of parameters is updated (Adam) on the side stream that completed -- and, on
+        # several ranks, exchanged -- its gradients, and the NEXT step's once-per-layer stage (Cholesky of Kuu, padded
+        # copies, KL) of that layer follows at once, overlapped with the rest of the backward pass, instead of opening the
+        # next step with ~115 us of single-CTA chains.  Needs the segments' gradients to be final when the hook fires:
+        # one rank, or overlap_comm.
+        self.pipeline = bool(pipeline) and (self.world_size == 1 or self.overlap_comm)
+        self._pro_ready = False        # the engine's once-per-layer stages match the current parameters
         self.m = torch.zeros_like(self.flat.x)
         self.v = torch.zeros_like(self.flat.x)
+        self._build_bucket()
         self.lr, self.lr_decay = lr, lr_decay
         self.betas, self.eps = (beta1, beta2), eps
         self.seed = seed
@@ -119,29 +127,60 @@ class Trainer:
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float64, device=dev)
         self._lr_host = float(lr)
         self.use_graph = bool(use_graph)
+        self._updating = False
         self._graphs = None            # (graph_fwd_bwd, graph_update) once captured
         self._graph_launches = 0
         self._graph_row0 = None
         self.eager_steps_before_capture = 2
 
-    # ---- the exchange step: ONE all-reduce of the PACKED gradient bucket ----
+    # ---- the exchange step (packed gradient bucket, in segments) and the segment-wise update ----
     def _build_bucket(self):
         groups = []
-        if self.overlap_comm:
+        if self.overlap_comm or self.pipeline:
             gps = [r for r in self.engine.recs if r['type'] == 'gp']
             for r in reversed(gps):                      # the order in which the backward pass completes them
                 layer, base, feat = r['layer'], r['base'], r['feat']
-                if r['gi'] == 0:
-                    groups.append((('gp_q', 0), [layer.q_mu, layer.q_sqrt]))
-                    continue
-                ps = [feat.Z, base.lengthscales, base.variance, layer.q_mu, layer.q_sqrt]
+                hyp = [feat.Z, base.lengthscales, base.variance]
                 if r['mix']:
-                    ps.append(layer.kern.W)
+                    hyp.append(layer.kern.W)
                 if r['mf'] == 'Linear':
-                    ps += [layer.mean_function.A, layer.mean_function.b]
-                groups.append((('gp', r['gi']), ps))
+                    hyp += [layer.mean_function.A, layer.mean_function.b]
+                if r['gi'] == 0:
+                    groups.append((('gp_h', 0), hyp))
+                    groups.append((('gp_q', 0), [layer.q_mu, layer.q_sqrt]))
+                else:
+                    groups.append((('gp', r['gi']), hyp + [layer.q_mu, layer.q_sqrt]))
         self.gbucket = GradBucket(self.flat, self.always_reduce, self.pg, groups)
-        self.engine.grad_hook = self.gbucket.allreduce if self.overlap_comm else None
+        # Adam masks: trainable entries of each segment (the packed index of a segment also holds always_reduce entries
+        # and, for 'final', the ELBO slot: the trainable mask filters those out)
+        f = self.flat
+        self.seg_mask = {}
+        for tag, (a, b) in self.gbucket.segments.items():
+            idx = self.gbucket.index[a:b]
+            idx = idx[idx < f.n]
+            mk = torch.zeros_like(f.mask)
+            mk[idx] = f.mask[idx]
+            self.seg_mask[tag] = mk
+        self._gp_by_gi = {r['gi']: r for r in self.engine.recs if r['type'] == 'gp'}
+        self.engine.grad_hook = self._segment_done if (self.overlap_comm or self.pipeline) else None
+        self._pro_ready = False
+
+    def _adam(self, mask, advance):
+        f = self.flat
+        capi.adam_step_counter_part(f.x, f.g, self.m, self.v, mask, f.theta_pos, f.n, f.n_pos, self.lr_dev,
+                                    self.betas[0], self.betas[1], self.eps, self.state, advance)
+
+    def _segment_done(self, tag):
+        """Engine.backward calls this on the side stream that has just completed the gradients of segment `tag`."""
+        if self.overlap_comm:
+            self.gbucket.allreduce(tag)
+        if not self.pipeline or not self._updating:
+            return
+        self._adam(self.seg_mask[tag], advance=False)
+        eng = self.engine
+        torch.cuda.current_stream().wait_event(eng.ev_loss)      # this step's loss assembly has read the KLs
+        r = self._gp_by_gi[tag[1]]
+        eng.prologue_layer(r, {'gp': 0, 'gp_h': LIB.FLAG_PRO_HYP, 'gp_q': LIB.FLAG_PRO_Q}[tag[0]])
 
     def allreduce_grads(self):
         """What is left to exchange after backward(): everything, or with overlap_comm the 'final' segment."""
@@ -150,14 +189,29 @@ class Trainer:
 
     # ---- the two halves of a step, written against device-side state only (capturable) ----
     def _fwd_bwd(self, row0):
-        self.engine.draw_noise(None, seed=self.seed, row0=row0, state=self.state)
-        self.engine.forward(join=False)
-        self.engine.backward()
+        eng = self.engine
+        eng.draw_noise(None, seed=self.seed, row0=row0, state=self.state)
+        if self.pipeline and not self._pro_ready:
+            # first step (or parameters were changed from outside): the once-per-layer stages, all at once
+            eng.forward(join=False, prologue=True)
+        else:
+            eng.forward(join=False, prologue=not self.pipeline)
+        self._updating = True
+        eng.backward()
+        self._updating = False
 
     def _update(self):
-        f = self.flat
-        capi.adam_step_counter(f.x, f.g, self.m, self.v, f.mask, f.theta_pos, f.n, f.n_pos, self.lr_dev, self.betas[0],
-                               self.betas[1], self.eps, self.state)
+        if self.pipeline:
+            self._adam(self.seg_mask['final'], advance=True)      # encoder, likelihood variance; closes the step
+            self._pro_ready = True
+        else:
+            self._adam(self.flat.mask, advance=True)
+
+    def invalidate(self):
+        """Call after changing parameter values from outside the trainer (assignment, loading a checkpoint): the next
+        step recomputes the once-per-layer stages instead of using the ones prepared at the end of the previous step."""
+        self._pro_ready = False
+        self._graphs = None
 
     def _capture(self, row0):
         l0 = capi.LAUNCHES
@@ -182,6 +236,7 @@ class Trainer:
                 self.graph_comm = False
                 if self.overlap_comm:          # segments issued from side streams need the capture: one bucket instead
                     self.overlap_comm = False
+                    self.pipeline = False
                     self._build_bucket()
                 capi.LAUNCHES = l0
         if self._graphs is None:
@@ -220,7 +275,9 @@ class Trainer:
             self.engine.set_batch_indices(self.model.X, self.model.Y, idx)
         else:
             self.engine.set_batch(X_local, Y_local)
-        graph = self.use_graph and self.t > self.eager_steps_before_capture
+        # (the graph is captured once the pipelined once-per-layer stages are in place: a step that still has to open
+        #  with them -- the first one, or after invalidate() -- runs eagerly)
+        graph = self.use_graph and self.t > self.eager_steps_before_capture and (not self.pipeline or self._pro_ready)
         if graph and (self._graphs is None or self._graph_row0 != row0):
             self._capture(row0)
         if graph and self._graphs[1] is None:          # one graph: noise, forward, backward, exchange, optimiser
@@ -256,6 +313,7 @@ class ReferenceIterationTrainer(Trainer):
         last.q_mu.set_trainable(False)          # handed to the natural-gradient optimiser (build_models.py:284-287)
         last.q_sqrt.set_trainable(False)
         kw['use_graph'] = False
+        kw['pipeline'] = False          # the NatGrad half rewrites q(u) of the last layer between two Adam evaluations
         kw['always_reduce'] = [last.q_mu, last.q_sqrt]
         super().__init__(model, B_local, lr=lr, lr_decay=lr_decay, **kw)
         self.ng_layer = last

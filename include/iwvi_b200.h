@@ -88,6 +88,13 @@ extern "C" {
 #define IWVI_FLAG_PART_B   512
 #define IWVI_FLAG_SKIP_KL  1024
 #define IWVI_FLAG_ONLY_KL  2048
+/* iwvi_gp_prologue_fwd in two halves, for callers that update a layer's parameters in two steps (training.Trainer updates
+ * Z / kernel parameters and q_mu / q_sqrt of the first GP layer at different moments of the backward pass, and prepares the
+ * NEXT step's factorisation as soon as the former are final):  PRO_HYP: everything that depends on Z, lengthscales,
+ * variance (scaled inducing inputs, constants, Cholesky factor and its block copies; resets info);  PRO_Q: everything that
+ * depends on q_mu, q_sqrt (padded copies, blocks of tril(q_sqrt), the KL).  Neither flag: both. */
+#define IWVI_FLAG_PRO_HYP 16384
+#define IWVI_FLAG_PRO_Q   32768
 /* iwvi_gp_rows_bwd (REDUCE / FINAL launches): the per-point half ran as two point chains (iwvi_gp_rows_bwd_range): sum the
  * per-CTA partials of both. */
 #define IWVI_FLAG_TWO_CHAINS 8192
@@ -325,6 +332,15 @@ int iwvi_adam_step_counter(double* x, const double* grad_elbo, double* m, double
  * each, `iters` iterations -> 2*256*8*iters*warps*blocks flops.  bench.py times it with CUDA events to state the FP64
  * tensor-pipe roofline denominator from the run itself.  out: blocks*warps*32 doubles (written, never read). */
 int iwvi_probe_dmma(double* out, int32_t blocks, int32_t warps, int32_t iters, void* stream);
+/* slots[idx] = %globaltimer (ns) when `stream` reaches this point; a one-thread launch, capturable (tools/graph_timeline.py) */
+int iwvi_debug_stamp(unsigned long long* slots, int32_t idx, void* stream);
+
+/* iwvi_adam_step_counter restricted to the entries with mask != 0 WITHOUT touching the others (their value, moments and
+ * constrained copies stay as they are), so that a step can update the parameters segment by segment as their gradients
+ * become final; advance != 0: increment state[0] afterwards (the last segment of a step). */
+int iwvi_adam_step_counter_part(double* x, const double* grad_elbo, double* m, double* v, const double* mask,
+                                double* theta_pos, int64_t n, int64_t n_pos, const double* lr, double beta1, double beta2,
+                                double eps, int64_t* state, int32_t advance, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
