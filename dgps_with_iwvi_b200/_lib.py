@@ -19,6 +19,7 @@ FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
 FLAG_NO_KDIAG = 4096
 FLAG_TWO_CHAINS = 8192
 FLAG_PRO_HYP, FLAG_PRO_Q = 16384, 32768
+FLAG_FAST_REDUCE = 65536
 
 ERRORS = {-1: 'bad descriptor', -2: 'unsupported size', -3: 'CUDA launch failure', -4: 'null pointer'}
 

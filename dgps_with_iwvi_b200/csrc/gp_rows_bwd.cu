@@ -74,7 +74,11 @@ inline int pick_reduce_split(int items, int npairs, int nchunks, int nsm) {
   return bestS;
 }
 
-inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
+inline bool fast_reduce_ok(const iwvi_gp_desc& d) {   // the tcgen05 variant tiles the output 128 x 256
+  return (d.flags & IWVI_FLAG_FAST_REDUCE) && iwvi_round_up(d.M, IWVI_BLK) % 128 == 0;
+}
+
+inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm, bool fast = false) {
   BwdWs w;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
   const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
@@ -87,7 +91,15 @@ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm) {
   // Split the points into S ranges.  CTAs are dispatched in blockIdx order to whichever SM frees up first; a diagonal
   // pair costs ~0.6 of an off-diagonal one (reduce_diag).  Pick the S whose simulated makespan is smallest, with a
   // small charge per extra partial the finalize kernel has to sum.
-  const int bestS = pick_reduce_split(items, w.npairs, nchunks, nsm);
+  int bestS = pick_reduce_split(items, w.npairs, nchunks, nsm);
+  if (fast) {
+    // tcgen05 variant: (R + 1) x tiles CTAs per point range, one wave in all
+    int tiles = 0;
+    for (int mt = 0; mt < al.Mp / 128; mt++) tiles += (mt * 128 + 128 + 255) / 256;
+    bestS = nsm / ((d.R + 1) * tiles);
+    if (bestS < 1) bestS = 1;
+    if (bestS > nchunks) bestS = nchunks;
+  }
   w.chunks_per_split = (nchunks + bestS - 1) / bestS;
   w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
@@ -1045,6 +1057,8 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
   }
 }
 
+#include "gp_reduce_fast.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // 4. fixed-order sums of the partials
 // ------------------------------------------------------------------------------------------------
@@ -1205,7 +1219,8 @@ extern "C" int64_t iwvi_gp_bwd_ws_doubles(const iwvi_gp_desc* d) {
   if (iwvi_check_gp_desc(d) != IWVI_OK) return -1;
   int nsm = 148, max_smem = 0;
   if (device_info(&nsm, &max_smem) != IWVI_OK) nsm = 148;
-  return bwd_ws_layout(*d, nsm).total;
+  const int64_t a = bwd_ws_layout(*d, nsm, false).total, b = bwd_ws_layout(*d, nsm, true).total;
+  return a > b ? a : b;   // either reduce variant (IWVI_FLAG_FAST_REDUCE) may run on it
 }
 
 extern "C" int iwvi_gp_bwd_tile_points(const iwvi_gp_desc* d) {
@@ -1241,7 +1256,8 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
   p.d_sample = d_sample; p.d_mean = d_mean; p.d_var = d_var;
   p.dX = dX; p.dZ = dZ; p.dls = dls; p.dvariance = dvariance; p.dq_mu = dq_mu; p.dq_sqrt = dq_sqrt; p.dLm = dLm;
   p.dW = dW; p.dmfA = dmfA; p.dmfb = dmfb; p.ws = ws;
-  p.wl = bwd_ws_layout(*d, nsm);
+  const bool fast = fast_reduce_ok(*d);
+  p.wl = bwd_ws_layout(*d, nsm, fast);
   int smem_bytes = 0;
   const int TP = pick_bwd_tp(p.wl.Tp, al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
   if (TP < 0) return IWVI_ERR_UNSUPPORTED;
@@ -1292,7 +1308,26 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
     p.q_lo = (do_a && !do_b) ? d->R : 0;
     const int nq = (do_a && do_b) ? d->R + 1 : (do_a ? 1 : d->R);
     p.q_n = nq;
-    gp_reduce_bwd_kernel<<<nq * per_q, RED_THREADS, red_smem, st>>>(p);
+    if (fast) {
+      // tcgen05 variant for dLq_r and dq_mu; dLm stays on the float64 kernel: its error would be amplified by the
+      // Cholesky adjoint behind it (measured: 1e-4 on dZ / kernel parameters instead of 1e-6)
+      const int q_hi = p.q_lo + nq;                        // one past the last matrix of this launch
+      const int nq_fast = (q_hi < d->R ? q_hi : d->R) - p.q_lo;
+      if (nq_fast > 0) {
+        const int fsmem = FR_STAGES * FR_STAGE_FLOATS * 4 + 1024;
+        if (cudaFuncSetAttribute(gp_reduce_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem) != cudaSuccess)
+          return IWVI_ERR_LAUNCH;
+        p.q_n = nq_fast;
+        gp_reduce_fast_kernel<<<nq_fast * p.wl.S * fast_reduce_tiles(al.Mp), FR_THREADS, fsmem, st>>>(p);
+        IWVI_CHECK_LAUNCH();
+      }
+      if (q_hi > d->R) {
+        p.q_lo = d->R; p.q_n = 1;
+        gp_reduce_bwd_kernel<<<per_q, RED_THREADS, red_smem, st>>>(p);
+      }
+    } else {
+      gp_reduce_bwd_kernel<<<nq * per_q, RED_THREADS, red_smem, st>>>(p);
+    }
     IWVI_CHECK_LAUNCH();
   }
   if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {

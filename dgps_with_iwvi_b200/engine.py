@@ -101,7 +101,7 @@ class Engine:
        mode 'vi'      : DGP_VI._build_likelihood,   points = [S*B] sample-major (models.py:50-53), K := S
        mode 'predict' : propagate without amortisation inputs, points = [S, N] (models.py:93-107), B := N, K := S"""
 
-    def __init__(self, model, B, K, mode='iw', world_size=1, rank=0, split_waves=True):
+    def __init__(self, model, B, K, mode='iw', world_size=1, rank=0, split_waves=True, fast_reduce=False):
         from .layers import GPLayer, LatentVariableLayer
         if not torch.cuda.is_available():
             raise RuntimeError('dgps_with_iwvi_b200: no CUDA device -- the IW-ELBO path has no CPU fallback')
@@ -109,6 +109,9 @@ class Engine:
         assert mode in ('iw', 'vi', 'predict')
         self.model, self.B, self.K, self.mode = model, int(B), int(K), mode
         self.world_size, self.rank = int(world_size), int(rank)
+        # OPTIONAL reduced-precision fast path (off by default; never used by the parity tests): the parameter contractions of
+        # the backward pass on tcgen05 / TMEM as 3xTF32 products (include/iwvi_b200.h, IWVI_FLAG_FAST_REDUCE)
+        self.fast_reduce = bool(fast_reduce)
         self.T = T = self.B * self.K
         self.flat = flat = FlatParams.of(model)
         dev = flat.device
@@ -510,7 +513,7 @@ class Engine:
                 pargs = (r['Lm'], r['aux'], self._cv(feat.Z), r['ls'], self._cv(base.variance), self._cv(layer.q_mu),
                          self._cv(layer.q_sqrt), r['dLm'], self.dkl, outs[0], outs[1], outs[2], outs[3], outs[4],
                          r['pbwd_ws'])
-                red = fl | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL
+                red = fl | LIB.FLAG_ONLY_REDUCE | LIB.FLAG_ONLY_FINAL | (LIB.FLAG_FAST_REDUCE if self.fast_reduce else 0)
                 if gi == 0:
                     # The first GP layer comes last in the backward pass, so nothing is left to hide its Cholesky / gram
                     # adjoint chain behind -- except its own reductions: dLm first (part A), then the chain on this stream

@@ -86,14 +86,16 @@ class DGP_VI(Parameterized):
     # ---- plans ------------------------------------------------------------------------------
     MAX_ENGINES = 4       # plans own every buffer of a pass (c3: 1 GB of saved panels per training plan, c4: 27 GB)
 
+    fast_reduce = False   # OPTIONAL reduced-precision fast path of the parameter contractions (engine.Engine); off = float64 parity path
+
     def engine(self, B, K, mode=None, world_size=1, rank=0):
         """The execution plan for (B, K, mode, world, rank, num_data); least-recently-used plans beyond MAX_ENGINES are
         dropped (their device buffers are freed) so that evaluating many different batch / test-set sizes cannot
         accumulate memory.  num_data is part of the key: the ELBO scale num_data / B is fixed inside a plan."""
-        key = (int(B), int(K), mode or self._mode, int(world_size), int(rank), int(self.num_data))
+        key = (int(B), int(K), mode or self._mode, int(world_size), int(rank), int(self.num_data), bool(self.fast_reduce))
         eng = self._engines.pop(key, None)
         if eng is None:
-            eng = Engine(self, key[0], key[1], key[2], world_size, rank)
+            eng = Engine(self, key[0], key[1], key[2], world_size, rank, fast_reduce=self.fast_reduce)
         self._engines[key] = eng                      # dicts keep insertion order: last = most recently used
         while len(self._engines) > self.MAX_ENGINES:
             self._engines.pop(next(iter(self._engines)))

@@ -98,6 +98,12 @@ extern "C" {
 /* iwvi_gp_rows_bwd (REDUCE / FINAL launches): the per-point half ran as two point chains (iwvi_gp_rows_bwd_range): sum the
  * per-CTA partials of both. */
 #define IWVI_FLAG_TWO_CHAINS 8192
+/* OPTIONAL reduced-precision fast path, NOT the float64 parity path: iwvi_gp_rows_bwd forms the parameter contractions over the
+ * points (dq_sqrt, dLm, dq_mu) on the tcgen05 tensor cores -- every float64 operand split into two TF32 numbers, three
+ * TF32 products per term, FP32 accumulation in tensor memory, float64 sums of the split-K partials.  Relative error about
+ * 1e-6 of the largest entry of each gradient; everything else (ELBO, dX, dZ, kernel parameters) is unchanged.  Needs M
+ * padded to a multiple of 128; otherwise the flag is ignored.  Pass it with the REDUCE and FINAL launches alike. */
+#define IWVI_FLAG_FAST_REDUCE 65536
 /* iwvi_gp_rows_bwd: leave the Kdiag term (d var / d variance = 1 per point) out of dvariance -- set by callers that
  * differentiate the prior covariance k(X, X) themselves (iwvi_gp_fullcov_bwd). */
 #define IWVI_FLAG_NO_KDIAG 4096

@@ -1,0 +1,46 @@
+"""The OPTIONAL reduced-precision fast path (IWVI_FLAG_FAST_REDUCE: parameter contractions of the backward pass as 3xTF32
+products on tcgen05 tensor cores with FP32 accumulation in tensor memory) -- reported separately from the float64 parity
+path, with ITS tolerance: dq_sqrt / dLm-dependent / dq_mu gradients within 2e-5 of the largest entry of each tensor
+(measured about 1e-6), everything else (ELBO, other gradients that do not pass through dLm) bit-identical."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import iwvi_oracle as O
+from oracle import synthetic as S
+
+pytestmark = pytest.mark.gpu
+FAST_TOL = 2e-5
+
+
+@pytest.mark.parametrize('cname,B', [('c3', 512), ('c2', 512), ('c4', 32)])
+def test_fast_reduce_against_oracle_and_exact_path(cname, B):
+    from dgps_with_iwvi_b200.build_models import model_from_spec
+    c = S.CONFIGS[cname]
+    X, Y = S.make_data(min(c['N'], 20000), c['D'], seed=0)
+    spec = S.make_spec(X, c['configuration'], c['M'], c['K'], lik_variance=c['lik_variance'], seed=0, perturb=0.1,
+                       inner_q_sqrt_scale=0.3)
+    spec['num_data'] = c['N']
+    K = c['K']
+    Xb, Yb = X[:B], Y[:B]
+    eps = S.make_noise(spec, (B, K), seed=1)
+    e_ref, g_ref = O.iw_elbo_and_grads(spec, Xb, Yb, eps, reference_style=True)
+    want = {k: v.numpy() for k, v in g_ref.items()}
+    exact = model_from_spec(spec, X, Y)
+    e0, g0 = exact.compute_log_likelihood_and_grads(Xb, Yb, eps)
+    fast = model_from_spec(spec, X, Y)
+    fast.fast_reduce = True
+    e1, g1 = fast.compute_log_likelihood_and_grads(Xb, Yb, eps)
+    assert fast.engine(B, K).fast_reduce and not exact.engine(B, K).fast_reduce
+    assert e1 == e0                                       # the forward pass is untouched
+    rep = H.grad_report(g1, want, rtol=0.0, atol_rel=FAST_TOL)
+    worst = max(v['normwise'] for v in rep.values())
+    print('%s: fast path worst normwise gradient error %.2e  %s' % (cname, worst, {k: '%.1e' % v['normwise'] for k, v in rep.items() if v['normwise'] > 1e-9}))
+    assert worst < FAST_TOL, {k: v['normwise'] for k, v in rep.items() if v['normwise'] > FAST_TOL}
+    # gradients that do not depend on the contractions are bit-identical to the float64 path
+    for k in g0:
+        if k.startswith('layers.0.encoder') or k == 'likelihood.variance':
+            assert np.array_equal(g0[k], g1[k]), k
+    # and the fast path really differs from the exact one (it ran): some q_sqrt gradient is not bit-identical
+    assert any(not np.array_equal(g0[k], g1[k]) for k in g0 if k.endswith('q_sqrt'))
