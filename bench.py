@@ -387,6 +387,8 @@ def main():
     X, Y = make_data(N, cfg['D'], seed=0)
     model = build_model(X, Y, cfg['configuration'], M=cfg['M'], num_IW_samples=K, minibatch_size=Bg,
                         likelihood_variance=cfg['lik_variance'], mode='IWAE', seed=0)
+    if os.environ.get('IWVI_FAST_REDUCE'):          # quick experiments; the reported fast-path line is fast_path_timing()
+        model.fast_reduce = True
     trainer = Trainer(model, B, lr=5e-3, seed=0)
     eng = trainer.engine
     dev = eng.dev

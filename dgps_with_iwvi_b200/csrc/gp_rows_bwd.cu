@@ -94,9 +94,10 @@ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm, bool fast = false) {
   int bestS = pick_reduce_split(items, w.npairs, nchunks, nsm);
   if (fast) {
     // tcgen05 variant: (R + 1) x tiles CTAs per point range, one wave in all
-    int tiles = 0;
-    for (int mt = 0; mt < al.Mp / 128; mt++) tiles += (mt * 128 + 128 + 255) / 256;
-    bestS = nsm / ((d.R + 1) * tiles);
+    const int mts = (al.Mp + 255) / 256, tiles = mts * (mts + 1) / 2;   // 256 x 256 tiles of the lower block triangle
+    bestS = nsm / (d.R * tiles);                                           // (dLm stays on the float64 kernel)
+    const int min_s = (nchunks + 63) / 64;                                 // at most 4096 points per CTA (its scale table)
+    if (bestS < min_s) bestS = min_s;
     if (bestS < 1) bestS = 1;
     if (bestS > nchunks) bestS = nchunks;
   }
@@ -127,6 +128,7 @@ struct BwdParams {
   int epi0;           // epilogue kernel: first 32-point CTA of this launch
   int q_lo;      // reduce kernel: first matrix index of this launch (0 .. R; R == dLm)
   int q_n;       // reduce kernel: number of matrices of this launch
+  int qmu_only;  // reduce kernel: 1 = only the items (q_lo, block row bi, block column 0), the ones that also form dq_mu
   int fin_part;  // finalize kernel: 0 = everything, 1 = part A outputs, 2 = part B outputs
 };
 
@@ -977,9 +979,14 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
   // slowest (round 1) a wave held the ranges of 2-3 matrices only and A was streamed from DRAM once per wave
   // (652 MB per launch against 390 MB of operands at c3, ncu).
   int item = blockIdx.x;
-  const int pair = item % wl.npairs; item /= wl.npairs;
-  const int q = p.q_lo + item % p.q_n;                           // q < R: dLq_q ; q == R: dLm
-  const int s = item / p.q_n;
+  int pair, q, s;
+  if (p.qmu_only) {                                              // grid = S x NB: block column 0 of matrix q_lo
+    pair = iwvi_pair(item % NB, 0); q = p.q_lo; s = item / NB;
+  } else {
+    pair = item % wl.npairs; item /= wl.npairs;
+    q = p.q_lo + item % p.q_n;                                   // q < R: dLq_q ; q == R: dLm
+    s = item / p.q_n;
+  }
   int bi = 0, acc_pairs = 0;
   while (acc_pairs + bi + 1 <= pair) { acc_pairs += bi + 1; bi++; }
   const int bj = pair - acc_pairs;                               // bj <= bi
@@ -1265,7 +1272,7 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
   p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
   cudaStream_t st = (cudaStream_t)stream;
   const int only = d->flags & IWVI_FLAG_ONLY_MASK;
-  p.q_lo = 0; p.q_n = d->R + 1; p.fin_part = 0;
+  p.q_lo = 0; p.q_n = d->R + 1; p.fin_part = 0; p.qmu_only = 0;
   p.tile0 = 0; p.tile1 = p.ntiles; p.slot0 = 0; p.n_slots = 0; p.epi0 = 0;
   int n_epi = p.wl.n_epi;
   if (ranged) {
@@ -1314,12 +1321,21 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
       const int q_hi = p.q_lo + nq;                        // one past the last matrix of this launch
       const int nq_fast = (q_hi < d->R ? q_hi : d->R) - p.q_lo;
       if (nq_fast > 0) {
-        const int fsmem = FR_STAGES * FR_STAGE_FLOATS * 4 + 1024;
+        const int fsmem = FR_STAGES * FR_STAGE_FLOATS * 4 + FR_MAX_RANGE * 4 + 1024;
+        if (p.wl.chunks_per_split * IWVI_BLK > FR_MAX_RANGE) return IWVI_ERR_UNSUPPORTED;
         if (cudaFuncSetAttribute(gp_reduce_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem) != cudaSuccess)
           return IWVI_ERR_LAUNCH;
         p.q_n = nq_fast;
         gp_reduce_fast_kernel<<<nq_fast * p.wl.S * fast_reduce_tiles(al.Mp), FR_THREADS, fsmem, st>>>(p);
         IWVI_CHECK_LAUNCH();
+        if (p.q_lo == 0) {
+          // the launch that owns matrix 0 owns dq_mu = A gmean_bar: the float64 kernel's (q = 0, block column 0) items,
+          // which form it as a ride-along (their dLq_0 blocks overwrite the tensor-core ones with float64 values)
+          p.qmu_only = 1; p.q_n = 1;
+          gp_reduce_bwd_kernel<<<p.wl.S * al.NB, RED_THREADS, red_smem, st>>>(p);
+          IWVI_CHECK_LAUNCH();
+          p.qmu_only = 0;
+        }
       }
       if (q_hi > d->R) {
         p.q_lo = d->R; p.q_n = 1;
