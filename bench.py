@@ -687,8 +687,8 @@ def kernel_timings(eng, capi, LIB, torch, peak_tf, reps=5):
     bwd(0)
     cases = [
         ('gp_rows_fwd_kernel', fwd, T * ((1 + R) * M * M + 2 * M * (D + 2 * R + 1))),
-        ('gp_tile_bwd_kernel', lambda: bwd(LIB.FLAG_ONLY_TILE if hasattr(LIB, 'FLAG_ONLY_TILE') else 32),
-         T * ((1 + R) * M * M + 2 * M * (3 * D + R + 1))),
+        ('gp_tile_bwd_kernel', lambda: bwd(LIB.FLAG_ONLY_TILE), T * ((1 + R) * M * M + 2 * M * (R + 1))),
+        ('gp_gram_bwd_kernel', lambda: bwd(LIB.FLAG_ONLY_GRAM), T * 2 * M * 3 * D),
         ('gp_reduce_bwd_kernel', lambda: bwd(64), T * (1 + R) * M * M + 2 * T * M * R),
     ]
     out = []

@@ -15,6 +15,7 @@ MF_IDS = {'Zero': 0, 'Identity': 1, 'Linear': 2}
 ACT_IDS = {'tanh': 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3, 'elu': 4, 'identity': 5}
 FLAG_SAMPLE, FLAG_SAVE, FLAG_ACCUM = 1, 2, 4
 FLAG_ONLY_EPI, FLAG_ONLY_TILE, FLAG_ONLY_REDUCE, FLAG_ONLY_FINAL = 16, 32, 64, 128
+FLAG_ONLY_GRAM = 8
 FLAG_PART_A, FLAG_PART_B, FLAG_SKIP_KL, FLAG_ONLY_KL = 256, 512, 1024, 2048
 FLAG_NO_KDIAG = 4096
 FLAG_TWO_CHAINS = 8192
@@ -46,6 +47,7 @@ P = C.c_void_p  # device pointers and the stream travel as opaque addresses
 
 SIGNATURES = {
     'iwvi_version': (C.c_int, []),
+    'iwvi_last_cuda_error': (C.c_char_p, []),
     'iwvi_gp_mp': (C.c_int32, [C.c_int32]),
     'iwvi_gp_lda': (C.c_int32, [C.c_int32]),
     'iwvi_gp_aux_doubles': (C.c_int64, [C.POINTER(GpDesc)]),
@@ -107,4 +109,7 @@ def load():
 
 def check(rc, what):
     if rc != 0:
-        raise RuntimeError('%s failed: %s (code %d)' % (what, ERRORS.get(rc, 'unknown error'), rc))
+        detail = ''
+        if rc == -3 and _lib is not None:
+            detail = ' [%s]' % _lib.iwvi_last_cuda_error().decode()
+        raise RuntimeError('%s failed: %s (code %d)%s' % (what, ERRORS.get(rc, 'unknown error'), rc, detail))

@@ -35,11 +35,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, timing=False):
+def build(force=False, verbose=False, timing=False, variant=None, extra=()):
     """timing=True: a second library, lib/libiwvi_b200_timing.so, compiled with -DIWVI_PHASE_TIMING (per-phase clock64()
-    totals, tools/phase_timing.py); select it with the environment variable IWVI_B200_LIB."""
+    totals, tools/phase_timing.py); select it with the environment variable IWVI_B200_LIB.
+    variant='name', extra=['-DX=1', ...]: a tuning build lib/libiwvi_b200_<name>.so with extra nvcc flags."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, 'obj_timing' if timing else 'obj')
+    if timing:
+        variant = 'timing'
+    objdir = os.path.join(LIBDIR, 'obj_' + variant if variant else 'obj')
     os.makedirs(objdir, exist_ok=True)
     srcs = sources()
     hdrs = _deps()
@@ -49,7 +52,7 @@ def build(force=False, verbose=False, timing=False):
         o = os.path.join(objdir, os.path.basename(s)[:-3] + '.o')
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([NVCC] + FLAGS + (['-DIWVI_PHASE_TIMING', '-rdc=true'] if timing else []) +
+            jobs.append([NVCC] + FLAGS + (['-DIWVI_PHASE_TIMING', '-rdc=true'] if timing else []) + list(extra) +
                         (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o])
 
     def run(cmd):
@@ -62,11 +65,13 @@ def build(force=False, verbose=False, timing=False):
         for out in ex.map(run, jobs):
             if verbose and out:
                 print(out)
-    lib = LIB.replace('.so', '_timing.so') if timing else LIB
+    lib = LIB.replace('.so', '_%s.so' % variant) if variant else LIB
     if jobs or force or _stale(lib, objs):
         run([NVCC, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
     return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, timing='--timing' in sys.argv))
+    variant = sys.argv[sys.argv.index('--variant') + 1] if '--variant' in sys.argv else None
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, timing='--timing' in sys.argv, variant=variant,
+                extra=[a for a in sys.argv[1:] if a.startswith('-D')]))

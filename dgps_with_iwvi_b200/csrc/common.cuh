@@ -581,4 +581,6 @@ extern __device__ unsigned long long iwvi_phase_cycles[3][16];
 #define PHASE_FLUSH(kern)
 #endif
 
-#define IWVI_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return IWVI_ERR_LAUNCH; } while (0)
+// the CUDA error behind the calling thread's last IWVI_ERR_LAUNCH (gp_prologue.cu; read through iwvi_last_cuda_error)
+void iwvi_note_cuda_error(cudaError_t e);
+#define IWVI_CHECK_LAUNCH() do { const cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { iwvi_note_cuda_error(e_); return IWVI_ERR_LAUNCH; } } while (0)

@@ -739,6 +739,9 @@ int launch_chol(const ProParams& p, int smem_bytes, cudaStream_t st) {
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" int iwvi_version(void) { return IWVI_VERSION; }
+static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+void iwvi_note_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+extern "C" const char* iwvi_last_cuda_error(void) { return cudaGetErrorName(g_last_cuda_error); }
 extern "C" int32_t iwvi_gp_mp(int32_t M) { return iwvi_round_up(M, IWVI_BLK); }
 extern "C" int32_t iwvi_gp_lda(int32_t M) { return iwvi_round_up(M, IWVI_BLK) + 4; }
 extern "C" int64_t iwvi_gp_aux_doubles(const iwvi_gp_desc* d) {

@@ -2,22 +2,24 @@
 // through temp_workaround.py:44-91,142-145 and layers.py:46-48; the formulas are derived in DESIGN.md and checked
 // against autograd in tests/test_staged.py.
 //
-// Four launches (the host may run 1-2 and 3-4 on different streams, see IWVI_FLAG_ONLY_* / IWVI_FLAG_PART_*):
+// Five launches (the host may run 1-3 and 4-5 on different streams, see IWVI_FLAG_ONLY_* / IWVI_FLAG_PART_*):
 //   1 gp_epi_bwd_kernel   32 points per CTA: un-mix the cotangents (gmean_bar, gvar_bar), mean-function part of dX
 //                         (skinny DMMA), partial sums of dW / dmfA / dmfb / dvariance.
 //   2 gp_tile_bwd_kernel  persistent, one tile of TP points per CTA iteration, shared-memory resident panel
 //                         (block-major), producer warp + TMA ring as in the forward kernel:
 //        Abar/2 = q_mu gmean_bar^T / 2 - A (sum_r gvar_bar_r) + sum_r tril(Lq_r) (U_r * gvar_bar_r)
-//        Bbar/2 = Lm^-T Abar/2                           (blocked back substitution, in place; stored for 3; the exact
-//                                                         factor 2 is restored where Bbar is consumed)
+//        Bbar/2 = Lm^-T Abar/2                           (blocked back substitution, in place; stored for 3 and 4; the
+//                                                         exact factor 2 is restored where Bbar is consumed)
+//   3 gp_gram_bwd_kernel  (gp_gram_bwd.cu) strips of 32 points, two CTAs per SM:
 //        G      = Bbar * dK/dr2 ; dX += 2/ls (x~ colsum(G) - G^T z~) ; dZ, dls, dvariance partials per CTA
-//   3 gp_reduce_bwd_kernel  contractions over the T points, split-K, one 64x64 output block per CTA (diagonal blocks:
+//   4 gp_reduce_bwd_kernel  contractions over the T points, split-K, one 64x64 output block per CTA (diagonal blocks:
 //                         lower triangle only):
 //        dLq_r = 2 tril(A diag(gvar_bar_r) U_r^T),  dLm = -tril(Bbar A^T),  dq_mu = A gmean_bar
-//   4 gp_finalize_bwd_kernel  fixed-order sums of all partials (deterministic; the only atomics are fire-and-forget
+//   5 gp_finalize_bwd_kernel  fixed-order sums of all partials (deterministic; the only atomics are fire-and-forget
 //                         adds to addresses owned by a single thread).
 #include <stdlib.h>
 #include "common.cuh"
+#include "gp_bwd.cuh"
 
 namespace {
 
@@ -32,105 +34,10 @@ template <int TP> struct TileCfg {
 };
 
 #define RED_NST 6          // ring depth of the reduce kernel: two stages per 64-point chunk step, three steps in flight
-#define EPI_STRIDE 1344   // >= P*R + D*P + P + 1 at the maxima (32*8 + 32*32 + 32 + 1 = 1313)
-#define EPI_PTS 32
-#define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
 #define TILE_THREADS IWVI_WS_THREADS    // 8 consumer warps + the producer warpgroup (1 active warp)
 #define BAR_ALL 1
 #define BAR_COL 2
 
-struct BwdWs {   // workspace layout (doubles)
-  int64_t off_bbar, off_gmb, off_gvb, off_epi, off_tile, off_red, off_qred, total;
-  int Tp, n_epi, grid_tile, S, npairs, chunks_per_split, tile_stride;
-};
-// host-side list-scheduling model behind the choice of S (see bwd_ws_layout); the last answer is cached per thread
-// because the entry points recompute the layout on every call
-inline int pick_reduce_split(int items, int npairs, int nchunks, int nsm) {
-  if (const char* e = getenv("IWVI_REDUCE_S")) { const int v = atoi(e); if (v >= 1) return v < nchunks ? v : nchunks; }   // tuning aid
-  static thread_local int key[4] = {-1, -1, -1, -1}, cached = 1;
-  if (key[0] == items && key[1] == npairs && key[2] == nchunks && key[3] == nsm) return cached;
-  int bestS = 1;
-  double best = 1e300;
-  const int ns = nsm < 256 ? (nsm > 0 ? nsm : 1) : 256;
-  for (int S = 1; S <= 16 && S <= nchunks; S++) {
-    const int cps = (nchunks + S - 1) / S;
-    double freeat[256];
-    for (int k = 0; k < ns; k++) freeat[k] = 0.0;
-    double makespan = 0.0;
-    for (int it = 0; it < items * S; it++) {
-      const int pair = it % npairs;
-      int bi = 0;
-      while ((bi + 1) * (bi + 2) / 2 <= pair) bi++;
-      const bool diag = (pair - bi * (bi + 1) / 2) == bi;
-      int k = 0;
-      for (int k2 = 1; k2 < ns; k2++) if (freeat[k2] < freeat[k]) k = k2;
-      freeat[k] += cps * (diag ? 0.6 : 1.0);
-      if (freeat[k] > makespan) makespan = freeat[k];
-    }
-    const double cost = makespan + 0.5 * S;
-    if (cost < best) { best = cost; bestS = S; }
-  }
-  key[0] = items; key[1] = npairs; key[2] = nchunks; key[3] = nsm; cached = bestS;
-  return bestS;
-}
-
-inline bool fast_reduce_ok(const iwvi_gp_desc& d) {   // the tcgen05 variant tiles the output 128 x 256
-  return (d.flags & IWVI_FLAG_FAST_REDUCE) && iwvi_round_up(d.M, IWVI_BLK) % 128 == 0;
-}
-
-inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm, bool fast = false) {
-  BwdWs w;
-  const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
-  const SaveLayout sv = iwvi_save_layout(d.T, d.M, d.R);
-  w.Tp = sv.Tp;
-  w.n_epi = (w.Tp + EPI_PTS - 1) / EPI_PTS;
-  w.grid_tile = nsm;
-  w.npairs = al.NB * (al.NB + 1) / 2;
-  const int nchunks = w.Tp / IWVI_BLK;
-  const int items = (d.R + 1) * w.npairs;
-  // Split the points into S ranges.  CTAs are dispatched in blockIdx order to whichever SM frees up first; a diagonal
-  // pair costs ~0.6 of an off-diagonal one (reduce_diag).  Pick the S whose simulated makespan is smallest, with a
-  // small charge per extra partial the finalize kernel has to sum.
-  int bestS = pick_reduce_split(items, w.npairs, nchunks, nsm);
-  if (fast) {
-    // tcgen05 variant: (R + 1) x tiles CTAs per point range, one wave in all
-    const int mts = (al.Mp + 255) / 256, tiles = mts * (mts + 1) / 2;   // 256 x 256 tiles of the lower block triangle
-    bestS = nsm / (d.R * tiles);                                           // (dLm stays on the float64 kernel)
-    const int min_s = (nchunks + 63) / 64;                                 // at most 4096 points per CTA (its scale table)
-    if (bestS < min_s) bestS = min_s;
-    if (bestS < 1) bestS = 1;
-    if (bestS > nchunks) bestS = nchunks;
-  }
-  w.chunks_per_split = (nchunks + bestS - 1) / bestS;
-  w.S = (nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
-  w.tile_stride = al.Mp * al.ldz + TILE_PART_EXTRA;
-  int64_t o = 0;
-  w.off_bbar = o; o += sv.u_stride;            // Bbar / 2, block-major like the saved A
-  w.off_gmb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
-  w.off_gvb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
-  w.off_epi = o;  o += (int64_t)w.n_epi * EPI_STRIDE;
-  w.off_tile = o; o += (int64_t)2 * w.grid_tile * w.tile_stride;   // per-CTA partials of the tile kernel: two point chains (see iwvi_gp_rows_bwd_range)
-  w.off_red = o;  o += (int64_t)(d.R + 1) * w.S * w.npairs * IWVI_BLK * IWVI_BLK;
-  w.off_qred = o; o += (int64_t)w.S * al.NB * IWVI_BLK * IWVI_MAX_R;
-  w.total = o;
-  return w;
-}
-
-struct BwdParams {
-  iwvi_gp_desc d;
-  const double *Lm, *aux, *save, *X, *W, *mfA, *mfb, *eps, *d_sample, *d_mean, *d_var;
-  double *dX, *dZ, *dls, *dvariance, *dq_mu, *dq_sqrt, *dLm, *dW, *dmfA, *dmfb, *ws;
-  BwdWs wl;
-  int ntiles, grid_tile;
-  int tile0, tile1;   // tile kernel: tiles [tile0, tile1) of this launch
-  int slot0;          // tile kernel: first per-CTA partial slot of this launch (0: first chain, nsm: second chain)
-  int n_slots;        // tile kernel: slots per chain; a ranged launch zeroes the slots of its chain that its grid does not own
-  int epi0;           // epilogue kernel: first 32-point CTA of this launch
-  int q_lo;      // reduce kernel: first matrix index of this launch (0 .. R; R == dLm)
-  int q_n;       // reduce kernel: number of matrices of this launch
-  int qmu_only;  // reduce kernel: 1 = only the items (q_lo, block row bi, block column 0), the ones that also form dq_mu
-  int fin_part;  // finalize kernel: 0 = everything, 1 = part A outputs, 2 = part B outputs
-};
 
 // ------------------------------------------------------------------------------------------------
 // 1. per-point epilogue adjoint
@@ -255,8 +162,8 @@ __global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
 // 2. tile kernel
 // ------------------------------------------------------------------------------------------------
 struct BwdSeq {
-  int NB, R, npairs, ldz, tp_bytes;
-  const double *Zt, *Lmb, *Lqb, *A_T, *U_T;
+  int NB, R, npairs, tp_bytes;
+  const double *Lmb, *Lqb, *A_T, *U_T;
   int64_t u_stride;
   int64_t tile_off;   // offset of this tile's rows inside block 0 of its 64-point chunk (block-major saved arrays)
   int ph, r, i, j;
@@ -265,7 +172,7 @@ struct BwdSeq {
     ph = 0; r = 0; i = -1; j = 0; a_turn = false;
     tile_off = (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
   }
-  __device__ __forceinline__ bool done() const { return ph == 3; }
+  __device__ __forceinline__ bool done() const { return ph == 2; }
   __device__ __forceinline__ BlockSrc get() const {
     BlockSrc b;
     b.bytes = IWVI_STAGE_DOUBLES * 8;
@@ -277,10 +184,8 @@ struct BwdSeq {
       } else {               // tril(q_sqrt_r) block (row block i, col block j), i >= j
         b.src = Lqb + ((size_t)r * npairs + iwvi_pair(i, j)) * IWVI_STAGE_DOUBLES;
       }
-    } else if (ph == 1) {    // Lm block (row block j, col block i), j > i; j == NB: inverted diagonal block i
+    } else {                 // Lm block (row block j, col block i), j > i; j == NB: inverted diagonal block i
       b.src = Lmb + (size_t)(j < NB ? iwvi_pair(j, i) : iwvi_pair(i, i)) * IWVI_STAGE_DOUBLES;
-    } else {                 // scaled inducing inputs, block i
-      b.src = Zt + (size_t)i * IWVI_BLK * ldz; b.bytes = (uint32_t)(IWVI_BLK * ldz * 8);
     }
     return b;
   }
@@ -289,11 +194,9 @@ struct BwdSeq {
       if (a_turn) { a_turn = false; return; }
       if (++i == NB) { ++j; i = j - 1; if (j == NB) { ++r; j = 0; i = -1; if (r == R) { ph = 1; i = NB - 1; j = NB; } } }
       a_turn = (ph == 0 && r == 0 && j == 0 && i >= 0);
-    } else if (ph == 1) {
-      if (j < NB) ++j;
-      else { --i; j = i + 1; if (i < 0) { ph = 2; i = 0; } }
     } else {
-      if (++i == NB) ph = 3;
+      if (j < NB) ++j;
+      else { --i; j = i + 1; if (i < 0) ph = 2; }
     }
   }
 };
@@ -342,39 +245,14 @@ __device__ __forceinline__ void lq_v_product(double (&acc)[TM][2][2], const doub
   static_assert(NG == 8, "lq_v_product is written out for eight groups of two k-steps");
 }
 
-// acc[b] += sum_k a(k) * B(k, 8 b + g) for b < NB8: one 8-row A tile (this lane's element of k-step k0 is ap[k0 * a_stride])
-// against NB8 column tiles of a [k][ld] operand (bp already points at row t, column g); columns >= ncols read as 0.
-template <int NB8>
-__device__ __forceinline__ void skinny_gemm(double (&acc)[4][2], const double* __restrict__ ap, int a_stride,
-                                            const double* __restrict__ bp, int ld, int K, int g, int ncols) {
-#pragma unroll 4
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    const double a = ap[k0 * a_stride];
-#pragma unroll
-    for (int b = 0; b < NB8; b++) {
-      const double bv = (b * 8 + g < ncols) ? bp[k0 * ld + b * 8] : 0.0;
-      dmma884(acc[b], a, bv);
-    }
-  }
-}
-
-struct TileSmem { int panel, stages, xs, xn, gmb, gvb, gsum, gs, gr, dls, red, bars, total_doubles; };
-__host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp, int ldx) {
+struct TileSmem { int panel, stages, gmb, gvb, gsum, bars, total_doubles; };
+__host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp) {
   TileSmem s; int o = 0;
   s.panel = o;  o += (Mp / IWVI_BLK) * TP * IWVI_LDS;   // block-major [m-block][point][68], see gp_rows_fwd.cu
   s.stages = o; o += IWVI_NST * IWVI_STAGE_DOUBLES;
-  s.xs = o;     o += TP * ldx;
-  s.xn = o;     o += TP;
   s.gmb = o;    o += IWVI_MAX_R * TP;
   s.gvb = o;    o += IWVI_MAX_R * TP;
   s.gsum = o;   o += TP;
-  // gs [WMG][TP] column sums of G per warp row group, gr [2][WNG][64] row sums per warp column group (double buffered):
-  // only alive in the gram adjoint, when the per-point cotangents gmb / gvb are dead -> share their memory if they fit
-  const int n_gs = 4 * TP, n_gr = 2 * 4 * IWVI_BLK;
-  if (n_gs + n_gr <= 2 * IWVI_MAX_R * TP) { s.gs = s.gmb; s.gr = s.gmb + n_gs; }
-  else { s.gs = o; o += n_gs; s.gr = o; o += n_gr; }
-  s.dls = o;    o += 8 * 32;               // [warp][32]
-  s.red = o;    o += 32;
   s.bars = o;   o += 2 * IWVI_NST;
   s.total_doubles = o;
   return s;
@@ -387,21 +265,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
   const AuxLayout al = iwvi_aux_layout(d.M, d.D, d.R);
-  const int Mp = al.Mp, NB = al.NB, ldz = al.ldz, R = d.R, D = d.D, T = d.T, M = d.M;
+  const int Mp = al.Mp, NB = al.NB, R = d.R, T = d.T, M = d.M;
   constexpr int PSTR = TP * IWVI_LDS;   // element (point n, m) of m-block b: panel[b * PSTR + n * IWVI_LDS + m]
-  const int Dk = iwvi_round_up(D, 4);
-  const int nd8 = (D + 7) / 8;
-  const TileSmem sl = tile_smem_layout(TP, Mp, ldz);
+  const TileSmem sl = tile_smem_layout(TP, Mp);
   double* panel = smem + sl.panel;
-  double* xs = smem + sl.xs;
-  double* xn = smem + sl.xn;
   double* gmb_s = smem + sl.gmb;
   double* gvb_s = smem + sl.gvb;
   double* gsum_s = smem + sl.gsum;
-  double* gs_s = smem + sl.gs;
-  double* gr_s = smem + sl.gr;
-  double* dls_s = smem + sl.dls;
-  double* red = smem + sl.red;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* aux = p.aux;
@@ -415,8 +285,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     if (warp > C::NW) return;      // padding of the producer warpgroup
     // producer warp: the block sequence is the same for every tile
     BwdSeq seq;
-    seq.NB = NB; seq.R = R; seq.npairs = al.npairs; seq.ldz = ldz;
-    seq.Zt = aux + al.off_zt; seq.Lmb = aux + al.off_lmb; seq.Lqb = aux + al.off_lqb;
+    seq.NB = NB; seq.R = R; seq.npairs = al.npairs;
+    seq.Lmb = aux + al.off_lmb; seq.Lqb = aux + al.off_lqb;
     const SaveLayout svp = iwvi_save_layout(T, M, R);
     seq.A_T = p.save + svp.off_a; seq.U_T = p.save + svp.off_u; seq.u_stride = svp.u_stride;
     seq.tp_bytes = TP * IWVI_LDS * 8;
@@ -437,36 +307,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   const int wn0 = (warp / C::WMG) * C::WN;
   const int colbar = BAR_COL + warp / C::WMG;
 
-  const double* zn = aux + al.off_zn;
   const double* qmu = aux + al.off_qmu;
-  const double* consts = aux + al.off_consts;
-  const double variance = consts[IWVI_C_VARIANCE];
   const SaveLayout sv = iwvi_save_layout(T, M, R);
   const double* A_T = p.save + sv.off_a;
   const double* U_T = p.save + sv.off_u;
   const double* gmb = p.ws + p.wl.off_gmb;
   const double* gvb = p.ws + p.wl.off_gvb;
   double* bbar_T = p.ws + p.wl.off_bbar;
-  double* mypart = p.ws + p.wl.off_tile + (size_t)(p.slot0 + blockIdx.x) * p.wl.tile_stride;
-
-  // this CTA's partial of dZ (accumulated across its tiles in global memory, exclusive owner) and dls
-  for (int idx = tid; idx < p.wl.tile_stride; idx += 256) mypart[idx] = 0.0;
-  // one of two point chains (iwvi_gp_rows_bwd_range): the finalize kernel will sum ALL slots of both chains, and the slots
-  // of this chain beyond this launch's grid may hold partials of an earlier call -- clear them (no other launch touches
-  // this chain's slots before the finalize kernel reads them)
-  if (p.n_slots > 0)
-    for (int s2 = blockIdx.x + gridDim.x; s2 < p.n_slots; s2 += gridDim.x) {
-      double* other = p.ws + p.wl.off_tile + (size_t)(p.slot0 + s2) * p.wl.tile_stride;
-      for (int idx = tid; idx < p.wl.tile_stride; idx += 256) other[idx] = 0.0;
-    }
-  dls_s[tid] = 0.0;
-  double dvar_acc = 0.0;
-  // lengthscale adjoint: sum_mn G_mn (x~_nd - z~_md)^2 = sum_n colsum_n x~_nd^2 + sum_m z~_md (rowsum_m z~_md - 2 (G x~)_md),
-  // assembled from quantities the dX / dZ sections hold anyway (the same expanded form GPflow uses for r^2 itself);
-  // this thread's slots are the input columns d = 8 b + 2 t + c
-  double dl_acc[4][2];
-#pragma unroll
-  for (int b = 0; b < 4; b++) { dl_acc[b][0] = 0.0; dl_acc[b][1] = 0.0; }
 
   PHASE_DECL;
   for (int tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
@@ -474,25 +321,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
     named_bar_sync(BAR_ALL, 256);
     PHASE_MARK(7);
 
-    // ---- per-point cotangents of this tile, x tile
+    // ---- per-point cotangents of this tile
     for (int idx = tid; idx < IWVI_MAX_R * TP; idx += 256) {
       const int r = idx / TP, n = idx - r * TP;
       gmb_s[idx] = gmb[(size_t)(n0 + n) * IWVI_MAX_R + r];
       gvb_s[idx] = gvb[(size_t)(n0 + n) * IWVI_MAX_R + r];
     }
-    for (int idx = tid; idx < TP * ldz; idx += 256) {
-      const int n = idx / ldz, k = idx - n * ldz;
-      double v = 0.0;
-      if (k < D && n0 + n < T) v = p.X[(size_t)(n0 + n) * D + k] * consts[IWVI_C_INVLS + k];
-      xs[idx] = v;
-    }
-    named_bar_sync(BAR_ALL, 256);
-    if (tid < TP) {
-      double s = 0.0;
-      for (int k = 0; k < Dk; k++) { const double v = xs[tid * ldz + k]; s += v * v; }
-      xn[tid] = s;
+    if (tid < TP) {   // (each thread sums the entries it reads itself: no barrier in between)
       double gsum = 0.0;
-      for (int r = 0; r < R; r++) gsum += gvb_s[r * TP + tid];
+      for (int r = 0; r < R; r++) gsum += gvb[(size_t)(n0 + tid) * IWVI_MAX_R + r];
       gsum_s[tid] = gsum;
     }
     named_bar_sync(BAR_ALL, 256);
@@ -651,173 +488,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
       if (lane < NB) {   // one bulk operation per m-block (block-major panel == block-major destination)
         bulk_s2g(dst + (int64_t)lane * IWVI_STAGE_DOUBLES, panel + lane * PSTR, TP * IWVI_LDS * 8);
         bulk_commit();
-        bulk_wait_read();   // the gram adjoint below overwrites the panel in place
+        bulk_wait_read();   // the next tile overwrites the panel
       }
       __syncwarp();
     }
-    named_bar_sync(BAR_ALL, 256);
-
     PHASE_MARK(4);
-    // ---- gram adjoint, block row by block row
-    double accx[4][2];
-#pragma unroll
-    for (int b = 0; b < 4; b++) { accx[b][0] = 0.0; accx[b][1] = 0.0; }
-    for (int i = 0; i < NB; i++) {
-      double znr[C::TM];                // |z|^2 of this thread's rows: fetched before the wait so the latency overlaps
-#pragma unroll
-      for (int a = 0; a < C::TM; a++) znr[a] = __ldg(zn + i * IWVI_BLK + wr0 + a * MR + g);
-      const double* st = pipe.wait();   // scaled inducing inputs of block i: st[m*ldz + k]
-      double acc[C::TM][C::TN][2];
-      acc_zero<C::TM, C::TN>(acc);
-      warp_gemm<C::TM, C::TN, 0, 0, C::WMG>(acc, st + wr0 * ldz, ldz, xs + wn0 * ldz, ldz, Dk, lane);
-      PHASE_MARK(8);
-      double cs[C::TN][2];
-#pragma unroll
-      for (int b = 0; b < C::TN; b++) { cs[b][0] = 0.0; cs[b][1] = 0.0; }
-#pragma unroll
-      for (int a = 0; a < C::TM; a++) {
-        double rs = 0.0;
-        const int ml = wr0 + a * MR + g;
-        const int mg = i * IWVI_BLK + ml;
-        double kv[C::TN * 2], dkv[C::TN * 2];
-#pragma unroll
-        for (int b = 0; b < C::TN; b++)
-#pragma unroll
-          for (int c = 0; c < 2; c++) kv[b * 2 + c] = znr[a] + xn[wn0 + b * 8 + 2 * t + c] - 2.0 * acc[a][b][c];
-        kern_n<KIND, C::TN * 2, true>(kv, dkv, variance);           // K and dK/dr2 of the row in lock step
-#pragma unroll
-        for (int b = 0; b < C::TN; b++)
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int n = wn0 + b * 8 + 2 * t + c;
-            const bool valid = (mg < M) && (n0 + n < T);
-            double* pe = panel + i * PSTR + n * IWVI_LDS + ml;
-            const double bb = 2.0 * *pe;
-            const double G = valid ? bb * dkv[b * 2 + c] : 0.0;
-            if (valid) dvar_acc += bb * kv[b * 2 + c];
-            *pe = G;
-            acc[a][b][c] = G;
-            cs[b][c] += G;
-            rs += G;
-          }
-        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-        if (t == 0) gr_s[((i & 1) * C::WNG + warp / C::WMG) * IWVI_BLK + wr0 + a * MR + g] = rs;
-      }
-#pragma unroll
-      for (int b = 0; b < C::TN; b++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          double v = cs[b][c];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) {   // one writer per slot: the first block row initialises, the others accumulate
-            double* gp = &gs_s[(warp % C::WMG) * TP + wn0 + b * 8 + 2 * t + c];
-            *gp = (i == 0 ? 0.0 : *gp) + v;
-          }
-        }
-      PHASE_MARK(9);
-      named_bar_sync(BAR_ALL, 256);   // G_i visible in the panel, gr_s complete
-      PHASE_MARK(10);
-
-      // dX partial: accx[n][d] += sum_{m in block} G[m][n] z~[m][d]   (warp w owns points 8w..8w+7)
-      if (warp < TP / 8) {
-        const double* ap = panel + i * PSTR + (warp * 8 + g) * IWVI_LDS + t;
-        switch (nd8) {   // compile-time column-tile count: no DMMA under a predicate
-          case 1: skinny_gemm<1>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
-          case 2: skinny_gemm<2>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
-          case 3: skinny_gemm<3>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
-          default: skinny_gemm<4>(accx, ap, 1, st + t * ldz + g, ldz, IWVI_BLK, g, ldz); break;
-        }
-      }
-      PHASE_MARK(11);
-      // dZ partial of block row i: sum_n G[m][n] x~[n][d]   (warp w owns rows 8w..8w+7 of the block)
-      {
-        double accz[4][2];
-#pragma unroll
-        for (int b = 0; b < 4; b++) { accz[b][0] = 0.0; accz[b][1] = 0.0; }
-        const double* ap = panel + i * PSTR + t * IWVI_LDS + warp * 8 + g;
-        switch (nd8) {
-          case 1: skinny_gemm<1>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
-          case 2: skinny_gemm<2>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
-          case 3: skinny_gemm<3>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
-          default: skinny_gemm<4>(accz, ap, IWVI_LDS, xs + t * ldz + g, ldz, TP, g, ldz); break;
-        }
-        const int ml = warp * 8 + g;
-        const int mg = i * IWVI_BLK + ml;
-        double grv = 0.0;
-#pragma unroll
-        for (int wg = 0; wg < C::WNG; wg++) grv += gr_s[((i & 1) * C::WNG + wg) * IWVI_BLK + ml];
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int dcol = b * 8 + 2 * t + c;
-            if (b < nd8 && dcol < D && mg < M) {
-              const double zv = st[ml * ldz + dcol];
-              red_add(&mypart[(size_t)mg * ldz + dcol], -2.0 * consts[IWVI_C_INVLS + dcol] * (accz[b][c] - zv * grv));
-              dl_acc[b][c] += zv * (grv * zv - 2.0 * accz[b][c]);   // z part of sum G (x~ - z~)^2, see dl_acc
-            }
-          }
-      }
-      pipe.release(lane);
-      PHASE_MARK(12);
-    }
-
-    PHASE_MARK(5);
-    // ---- dX += 2/ls (x~ colsum(G) - G^T z~)
-    if (warp < TP / 8) {
-      const int n = warp * 8 + g;
-      const size_t pt = (size_t)(n0 + n);
-      if (pt < (size_t)T) {
-        double gsv = 0.0;
-#pragma unroll
-        for (int wg = 0; wg < C::WMG; wg++) gsv += gs_s[wg * TP + n];
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int dcol = b * 8 + 2 * t + c;
-            if (b < nd8 && dcol < D) {
-              const double xv = xs[n * ldz + dcol];
-              red_add(&p.dX[pt * D + dcol], 2.0 * consts[IWVI_C_INVLS + dcol] * (xv * gsv - accx[b][c]));
-              dl_acc[b][c] += gsv * xv * xv;                        // x part of sum G (x~ - z~)^2
-            }
-          }
-      }
-    }
   }
-
-  PHASE_MARK(6);
   PHASE_FLUSH(1);
-  named_bar_sync(BAR_ALL, 256);
-  {
-    const double v = warp_sum(dvar_acc);
-    if (lane == 0) red[warp] = v;
-    named_bar_sync(BAR_ALL, 256);
-    if (tid == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < C::NW; w++) tot += red[w];
-      mypart[(size_t)Mp * ldz + 32] = tot / variance;
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < 4; b++)
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      double v = dl_acc[b][c];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (g == 0) dls_s[warp * 32 + b * 8 + 2 * t + c] = v;
-    }
-  named_bar_sync(BAR_ALL, 256);
-  if (tid < 32) {
-    double s = 0.0;
-    for (int w = 0; w < C::NW; w++) s += dls_s[w * 32 + tid];
-    mypart[(size_t)Mp * ldz + tid] = (tid < D) ? -2.0 * consts[IWVI_C_INVLS + tid] * s : 0.0;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1203,8 +880,8 @@ static int launch_tile(const BwdParams& p, int smem_bytes, cudaStream_t st) {
 // tile width of the tile kernel: 64 points when that still gives every SM at least two tiles (or 32 does not fit),
 // else 32 -- the rule of the forward kernel (iwvi_pick_tp), c2: 0.529 -> 0.507 ms/step.  With few points (c2: 160 tiles of 64 on 148 SMs) the
 // wider tile left most of the second wave empty.
-int pick_bwd_tp(int Tp, int Mp, int ldz, int nsm, int max_smem, int* smem_bytes) {
-  const int b64 = tile_smem_layout(64, Mp, ldz).total_doubles * 8, b32 = tile_smem_layout(32, Mp, ldz).total_doubles * 8;
+int pick_bwd_tp(int Tp, int Mp, int nsm, int max_smem, int* smem_bytes) {
+  const int b64 = tile_smem_layout(64, Mp).total_doubles * 8, b32 = tile_smem_layout(32, Mp).total_doubles * 8;
   const bool fits64 = b64 <= max_smem, fits32 = b32 <= max_smem;
   // (a single, partly filled wave of 64-point tiles is kept: at c1's size the narrower tiles measured slower)
   if (fits64 && (Tp / 64 >= 2 * nsm || Tp / 64 <= nsm || !fits32)) { *smem_bytes = b64; return 64; }
@@ -1236,7 +913,7 @@ extern "C" int iwvi_gp_bwd_tile_points(const iwvi_gp_desc* d) {
   if (device_info(&nsm, &max_smem) != IWVI_OK) return IWVI_ERR_LAUNCH;
   const AuxLayout al = iwvi_aux_layout(d->M, d->D, d->R);
   int smem_bytes = 0;
-  const int TP = pick_bwd_tp(iwvi_round_up(d->T, 128), al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
+  const int TP = pick_bwd_tp(iwvi_round_up(d->T, 128), al.Mp, nsm, max_smem, &smem_bytes);
   return TP < 0 ? IWVI_ERR_UNSUPPORTED : TP;
 }
 
@@ -1266,7 +943,7 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
   const bool fast = fast_reduce_ok(*d);
   p.wl = bwd_ws_layout(*d, nsm, fast);
   int smem_bytes = 0;
-  const int TP = pick_bwd_tp(p.wl.Tp, al.Mp, al.ldz, nsm, max_smem, &smem_bytes);
+  const int TP = pick_bwd_tp(p.wl.Tp, al.Mp, nsm, max_smem, &smem_bytes);
   if (TP < 0) return IWVI_ERR_UNSUPPORTED;
   p.ntiles = p.wl.Tp / TP;   // covers the zero-padded rows too, so every row of Bbar is written
   p.grid_tile = p.ntiles < nsm ? p.ntiles : nsm;
@@ -1274,6 +951,7 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
   const int only = d->flags & IWVI_FLAG_ONLY_MASK;
   p.q_lo = 0; p.q_n = d->R + 1; p.fin_part = 0; p.qmu_only = 0;
   p.tile0 = 0; p.tile1 = p.ntiles; p.slot0 = 0; p.n_slots = 0; p.epi0 = 0;
+  p.strip0 = 0; p.strip1 = p.wl.Tp / GRAM_PTS;
   int n_epi = p.wl.n_epi;
   if (ranged) {
     // one of the two point chains of the per-point half: [0, point_end) or [point_begin, T)
@@ -1283,12 +961,13 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
     if (point_begin % TP || (point_end != d->T && point_end % TP)) return IWVI_ERR_BAD_DESC;
     p.tile0 = (int)(point_begin / TP);
     p.tile1 = point_end == d->T ? p.ntiles : (int)(point_end / TP);
+    p.strip0 = p.tile0 * (TP / GRAM_PTS); p.strip1 = p.tile1 * (TP / GRAM_PTS);
     p.epi0 = (int)(point_begin / EPI_PTS);
     n_epi = (point_end == d->T ? p.wl.n_epi : (int)(point_end / EPI_PTS)) - p.epi0;
-    p.n_slots = nsm;
+    p.n_slots = p.wl.gram_slots;
     if (point_begin != 0) {
-      if (p.tile1 - p.tile0 > nsm) return IWVI_ERR_UNSUPPORTED;   // the second chain runs one tile per CTA, one slot each
-      p.slot0 = nsm;
+      if (p.tile1 - p.tile0 > nsm) return IWVI_ERR_UNSUPPORTED;   // the second chain runs one tile per CTA
+      p.slot0 = p.wl.gram_slots;
     }
   }
 
@@ -1299,6 +978,11 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
 
   if (!only || (only & IWVI_FLAG_ONLY_TILE)) {
     rc = TP == 64 ? launch_tile<64>(p, smem_bytes, st) : launch_tile<32>(p, smem_bytes, st);
+    if (rc != IWVI_OK) return rc;
+  }
+
+  if (!only || (only & IWVI_FLAG_ONLY_GRAM)) {
+    rc = iwvi_launch_gram_bwd(p, nsm, max_smem, st);
     if (rc != IWVI_OK) return rc;
   }
 
@@ -1349,8 +1033,10 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
   if (!only || (only & IWVI_FLAG_ONLY_FINAL)) {
     const FinalLayout fl = final_layout(*d, p.wl);
     p.fin_part = (do_a && do_b) ? 0 : (do_a ? 1 : 2);
-    // the per-CTA partials of the tile kernel: one chain's slots, or (IWVI_FLAG_TWO_CHAINS) both chains' slots
-    if (d->flags & IWVI_FLAG_TWO_CHAINS) p.grid_tile = 2 * nsm;
+    // the per-CTA partials of the gram-adjoint kernel: the slots of its one launch over all strips, or
+    // (IWVI_FLAG_TWO_CHAINS) both chains' slots
+    p.strip0 = 0; p.strip1 = p.wl.Tp / GRAM_PTS;
+    p.grid_tile = (d->flags & IWVI_FLAG_TWO_CHAINS) ? 2 * p.wl.gram_slots : iwvi_gram_bwd_grid(p);
     gp_finalize_bwd_kernel<<<fl.grid_elem + fl.grid_warp, 256, 0, st>>>(p);
     IWVI_CHECK_LAUNCH();
   }

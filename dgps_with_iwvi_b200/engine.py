@@ -497,7 +497,7 @@ class Engine:
                     # Points are independent through the backward chain of GP layers too: the full waves of tiles run on
                     # the main stream, the remaining tiles (one per CTA) as a second chain whose CTAs fill the SMs the
                     # last wave of every layer leaves idle; the parameter reductions wait for both.
-                    dpt = capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE)
+                    dpt = capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE | LIB.FLAG_ONLY_GRAM)
                     capi.gp_rows_bwd_range(dpt, *args, 0, self.split_bwd)
                     with torch.cuda.stream(self.side_f):
                         capi.gp_rows_bwd_range(dpt, *args, self.split_bwd, self.T)
@@ -507,7 +507,7 @@ class Engine:
                     if gi == 0:
                         self.side_b.wait_event(self.ev_rows_b[gi])
                 else:
-                    capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE), *args)
+                    capi.gp_rows_bwd(capi.with_flags(r['d'], fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE | LIB.FLAG_ONLY_GRAM), *args)
                 self.ev_rows[gi].record(main)
                 side.wait_event(self.ev_rows[gi])
                 pargs = (r['Lm'], r['aux'], self._cv(feat.Z), r['ls'], self._cv(base.variance), self._cv(layer.q_mu),

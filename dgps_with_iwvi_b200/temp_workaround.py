@@ -178,7 +178,7 @@ class _GPFullCov(torch.autograd.Function):
         ws = zr(capi.gp_bwd_ws_doubles(d))
         fl = d.flags | LIB.FLAG_NO_KDIAG
         args = (Lm, aux, save2, Xc, None, Ac, bc, None, None, gm, ones, dX, dZ, dls, dv, dqm, dqs, dLm, None, dA, db, ws)
-        capi.gp_rows_bwd(capi.with_flags(d, fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE), *args)
+        capi.gp_rows_bwd(capi.with_flags(d, fl | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE | LIB.FLAG_ONLY_GRAM), *args)
         # the A panel is the first slot of the save layout (csrc/common.cuh SaveLayout): [Tp/64][Mp/64][64][68]
         n_a = ((T + 127) // 128 * 2) * (Mp // 64) * 64 * 68
         save2[:n_a].copy_(save[:n_a])

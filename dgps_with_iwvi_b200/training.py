@@ -214,6 +214,20 @@ class Trainer:
         self._graphs = None
 
     def _capture(self, row0):
+        # The cyclic garbage collector must not run inside the capture: a finaliser that destroys CUDA objects of an
+        # earlier engine (graphs, streams, cached plans) is an operation the global capture mode forbids, and it
+        # invalidates the capture at whatever launch happens to come next.
+        import gc
+        gc.collect()
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            self._capture_impl(row0)
+        finally:
+            if was_enabled:
+                gc.enable()
+
+    def _capture_impl(self, row0):
         l0 = capi.LAUNCHES
         torch.cuda.synchronize()
         self._graphs = None

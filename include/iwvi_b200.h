@@ -71,15 +71,17 @@ extern "C" {
 #define IWVI_FLAG_SAMPLE 1  /* eps given: produce sample = mean + eps*sqrt(var) (temp_workaround.py:89-91) */
 #define IWVI_FLAG_SAVE   2  /* keep A, U, latent mean/var for the backward pass */
 #define IWVI_FLAG_ACCUM  4  /* iwvi_gp_prologue_bwd adds into its outputs instead of overwriting them */
-/* iwvi_gp_rows_bwd is a four-launch sequence (epilogue adjoint, tile kernel, split-K reduce, finalize).  When any of
- * these is set only the selected launches run, on the buffers the earlier ones have filled: used to time each alone,
- * and by the host to run EPI|TILE (dX, Bbar, per-CTA partials) on one stream and REDUCE|FINAL (every parameter
- * gradient) on another, so that the reductions of one layer overlap with the tile kernel of the layer below. */
+/* iwvi_gp_rows_bwd is a five-launch sequence (epilogue adjoint, tile kernel, gram adjoint, split-K reduce, finalize).
+ * When any of these is set only the selected launches run, on the buffers the earlier ones have filled: used to time
+ * each alone, and by the host to run EPI|TILE|GRAM (dX, Bbar, per-CTA partials) on one stream and REDUCE|FINAL (every
+ * parameter gradient) on another, so that the reductions of one layer overlap with the per-point kernels of the layer
+ * below.  REDUCE needs TILE's output only; FINAL needs GRAM's and REDUCE's. */
+#define IWVI_FLAG_ONLY_GRAM   8
 #define IWVI_FLAG_ONLY_EPI    16
 #define IWVI_FLAG_ONLY_TILE   32
 #define IWVI_FLAG_ONLY_REDUCE 64
 #define IWVI_FLAG_ONLY_FINAL  128
-#define IWVI_FLAG_ONLY_MASK   (16 | 32 | 64 | 128)
+#define IWVI_FLAG_ONLY_MASK   (8 | 16 | 32 | 64 | 128)
 /* The reduce + finalize launches in two halves, so that iwvi_gp_prologue_bwd (needs dLm, dZ, dls, dvariance only) can
  * overlap with the second one on another stream:  PART_A: dLm, dZ, dls, dvariance, dW, dmfA, dmfb;  PART_B: dq_mu, dq_sqrt.
  * Neither flag: everything.  With the split, run iwvi_gp_prologue_bwd with IWVI_FLAG_SKIP_KL after part A and with
@@ -123,6 +125,8 @@ typedef struct iwvi_gp_desc {
 } iwvi_gp_desc;
 
 int iwvi_version(void);
+/* Name of the CUDA runtime error behind the calling thread's most recent IWVI_ERR_LAUNCH ("cudaSuccess" if none yet). */
+const char* iwvi_last_cuda_error(void);
 
 /* derived sizes (host-side helpers, no device work) */
 int32_t iwvi_gp_mp(int32_t M);                         /* M padded to a multiple of 64                 */
@@ -179,7 +183,7 @@ int iwvi_gp_rows_bwd(const iwvi_gp_desc* d, const double* Lm, const double* aux,
                      double* dLm, double* dW, double* dmfA, double* dmfb, double* ws, void* stream);
 
 /*
- * The per-point half of iwvi_gp_rows_bwd (flags: IWVI_FLAG_ONLY_EPI and / or IWVI_FLAG_ONLY_TILE) over one of TWO point
+ * The per-point half of iwvi_gp_rows_bwd (flags: any of IWVI_FLAG_ONLY_EPI / _TILE / _GRAM) over one of TWO point
  * chains: [0, point_end) or [point_begin, T), split on a multiple of iwvi_gp_bwd_tile_points(d).  Points are independent
  * through the whole backward chain of GP layers as they are through the forward one, so the caller can run the chain of
  * the full waves of tiles and the chain of the remainder on two streams (the remainder, at most one tile per SM, fills
@@ -226,7 +230,7 @@ int64_t iwvi_gp_fullcov_ws_doubles(const iwvi_gp_desc* d, int32_t S, int32_t N);
  * adjoint as in TF's CholeskyGrad, symmetrised), N <= 256 (ws as for the forward call).  Cotangents d_sample [S*N,R] and d_cov [S,R,N,N] (either may
  * be NULL).  It prepares what iwvi_gp_rows_bwd needs to finish the job with its existing kernels:
  *   save2 (same size as save, zero-initialised by the caller): save2.A = A_s (sum_r H_r) / R, save2.U_r = U_rs H_r, with
- *         H_r the symmetric N x N cotangent of C_r.  Run iwvi_gp_rows_bwd(IWVI_FLAG_ONLY_EPI | ONLY_TILE | NO_KDIAG) on
+ *         H_r the symmetric N x N cotangent of C_r.  Run iwvi_gp_rows_bwd(IWVI_FLAG_ONLY_EPI | ONLY_TILE | ONLY_GRAM | NO_KDIAG) on
  *         save2 with d_mean = d_mean + d_sample, d_var = ones [T,R], d_sample = NULL; then copy save.A over save2.A
  *         and run the ONLY_REDUCE | ONLY_FINAL half on save2.
  *   dX_knn [S*N,D] and part [S,40] (dls partials at 0..D-1, dvariance partial at 32): the adjoint of k(X_s, X_s); the

@@ -488,7 +488,7 @@ def test_rows_bwd_range_two_chains_equal_whole_call(T, M, split):
                 o['dqs'], o['dLm'], o['dW'], o['dA'], o['db'], o['ws'])
     a, b = outs(), outs()
     capi.gp_rows_bwd(d, *args(a))
-    pt = capi.with_flags(d, d.flags | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE)
+    pt = capi.with_flags(d, d.flags | LIB.FLAG_ONLY_EPI | LIB.FLAG_ONLY_TILE | LIB.FLAG_ONLY_GRAM)
     s2 = torch.cuda.Stream()
     ev0, ev1 = torch.cuda.Event(), torch.cuda.Event()
     ev0.record()
