@@ -8,7 +8,7 @@
 #define EPI_PTS 32
 #define TILE_PART_EXTRA 40  // dls[32], dvariance, pad
 #ifndef GRAM_PTS
-#define GRAM_PTS 32         // points per strip of the gram-adjoint kernel
+#define GRAM_PTS 16         // points per strip of the gram-adjoint kernel (32: register spills at 128 registers per thread)
 #endif
 #define GRAM_THREADS 256
 #define GRAM_CTAS_PER_SM 2

@@ -27,16 +27,20 @@
 
 namespace {
 
-#define GRAM_SLOT_LD 40      // slot row stride: 128-bit stores of (2t, 2t+1) pairs are conflict-free
+#define GRAM_SLOT_LD (GRAM_PTS + 8)   // slot row stride (24 or 40): 128-bit stores of (2t, 2t+1) pairs are conflict-free
 #define GRAM_NSLOT 4         // warps 4-7 hand their strip sums to warps 0-3 through these
 
-struct GramSmem { int dz, xs, xn, slots, dlx, red, total_doubles, ldd, slot_rows; };
-__host__ __device__ inline GramSmem gram_smem_layout(int Mp, int ldz, int D, int ndx, int xcol, int pts) {
+struct GramSmem { int dz, zt, zn, xs, xn, slots, dlx, red, total_doubles, ldd, slot_rows; };
+__host__ __device__ inline GramSmem gram_smem_layout(int Mp, int ldz, int D, int ndx, int xcol, int pts, bool zsmem) {
   GramSmem s; int o = 0;
   s.ldd = D | 1;                                  // odd row stride of the dZ accumulator
   s.slot_rows = ndx + xcol + 1;                   // dX^T rows of the DMMA tiles, the extra column, colsum(G)
   s.dz = o;    o += Mp * s.ldd;
   o = (o + 1) & ~1;
+  // length-scaled inducing inputs and their squared norms: a shared-memory copy when that still leaves room for two
+  // CTAs per SM (ZSMEM), else read through L1
+  s.zt = o;    o += zsmem ? Mp * ldz : 0;
+  s.zn = o;    o += zsmem ? Mp : 0;
   s.xs = o;    o += 2 * pts * ldz;                // length-scaled inputs of the strip, double buffered
   s.xn = o;    o += 2 * pts;
   s.slots = o; o += GRAM_NSLOT * s.slot_rows * GRAM_SLOT_LD;
@@ -47,8 +51,15 @@ __host__ __device__ inline GramSmem gram_smem_layout(int Mp, int ldz, int D, int
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// A load that stays where it is written: ptxas sinks ordinary loads down to their first use to save registers, which
+// turns a prefetch back into an exposed HBM round trip (volatile asm keeps its order relative to the DMMAs, also volatile).
+__device__ __forceinline__ double ldg_here(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 
-template <int KIND, int ND8, bool XCOL, int NBT>
+template <int KIND, int ND8, bool XCOL, int NBT, bool ZSMEM>
 __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) double smem[];
   const iwvi_gp_desc& d = p.d;
@@ -58,7 +69,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
   constexpr int PTS = 8 * NBT;                    // points per strip
   constexpr int KS = XCOL ? ND8 * 2 : 0;          // k-steps of the gram product (XCOL: exactly the tiled columns)
   const int ks_n = XCOL ? KS : iwvi_round_up(D, 4) / 4;
-  const GramSmem sl = gram_smem_layout(Mp, ldz, D, NDX, XCOL ? 1 : 0, PTS);
+  const GramSmem sl = gram_smem_layout(Mp, ldz, D, NDX, XCOL ? 1 : 0, PTS, ZSMEM);
   const int ldd = sl.ldd;
   double* dz_s = smem + sl.dz;
   double* xs_b = smem + sl.xs;
@@ -71,8 +82,12 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const double* aux = p.aux;
-  const double* zt = aux + al.off_zt;
-  const double* zn = aux + al.off_zn;
+  const double* zt = ZSMEM ? smem + sl.zt : aux + al.off_zt;
+  const double* zn = ZSMEM ? smem + sl.zn : aux + al.off_zn;
+  if (ZSMEM) {
+    for (int idx = tid; idx < Mp * ldz; idx += GRAM_THREADS) smem[sl.zt + idx] = __ldg(aux + al.off_zt + idx);
+    for (int idx = tid; idx < Mp; idx += GRAM_THREADS) smem[sl.zn + idx] = __ldg(aux + al.off_zn + idx);
+  }
   const double* consts = aux + al.off_consts;
   const double variance = consts[IWVI_C_VARIANCE];
   const double* bbar = p.ws + p.wl.off_bbar;
@@ -100,7 +115,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int k = xl_j + 8 * q;
-      xv[q] = (xl_n < PTS && k < D && pt < (size_t)T) ? p.X[pt * D + k] * consts[IWVI_C_INVLS + k] : 0.0;
+      xv[q] = (xl_n < PTS && k < D && pt < (size_t)T) ? ldg_here(p.X + pt * D + k) : 0.0;
     }
   };
   auto store_x = [&](int buf, const double (&xv)[4]) {
@@ -109,8 +124,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int k = xl_j + 8 * q;
-      if (xl_n < PTS && k < ldz) xs[xl_n * ldz + k] = xv[q];
-      ss += xv[q] * xv[q];
+      const double v = (k < D) ? xv[q] * consts[IWVI_C_INVLS + k] : 0.0;
+      if (xl_n < PTS && k < ldz) xs[xl_n * ldz + k] = v;
+      ss += v * v;
     }
     if (xl_n < PTS && ldz > 32 && xl_j < ldz - 32) xs[xl_n * ldz + 32 + xl_j] = 0.0;
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
@@ -119,15 +135,24 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
     if (xl_n < PTS && xl_j == 0) xn_b[buf * PTS + xl_n] = ss;
   };
 
+  auto bb_of = [&](int n0) {
+    return bbar + ((int64_t)(n0 >> 6) * NB * IWVI_BLK + (n0 & 63) + 2 * t) * IWVI_LDS + warp * 8 + g;
+  };
   int s = p.strip0 + blockIdx.x, buf = 0;
+  double bb_pf[NBT][2];
+  const double* bb_base = bb_of(s * PTS);
   if (s < p.strip1) {
     double xv[4];
     load_x(s, xv);
+#pragma unroll
+    for (int b = 0; b < NBT; b++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) bb_pf[b][c] = ldg_here(bb_base + (8 * b + c) * IWVI_LDS);
     store_x(0, xv);
   }
   __syncthreads();
 
-  for (; s < p.strip1; s += gridDim.x, buf ^= 1) {
+  for (; s < p.strip1; s += gridDim.x, buf ^= 1, bb_base = bb_of(s * PTS)) {
     const int n0 = s * PTS;
     const double* xs = xs_b + buf * PTS * ldz;
     const double* xn = xn_b + buf * PTS;
@@ -148,8 +173,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
         xnr[b][c] = xn[n];
         xe[b][c] = XCOL ? xs[n * ldz + NDX] : 0.0;
       }
-    // Bbar / 2 of (point n0 + 8 b + 2 t + c, row 8 warp + g of block i): block-major [chunk][m-block][64][68]
-    const double* bb_base = bbar + ((int64_t)(n0 >> 6) * NB * IWVI_BLK + (n0 & 63) + 2 * t) * IWVI_LDS + warp * 8 + g;
+    // Bbar / 2 of (point n0 + 8 b + 2 t + c, row 8 warp + g of block i), block-major [chunk][m-block][64][68]: fetched
+    // one pass ahead (it comes from HBM / L2; everything else a pass reads is L1- or shared-memory resident)
+    const int n0_next = (s + (int)gridDim.x) * PTS;
+    const double* bb_next_strip = bb_of(n0_next);
 
     for (int i = 0; i < NB; i++) {
       const int mg = i * IWVI_BLK + warp * 8 + g;
@@ -158,9 +185,16 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
 #pragma unroll
       for (int b = 0; b < NBT; b++)
 #pragma unroll
-        for (int c = 0; c < 2; c++) bb[b][c] = __ldg(bb_base + (int64_t)i * IWVI_STAGE_DOUBLES + (8 * b + c) * IWVI_LDS);
-      const double znr = __ldg(zn + mg);
-      const double ze = XCOL ? __ldg(zrow + NDX) : 0.0;
+        for (int c = 0; c < 2; c++) bb[b][c] = bb_pf[b][c];
+      if (i + 1 < NB || has_next) {
+        const double* src = (i + 1 < NB) ? bb_base + (int64_t)(i + 1) * IWVI_STAGE_DOUBLES : bb_next_strip;
+#pragma unroll
+        for (int b = 0; b < NBT; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) bb_pf[b][c] = ldg_here(src + (8 * b + c) * IWVI_LDS);
+      }
+      const double znr = zn[mg];
+      const double ze = XCOL ? zrow[NDX] : 0.0;
 
       // ---- r2 tile: 8 rows x 32 points
       double acc[NBT][2];
@@ -169,13 +203,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
       if (XCOL) {
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
-          const double a = __ldg(zrow + 4 * ks + t);
+          const double a = zrow[4 * ks + t];
 #pragma unroll
           for (int b = 0; b < NBT; b++) dmma884(acc[b], a, xs[(8 * b + g) * ldz + 4 * ks + t]);
         }
       } else {
         for (int ks = 0; ks < ks_n; ks++) {
-          const double a = __ldg(zrow + 4 * ks + t);
+          const double a = zrow[4 * ks + t];
 #pragma unroll
           for (int b = 0; b < NBT; b++) dmma884(acc[b], a, xs[(8 * b + g) * ldz + 4 * ks + t]);
         }
@@ -228,7 +262,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
         for (int c = 0; c < 2; c++) {
           const int dcol = 8 * dt + 2 * t + c;
           if (8 * dt + 8 <= 20 || dcol < ldz) {
-            const double zv = __ldg(zrow + dcol);
+            const double zv = zrow[dcol];
             if (dcol < D) dz_s[mg * ldd + dcol] += accz[dt][c] - zv * rs;
             dlz[dt][c] = fma(zv, rs * zv - 2.0 * accz[dt][c], dlz[dt][c]);
           }
@@ -254,7 +288,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
         const double* zr2 = zt + (size_t)(i * IWVI_BLK + warp * 8 + 4 * h + t) * ldz + g;
         double za[ND8 > 0 ? ND8 : 1];
 #pragma unroll
-        for (int dt = 0; dt < ND8; dt++) za[dt] = (8 * dt + 8 <= 20 || 8 * dt + g < ldz) ? __ldg(zr2 + 8 * dt) : 0.0;
+        for (int dt = 0; dt < ND8; dt++) za[dt] = (8 * dt + 8 <= 20 || 8 * dt + g < ldz) ? zr2[8 * dt] : 0.0;
 #pragma unroll
         for (int b = 0; b < NBT; b++) {
           const double v0 = shfl_d(acc[b][0], src), v1 = shfl_d(acc[b][1], src);
@@ -334,7 +368,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
         for (int k = 0; k < GRAM_NSLOT; k++) sum += slots[k * slot_doubles + dcol * GRAM_SLOT_LD + n];
         if (pt < (size_t)T) {
           const double xv = xs[n * ldz + dcol];
-          p.dX[pt * D + dcol] += 2.0 * consts[IWVI_C_INVLS + dcol] * (xv * gsv - sum);
+          // (one adder per address in this launch, on top of what gp_epi_bwd_kernel stored: order is fixed)
+          red_add(&p.dX[pt * D + dcol], 2.0 * consts[IWVI_C_INVLS + dcol] * (xv * gsv - sum));
           dlx_s[dcol * PTS + n] += gsv * xv * xv;
         }
       }
@@ -366,9 +401,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
       for (int c = 0; c < 2; c++) red[warp * 32 + 8 * dt + 2 * t + c] = dt < ND8 ? dlz[dt < ND8 ? dt : 0][c] : 0.0;
   }
   __syncthreads();
-  for (int idx = tid; idx < Mp * ldz; idx += GRAM_THREADS) {
-    const int m = idx / ldz, k = idx - m * ldz;
-    mypart[idx] = (k < D) ? -2.0 * consts[IWVI_C_INVLS + k] * dz_s[m * ldd + k] : 0.0;
+  for (int k = lane; k < ldz; k += 32) {
+    const double sc = (k < D) ? -2.0 * consts[IWVI_C_INVLS + k] : 0.0;
+    for (int m = warp; m < Mp; m += GRAM_THREADS / 32) mypart[m * ldz + k] = (k < D) ? sc * dz_s[m * ldd + k] : 0.0;
   }
   if (tid < 32) {
     double sacc = 0.0;
@@ -386,14 +421,14 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
   }
 }
 
-template <int KIND, int ND8, bool XCOL>
-int launch_gram_v(const BwdParams& p, int nsm, int max_smem, cudaStream_t st) {
+template <int KIND, int ND8, bool XCOL, bool ZSMEM>
+int launch_gram_z(const BwdParams& p, int nsm, int max_smem, cudaStream_t st) {
   constexpr int NBT = GRAM_PTS / 8;
   const AuxLayout al = iwvi_aux_layout(p.d.M, p.d.D, p.d.R);
-  const GramSmem sl = gram_smem_layout(al.Mp, al.ldz, p.d.D, ND8 * 8, XCOL ? 1 : 0, GRAM_PTS);
+  const GramSmem sl = gram_smem_layout(al.Mp, al.ldz, p.d.D, ND8 * 8, XCOL ? 1 : 0, GRAM_PTS, ZSMEM);
   const int smem_bytes = sl.total_doubles * 8;
   if (smem_bytes > max_smem) return IWVI_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(gp_gram_bwd_kernel<KIND, ND8, XCOL, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
+  if (cudaFuncSetAttribute(gp_gram_bwd_kernel<KIND, ND8, XCOL, NBT, ZSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
       cudaSuccess)
     return IWVI_ERR_LAUNCH;
   const int ns = p.strip1 - p.strip0;
@@ -402,9 +437,18 @@ int launch_gram_v(const BwdParams& p, int nsm, int max_smem, cudaStream_t st) {
   const int per = (ns + p.wl.gram_slots - 1) / p.wl.gram_slots;
   const int grid = (ns + per - 1) / per;
   (void)nsm;
-  gp_gram_bwd_kernel<KIND, ND8, XCOL, NBT><<<grid, GRAM_THREADS, smem_bytes, st>>>(p);
+  gp_gram_bwd_kernel<KIND, ND8, XCOL, NBT, ZSMEM><<<grid, GRAM_THREADS, smem_bytes, st>>>(p);
   IWVI_CHECK_LAUNCH();
   return IWVI_OK;
+}
+
+template <int KIND, int ND8, bool XCOL>
+int launch_gram_v(const BwdParams& p, int nsm, int max_smem, cudaStream_t st) {
+  const AuxLayout al = iwvi_aux_layout(p.d.M, p.d.D, p.d.R);
+  const int with_z = gram_smem_layout(al.Mp, al.ldz, p.d.D, ND8 * 8, XCOL ? 1 : 0, GRAM_PTS, true).total_doubles * 8;
+  const int two_ctas = (228 * 1024) / GRAM_CTAS_PER_SM - 1024;   // shared memory per SM, 1 KB reserved per CTA
+  if (with_z <= two_ctas && with_z <= max_smem) return launch_gram_z<KIND, ND8, XCOL, true>(p, nsm, max_smem, st);
+  return launch_gram_z<KIND, ND8, XCOL, false>(p, nsm, max_smem, st);
 }
 
 template <int KIND>

@@ -245,14 +245,13 @@ __device__ __forceinline__ void lq_v_product(double (&acc)[TM][2][2], const doub
   static_assert(NG == 8, "lq_v_product is written out for eight groups of two k-steps");
 }
 
-struct TileSmem { int panel, stages, gmb, gvb, gsum, bars, total_doubles; };
+struct TileSmem { int panel, stages, gmb, gvb, bars, total_doubles; };
 __host__ __device__ inline TileSmem tile_smem_layout(int TP, int Mp) {
   TileSmem s; int o = 0;
   s.panel = o;  o += (Mp / IWVI_BLK) * TP * IWVI_LDS;   // block-major [m-block][point][68], see gp_rows_fwd.cu
   s.stages = o; o += IWVI_NST * IWVI_STAGE_DOUBLES;
   s.gmb = o;    o += IWVI_MAX_R * TP;
   s.gvb = o;    o += IWVI_MAX_R * TP;
-  s.gsum = o;   o += TP;
   s.bars = o;   o += 2 * IWVI_NST;
   s.total_doubles = o;
   return s;
@@ -271,7 +270,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   double* panel = smem + sl.panel;
   double* gmb_s = smem + sl.gmb;
   double* gvb_s = smem + sl.gvb;
-  double* gsum_s = smem + sl.gsum;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* aux = p.aux;
@@ -315,27 +313,38 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
   const double* gvb = p.ws + p.wl.off_gvb;
   double* bbar_T = p.ws + p.wl.off_bbar;
 
+  // Everything a warp touches outside the ring belongs to its COLUMN GROUP (the C::WMG warps that share WN points): panel
+  // columns, per-point cotangents, the Bbar stores.  So the tile boundary needs no block-wide barrier: each group waits
+  // for its own stores, swaps in its own cotangents (fetched into registers before the previous tile's back
+  // substitution, so that their latency is not exposed here) and goes on.
+  const bool group_lead = (warp % C::WMG == 0) && lane == 0;
+  const int gt = (warp % C::WMG) * 32 + lane;                 // thread index inside the column group
+  constexpr int GTH = C::WMG * 32;
+  constexpr int NPRE = IWVI_MAX_R * C::WN / GTH;              // cotangent entries per thread and array
+  static_assert(NPRE * GTH == IWVI_MAX_R * C::WN, "column-group cotangent loader");
+  double pre_m[NPRE], pre_v[NPRE];
+  auto prefetch_cot = [&](int tile_) {                        // entries (point wn0 + e / 8, r = e % 8): contiguous
+    const size_t base = ((size_t)tile_ * TP + wn0) * IWVI_MAX_R;
+#pragma unroll
+    for (int q = 0; q < NPRE; q++) {
+      asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(pre_m[q]) : "l"(gmb + base + gt + q * GTH));
+      asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(pre_v[q]) : "l"(gvb + base + gt + q * GTH));
+    }
+  };
+  if (p.tile0 + (int)blockIdx.x < p.tile1) prefetch_cot(p.tile0 + blockIdx.x);
+
   PHASE_DECL;
   for (int tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
     const int n0 = tile * TP;
-    named_bar_sync(BAR_ALL, 256);
-    PHASE_MARK(7);
-
-    // ---- per-point cotangents of this tile
-    for (int idx = tid; idx < IWVI_MAX_R * TP; idx += 256) {
-      const int r = idx / TP, n = idx - r * TP;
-      gmb_s[idx] = gmb[(size_t)(n0 + n) * IWVI_MAX_R + r];
-      gvb_s[idx] = gvb[(size_t)(n0 + n) * IWVI_MAX_R + r];
+    if (group_lead) bulk_wait_read();     // this group's Bbar stores of the previous tile have read the panel
+#pragma unroll
+    for (int q = 0; q < NPRE; q++) {
+      const int e = gt + q * GTH, n = e / IWVI_MAX_R, rr = e % IWVI_MAX_R;
+      gmb_s[rr * TP + wn0 + n] = pre_m[q];
+      gvb_s[rr * TP + wn0 + n] = pre_v[q];
     }
-    if (tid < TP) {   // (each thread sums the entries it reads itself: no barrier in between)
-      double gsum = 0.0;
-      for (int r = 0; r < R; r++) gsum += gvb[(size_t)(n0 + tid) * IWVI_MAX_R + r];
-      gsum_s[tid] = gsum;
-    }
-    named_bar_sync(BAR_ALL, 256);
+    named_bar_sync(colbar, GTH);
     PHASE_MARK(0);
-
-    PHASE_MARK(1);
 
     // ---- Abar / 2 = (q_mu gmean_bar^T) / 2 - A gsum  +  sum_r tril(Lq_r) V_r,  V_r = U_r * gvar_bar_r held as register
     //      B-fragments per k-block j (the saved U_r block comes through the ring, ahead of the tril(q_sqrt) blocks that
@@ -390,7 +399,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
 #pragma unroll
               for (int c = 0; c < 2; c++) {
                 const int n = wn0 + b * 8 + 2 * t + c;
-                const double gs_n = gsum_s[n];
+                double gs_n = 0.0;                      // sum_r gvar_bar_r (columns beyond R hold zeros)
+#pragma unroll
+                for (int rr = 0; rr < IWVI_MAX_R; rr++) gs_n += gvb_s[rr * TP + n];
 #pragma unroll
                 for (int a_ = 0; a_ < C::TM; a_++)
                   acc[a_][b][c] = 0.5 * acc[a_][b][c] - sa[n * IWVI_LDS + wr0 + a_ * MR + g] * gs_n;   // Abar / 2, first term
@@ -433,8 +444,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
         }
       }
     }
-    named_bar_sync(BAR_ALL, 256);
+    named_bar_sync(colbar, GTH);
     PHASE_MARK(2);
+    if (tile + (int)gridDim.x < p.tile1) prefetch_cot(tile + gridDim.x);   // (the cotangents in shared memory are dead from here on)
 
     // ---- Bbar / 2 = Lm^-T (Abar / 2), blocked back substitution in place.  The factor 2 is restored where Bbar is
     //      consumed: the gram adjoint below and the reduce kernel's dLm scale.
@@ -475,25 +487,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) gp_tile_bwd_kernel(const BwdP
 #pragma unroll
           for (int c = 0; c < 2; c++)
             panel[i * PSTR + (wn0 + b * 8 + 2 * t + c) * IWVI_LDS + wr0 + a * MR + g] = acc[a][b][c];
-      named_bar_sync(colbar, C::WMG * 32);
-    }
-
-    PHASE_MARK(3);
-    // ---- store Bbar / 2 (needed by the reduce kernel for dLm) with asynchronous TMA stores straight from the panel, one
-    //      512-byte run per (point, m-block); rows of invalid points are zero by construction
-    fence_async_smem();
-    named_bar_sync(BAR_ALL, 256);
-    if (warp == 0) {
-      double* dst = bbar_T + (int64_t)(n0 >> 6) * NB * IWVI_STAGE_DOUBLES + (int64_t)(n0 & 63) * IWVI_LDS;
-      if (lane < NB) {   // one bulk operation per m-block (block-major panel == block-major destination)
-        bulk_s2g(dst + (int64_t)lane * IWVI_STAGE_DOUBLES, panel + lane * PSTR, TP * IWVI_LDS * 8);
+      // Block row i of Bbar / 2 is final: this column group's WN points of it go out now (needed by the gram-adjoint
+      // and reduce kernels), as one asynchronous TMA store straight from the panel (block-major panel == block-major
+      // destination; rows of invalid points are zero by construction) that overlaps with the rows still to be solved.
+      fence_async_smem();
+      named_bar_sync(colbar, GTH);
+      if (group_lead) {
+        double* dst = bbar_T + ((int64_t)(n0 >> 6) * NB + i) * IWVI_STAGE_DOUBLES + (int64_t)((n0 & 63) + wn0) * IWVI_LDS;
+        bulk_s2g(dst, panel + i * PSTR + wn0 * IWVI_LDS, C::WN * IWVI_LDS * 8);
         bulk_commit();
-        bulk_wait_read();   // the next tile overwrites the panel
       }
-      __syncwarp();
     }
-    PHASE_MARK(4);
+    PHASE_MARK(3);
   }
+  if (group_lead) bulk_wait_read();       // the stores read this CTA's shared memory: it must outlive them
   PHASE_FLUSH(1);
 }
 
