@@ -103,14 +103,14 @@ def gp_prologue_fwd(d, Z, ls, variance, q_mu, q_sqrt, Lm, aux, kl, info):
 
 
 def gp_rows_fwd(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save):
-    _count(1)
+    _count(2 if d.flags & L.FLAG_SAVE else 1)      # row kernel (+ the per-point epilogue kernel of a saving call)
     L.check(L.load().iwvi_gp_rows_fwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(X), _ptr(W), _ptr(mfA), _ptr(mfb),
                                       _ptr(eps), _ptr(sample), _ptr(mean), _ptr(var), _ptr(save), _stream()),
             'iwvi_gp_rows_fwd')
 
 
 def gp_rows_fwd_range(d, Lm, aux, X, W, mfA, mfb, eps, sample, mean, var, save, point_begin, point_end):
-    _count(1)
+    _count(2 if d.flags & L.FLAG_SAVE else 1)
     L.check(L.load().iwvi_gp_rows_fwd_range(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(X), _ptr(W), _ptr(mfA), _ptr(mfb),
                                             _ptr(eps), _ptr(sample), _ptr(mean), _ptr(var), _ptr(save),
                                             int(point_begin), int(point_end), _stream()), 'iwvi_gp_rows_fwd_range')
@@ -125,8 +125,8 @@ def gp_tile_points(d):
 
 def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu, dq_sqrt,
                 dLm, dW, dmfA, dmfb, ws):
-    only = d.flags & 240
-    _count(bin(only).count('1') if only else 4)
+    only = d.flags & 248
+    _count(bin(only).count('1') if only else 5)
     L.check(L.load().iwvi_gp_rows_bwd(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(save), _ptr(X), _ptr(W), _ptr(mfA),
                                       _ptr(mfb), _ptr(eps), _ptr(d_sample), _ptr(d_mean), _ptr(d_var), _ptr(dX),
                                       _ptr(dZ), _ptr(dls), _ptr(dvariance), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(dLm),
@@ -135,7 +135,7 @@ def gp_rows_bwd(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, 
 
 def gp_rows_bwd_range(d, Lm, aux, save, X, W, mfA, mfb, eps, d_sample, d_mean, d_var, dX, dZ, dls, dvariance, dq_mu,
                       dq_sqrt, dLm, dW, dmfA, dmfb, ws, point_begin, point_end):
-    only = d.flags & 240
+    only = d.flags & 248
     _count(bin(only).count('1'))
     L.check(L.load().iwvi_gp_rows_bwd_range(C.byref(d), _ptr(Lm), _ptr(aux), _ptr(save), _ptr(X), _ptr(W), _ptr(mfA),
                                             _ptr(mfb), _ptr(eps), _ptr(d_sample), _ptr(d_mean), _ptr(d_var), _ptr(dX),

@@ -16,6 +16,7 @@
 // Nothing of size M x T touches HBM unless IWVI_FLAG_SAVE asks for A and U (kept for the backward pass: on B200 an
 // HBM round trip costs less than recomputing them at the 37 TFLOP/s fp64 rate).
 #include <type_traits>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -387,13 +388,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
 #pragma unroll
           for (int wg = 0; wg < C::WMG; wg++) us += usq[(r * C::WMG + wg) * TP + n];
           gv[r] = variance - fv0[n] + us;
-          gs[r] = do_sample ? gm[r] + p.eps[pt * R + r] * sqrt(gv[r]) : 0.0;
+          // (training: the per-point outputs are formed from the saved latent moments by gp_epi_fwd_kernel, at full
+          //  occupancy -- here, with one CTA per SM, their dependent global loads were 5 % of the kernel)
+          gs[r] = (do_sample && !do_save) ? gm[r] + p.eps[pt * R + r] * sqrt(gv[r]) : 0.0;
           if (do_save && q0 == 0) {
             p.save[sv.off_gvar + pt * R + r] = gv[r];
             p.save[sv.off_gmean + pt * R + r] = gm[r];
           }
         }
-        const int P = d.P;
+        const int P = do_save ? 0 : d.P;
         for (int q = q0; q < P; q += QT) {
           double mf = 0.0;
           if (d.mf == IWVI_MF_IDENTITY) mf = p.X[pt * D + q];
@@ -419,6 +422,58 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) gp_rows_fwd_kernel(const FwdPa
   }
   PHASE_FLUSH(0);
   if (warp == 0) bulk_wait_read();   // shared memory must outlive the last tile's bulk stores
+}
+
+// Per-point epilogue of a SAVING call (training), from the latent moments the row kernel left in `save`: sample / mean /
+// var = mixing by W (temp_workaround.py:142-145) + mean function (layers.py:46-48).  One CTA per 32 points: the points'
+// inputs and moments are staged in shared memory by coalesced loads (one global round trip per CTA), then thread
+// (point, output column) forms its outputs from shared memory and the stores are coalesced.  Same operation order as the
+// in-kernel epilogue above (the non-saving path), so both give identical bits.
+#define EPIF_PTS 32
+__global__ void __launch_bounds__(256) gp_epi_fwd_kernel(const FwdParams p, int pt0, int pt1) {
+  __shared__ double Ws[IWVI_MAX_P * IWVI_MAX_R], As[IWVI_MAX_D * IWVI_MAX_P], bs[IWVI_MAX_P];
+  __shared__ double Xs[EPIF_PTS * IWVI_MAX_D], gms[EPIF_PTS * IWVI_MAX_R], gvs[EPIF_PTS * IWVI_MAX_R], gss[EPIF_PTS * IWVI_MAX_R];
+  const iwvi_gp_desc& d = p.d;
+  const int R = d.R, P = d.P, D = d.D;
+  const SaveLayout sv = iwvi_save_layout(d.T, d.M, R);
+  const bool do_sample = (d.flags & IWVI_FLAG_SAMPLE) != 0;
+  const int tid = threadIdx.x;
+  const int64_t p0 = (int64_t)pt0 + (int64_t)blockIdx.x * EPIF_PTS;
+  const int npts = (int)((pt1 - p0) < EPIF_PTS ? (pt1 - p0) : EPIF_PTS);
+  if (d.mix) for (int i = tid; i < P * R; i += 256) Ws[i] = p.W[i];
+  if (d.mf == IWVI_MF_LINEAR) {
+    for (int i = tid; i < D * P; i += 256) As[i] = p.mfA[i];
+    if (tid < P) bs[tid] = p.mfb[tid];
+  }
+  if (d.mf != IWVI_MF_ZERO)
+    for (int i = tid; i < npts * D; i += 256) Xs[i] = p.X[p0 * D + i];
+  for (int i = tid; i < npts * R; i += 256) {
+    const double gm = p.save[sv.off_gmean + p0 * R + i], gv = p.save[sv.off_gvar + p0 * R + i];
+    gms[i] = gm; gvs[i] = gv;
+    gss[i] = do_sample ? gm + p.eps[p0 * R + i] * sqrt(gv) : 0.0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < npts * P; idx += 256) {
+    const int n = idx / P, q = idx - n * P;
+    const double *gm = gms + n * R, *gv = gvs + n * R, *gs = gss + n * R;
+    double mf = 0.0;
+    if (d.mf == IWVI_MF_IDENTITY) mf = Xs[n * D + q];
+    else if (d.mf == IWVI_MF_LINEAR) {
+      mf = bs[q];
+      for (int k = 0; k < D; k++) mf += Xs[n * D + k] * As[k * P + q];
+    }
+    double om, ov, os;
+    if (d.mix) {
+      om = 0.0; ov = 0.0; os = 0.0;
+      for (int r = 0; r < R; r++) {
+        const double w = Ws[q * R + r];
+        om += gm[r] * w; ov += gv[r] * w * w; os += gs[r] * w;
+      }
+    } else { om = gm[q]; ov = gv[q]; os = gs[q]; }
+    p.mean[p0 * P + idx] = om + mf;
+    p.var[p0 * P + idx] = ov;
+    if (do_sample) p.sample[p0 * P + idx] = os + mf;
+  }
 }
 
 template <int TP, int KIND>
@@ -524,8 +579,15 @@ extern "C" int iwvi_gp_rows_fwd_range(const iwvi_gp_desc* d, const double* Lm, c
   const bool partial = point_begin != 0 || point_end != d->T;
   const int grid = (partial || count < nsm) ? count : nsm;
   cudaStream_t st = (cudaStream_t)stream;
-  if (TP == 64) return launch_fwd<64>(p, smem_bytes, grid, st);
-  return launch_fwd<32>(p, smem_bytes, grid, st);
+  rc = TP == 64 ? launch_fwd<64>(p, smem_bytes, grid, st) : launch_fwd<32>(p, smem_bytes, grid, st);
+  if (rc != IWVI_OK) return rc;
+  if ((d->flags & IWVI_FLAG_SAVE) && !getenv("IWVI_SKIP_EPIF")) {
+    const int64_t npts = point_end - point_begin;
+    const int egrid = (int)((npts + EPIF_PTS - 1) / EPIF_PTS);
+    gp_epi_fwd_kernel<<<egrid, 256, 0, st>>>(p, (int)point_begin, (int)point_end);
+    IWVI_CHECK_LAUNCH();
+  }
+  return IWVI_OK;
 }
 
 extern "C" int iwvi_gp_rows_fwd(const iwvi_gp_desc* d, const double* Lm, const double* aux, const double* X,
