@@ -2,7 +2,7 @@
     profiles/ncu_<config>_summary.json   per kernel (the longest launch of each): duration, DRAM bytes, tensor/DMMA pipe
                                          activity, registers, shared memory, stall mix  (bench.py reads dram bytes from here)
     profiles/ncu_<config>_<round>.md     the same as a table plus the hottest source lines of each kernel
-usage: python tools/ncu_to_profiles.py gpurun_out/prof.ncu-rep c3 r01"""
+usage: python tools/ncu_to_profiles.py gpurun_out/prof.ncu-rep[,second.ncu-rep,...] c3 r01"""
 import csv
 import io
 import json
@@ -11,9 +11,20 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep, config, rnd = sys.argv[1], sys.argv[2], sys.argv[3]
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
+reps, config, rnd = sys.argv[1].split(','), sys.argv[2], sys.argv[3]
+rep = reps[0]
+rows = None
+for rp in reps:       # several single-kernel reports are concatenated (same metric set, same columns)
+    raw = subprocess.run(['ncu', '-i', rp, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    for r in rr[2:]:
+        r.append(rr[1])      # units differ between reports (Kbyte / Mbyte, us / ms): each row keeps its own
+        r.append(rp)
+    if rows is None:
+        rows = rr
+    else:
+        assert rr[0] == rows[0], 'reports with different metric sets'
+        rows += rr[2:]
 hdr, units = rows[0], rows[1]
 
 
@@ -51,7 +62,7 @@ def num(r, k):
         v = float(r[i].replace(',', ''))
     except ValueError:      # 'no data'
         return None
-    u = units[i]
+    u = r[-2][i]
     if k.endswith('_bytes') and u in ('Kbyte', 'Mbyte', 'Gbyte'):
         v *= {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
     if k == 'duration_us' and u in ('ns', 'ms', 's'):
@@ -64,7 +75,8 @@ for ki, r in enumerate(rows[2:]):
     name = r[iname]
     short = name.split('(')[0].split('::')[-1].split('<')[0]
     d = {k: num(r, k) for k in WANT}
-    d['kernel_index'] = ki
+    d['kernel_index'] = ki if len(reps) == 1 else 0
+    d['report'] = os.path.basename(r[-1])
     d['full_name'] = name[:120]
     st = [(h.split('issue_stalled_')[1].split('_per_')[0], float(r[i])) for i, h in enumerate(hdr)
           if h.startswith('smsp__average_warp') and 'issue_stalled' in h and h.endswith('_per_issue_active.ratio') and r[i]]
@@ -76,14 +88,14 @@ for ki, r in enumerate(rows[2:]):
     if short not in best or (d['duration_us'] or 0) > (best[short]['duration_us'] or 0):
         best[short] = d
 
-out = {'config': config, 'round': rnd, 'report': os.path.basename(rep),
+out = {'config': config, 'round': rnd, 'report': ','.join(os.path.basename(x) for x in reps),
        'note': 'per-launch values from one `ncu --set full --clock-control none` capture (cold caches, serialised '
                'launches); the longest launch of each kernel = an inner GP layer', 'kernels': best}
 os.makedirs(os.path.join(ROOT, 'profiles'), exist_ok=True)
 with open(os.path.join(ROOT, 'profiles', 'ncu_%s_summary.json' % config), 'w') as f:
     json.dump(out, f, indent=1, sort_keys=True)
 
-md = ['# ncu --set full, config %s, %s (%s)\n' % (config, rnd, os.path.basename(rep)),
+md = ['# ncu --set full, config %s, %s (%s)\n' % (config, rnd, ', '.join(os.path.basename(x) for x in reps)),
       '| kernel | us | DMMA pipe busy | tensor pipe active % | DRAM read MB | DRAM write MB | regs | dyn smem KB | L2 hit % |',
       '|---|---|---|---|---|---|---|---|---|']
 for k, d in sorted(best.items()):
@@ -95,7 +107,8 @@ for k, d in sorted(best.items()):
 md.append('')
 for k, d in sorted(best.items()):
     md.append('## %s (launch %d): stalls per issue %s\n' % (k, d['kernel_index'], d['stalls_per_issue']))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_lines.py'), rep, str(d['kernel_index']), k],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_lines.py'),
+                        os.path.join(os.path.dirname(rep), d['report']), str(d['kernel_index']), k],
                        capture_output=True, text=True)
     md.append('```\n' + (r.stdout.strip() or r.stderr.strip())[:6000] + '\n```\n')
 with open(os.path.join(ROOT, 'profiles', 'ncu_%s_%s.md' % (config, rnd)), 'w') as f:
