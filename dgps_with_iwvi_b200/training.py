@@ -269,7 +269,7 @@ class Trainer:
         (model.X, model.Y): the gather is one launch instead of torch indexing + copies."""
         return self.step_device(None, None, row0_global, idx=idx_local)
 
-    def step_device(self, X_local, Y_local, row0_global=None, idx=None):
+    def step_device(self, X_local, Y_local, row0_global=None, idx=None, data=None):
         """One training step on this rank's rows; returns the global ELBO as a 1-element device tensor (no sync)."""
         self.t += 1
         row0 = self.rank * self.B_local if row0_global is None else row0_global
@@ -286,7 +286,8 @@ class Trainer:
             self.lr_dev.fill_(lr)
             self._lr_host = lr
         if idx is not None:
-            self.engine.set_batch_indices(self.model.X, self.model.Y, idx)
+            Xd, Yd = data if data is not None else (self.model.X, self.model.Y)
+            self.engine.set_batch_indices(Xd, Yd, idx)
         else:
             self.engine.set_batch(X_local, Y_local)
         # (the graph is captured once the pipelined once-per-layer stages are in place: a step that still has to open
@@ -313,6 +314,54 @@ class Trainer:
     def step(self, X_host, Y_host):
         """End-to-end call: host (pinned) minibatch in, ELBO (python float) out."""
         return float(self.step_device(X_host, Y_host).item())
+
+    def step_pipelined(self, X_host, Y_host):
+        """End-to-end call for a training LOOP: host (pinned) minibatch in, ELBO (python float) of the PREVIOUS call out
+        (None on the first call; `flush()` returns the last one).  The host does not wait for the step it has just
+        enqueued: the minibatch goes to a device staging buffer on a copy stream while the previous step is still
+        running, one gather launch moves it into the plan's buffers when that step has finished, and the ELBO comes
+        back through a pinned word that is read one call later.  Every step still pays its own host-to-device copy
+        and its own device-to-host read; what is hidden is their latency and the launch latency of the step graph.
+        The caller may reuse X_host / Y_host as soon as the NEXT call has returned."""
+        if getattr(self, '_pipe', None) is None:
+            eng, dev = self.engine, self.flat.device
+            z = lambda *sh: torch.zeros(*sh, dtype=torch.float64, device=dev)
+            self._pipe = {
+                'X': [z(eng.B, eng.Dx) for _ in range(2)], 'Y': [z(eng.B, eng.Dy) for _ in range(2)],
+                'loss': [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)],
+                'h2d': [torch.cuda.Event() for _ in range(2)], 'free': [torch.cuda.Event() for _ in range(2)],
+                'done': [torch.cuda.Event() for _ in range(2)], 'stream': torch.cuda.Stream(device=dev),
+                'idx': torch.arange(eng.B, dtype=torch.int64, device=dev), 'i': 0}
+        P = self._pipe
+        i = P['i']
+        k = i % 2
+        main = torch.cuda.current_stream()
+        cs = P['stream']
+        if i >= 2:
+            cs.wait_event(P['free'][k])            # the gather of call i - 2 has read this staging buffer
+        with torch.cuda.stream(cs):
+            P['X'][k].copy_(torch.as_tensor(X_host, dtype=torch.float64).reshape(P['X'][k].shape), non_blocking=True)
+            P['Y'][k].copy_(torch.as_tensor(Y_host, dtype=torch.float64).reshape(P['Y'][k].shape), non_blocking=True)
+            P['h2d'][k].record(cs)
+        main.wait_event(P['h2d'][k])
+        loss = self.step_device(None, None, idx=P['idx'], data=(P['X'][k], P['Y'][k]))
+        P['free'][k].record(main)
+        P['loss'][k].copy_(loss, non_blocking=True)
+        P['done'][k].record(main)
+        P['i'] = i + 1
+        if i == 0:
+            return None
+        P['done'][1 - k].synchronize()
+        return float(P['loss'][1 - k][0])
+
+    def flush(self):
+        """ELBO of the last step_pipelined call (waits for it)."""
+        P = getattr(self, '_pipe', None)
+        if P is None or P['i'] == 0:
+            return None
+        k = (P['i'] - 1) % 2
+        P['done'][k].synchronize()
+        return float(P['loss'][k][0])
 
 
 class ReferenceIterationTrainer(Trainer):

@@ -101,3 +101,27 @@ def test_positive_fwd_and_plain_adam_entry_points():
         x, m, v = AO.adam_step(x, g, m, v, t, 3e-3, n_pos, mask)
         np.testing.assert_allclose(xd.cpu().numpy(), x, rtol=1e-13, atol=1e-15)
         np.testing.assert_allclose(th.cpu().numpy(), AO.positive_forward(x[:n_pos]), rtol=1e-14, atol=0)
+
+
+def test_step_pipelined_matches_step():
+    """Trainer.step_pipelined (staged H2D on a copy stream, ELBO handed back one call later) trains exactly like
+    Trainer.step: same ELBO sequence, same parameters after six steps (eager steps, capture, replays)."""
+    outs = []
+    for pipelined in (False, True):
+        X, Y, model, tr, B = _trainer(True, 1e-2, 0.98)
+        Xh, Yh = torch.as_tensor(X).pin_memory(), torch.as_tensor(Y).pin_memory()
+        elbos = []
+        for i in range(6):
+            xs, ys = Xh[i * B:(i + 1) * B].clone().pin_memory(), Yh[i * B:(i + 1) * B].clone().pin_memory()
+            if pipelined:
+                v = tr.step_pipelined(xs, ys)
+                if v is not None:
+                    elbos.append(v)
+            else:
+                elbos.append(tr.step(xs, ys))
+        if pipelined:
+            elbos.append(tr.flush())
+        outs.append((elbos, tr.flat.x.cpu().numpy().copy()))
+    assert len(outs[0][0]) == len(outs[1][0]) == 6
+    np.testing.assert_array_equal(np.array(outs[0][0]), np.array(outs[1][0]))
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
