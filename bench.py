@@ -319,14 +319,16 @@ def workload_config(name, cfg, gpus):
               'rewrites every buffer; no explicit flush'}
 
 
-def arm_description(arm, gpus):
+def arm_description(arm, gpus, exchange=None):
     if arm == 'reference':
         return {'parallelism': 'none: rank 0 alone, all host cores (torch intra-op threads)',
                 'optimizer': 'none (forward + autograd of the IW-ELBO only: this arm does LESS work per step than the GPU arm)',
                 'launch': 'oracle/iwvi_oracle.py, float64 torch-CPU op-for-op restatement of the reference (TF1/GPflow1 '
                           'cannot be installed here); each step = one evaluation on a bounded row sample of the minibatch'}
-    return {'parallelism': 'dp%d rows sharded, one NCCL all-reduce of the packed fp64 gradient bucket' % gpus,
-            'optimizer': 'adam (fused kernel)', 'launch': 'whole step replayed as a CUDA graph'}
+    return {'parallelism': 'dp%d rows sharded; per-layer segments of the packed fp64 gradient bucket exchanged inside the step '
+                           'graph, %s' % (gpus, exchange or 'no exchange at one rank'),
+            'optimizer': 'adam (fused kernel, segment-wise as each layer\'s gradients are final)',
+            'launch': 'whole step replayed as a CUDA graph'}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -509,7 +511,10 @@ def main():
         'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': workload_config(args.config, cfg, world),
-        'arm': arm_description('b200', world),
+        'arm': arm_description('b200', world, None if world == 1 else (
+            'one-shot all-reduce over NVLink peer memory (iwvi_dp_push / iwvi_dp_reduce: pack, transfer, rank-ordered sum and '
+            'unpack in two launches)' if trainer.gbucket.p2p is not None else
+            'NCCL all-reduce between a pack and an unpack launch (peer mapping unavailable: %s)' % trainer.gbucket.p2p_error)),
         'clocks': clocks,
         'e2e': {'value': Bg * K / (ms_e2e / 1e3 / args.steps), 'unit': 'KxN samples/s',
                 'ms_per_step': ms_e2e / args.steps, 'h2d_bytes_per_step': B * (cfg['D'] + 1) * 8 + 0,

@@ -81,6 +81,8 @@ SIGNATURES = {
                                                C.c_int32, P]),
     'iwvi_positive_fwd': (C.c_int, [P, P, C.c_int64, P]),
     'iwvi_batch_gather': (C.c_int, [P, P, P, C.c_int32, C.c_int32, C.c_int32, P, P, P, P]),
+    'iwvi_dp_push': (C.c_int, [P, P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, P, P, P, P, P]),
+    'iwvi_dp_reduce': (C.c_int, [P, P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, P, P, P, P, P]),
     'iwvi_debug_stamp': (C.c_int, [P, C.c_int32, P]),
     'iwvi_probe_dmma': (C.c_int, [P, C.c_int32, C.c_int32, C.c_int32, P]),
     'iwvi_adam_step': (C.c_int, [P] * 6 + [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,

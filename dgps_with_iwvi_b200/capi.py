@@ -266,3 +266,19 @@ def batch_gather(X, Y, idx, B, Dx, Dy, Xb, Yb, XYb):
     _count(1)
     L.check(L.load().iwvi_batch_gather(_ptr(X), _ptr(Y), _ptr(idx), int(B), int(Dx), int(Dy), _ptr(Xb), _ptr(Yb),
                                        _ptr(XYb), _stream()), 'iwvi_batch_gather')
+
+
+def dp_push(g, index, n, seg_off, bucket_len, seg, rank, world, recv_ptrs, flag_ptrs, epoch, counters):
+    """recv_ptrs / flag_ptrs: ctypes arrays (c_uint64 * world) of device addresses (host memory)."""
+    _count(1)
+    L.check(L.load().iwvi_dp_push(_ptr(g), _ptr(index), int(n), int(seg_off), int(bucket_len), int(seg), int(rank),
+                                  int(world), C.cast(recv_ptrs, C.c_void_p), C.cast(flag_ptrs, C.c_void_p), _ptr(epoch),
+                                  _ptr(counters), _stream()), 'iwvi_dp_push')
+
+
+def dp_reduce(g, index, n, seg_off, bucket_len, seg, world, recv_local, flags_local, epoch, counters):
+    """recv_local / flags_local: integer device addresses of this rank's own receive buffer and flag array."""
+    _count(2)
+    L.check(L.load().iwvi_dp_reduce(_ptr(g), _ptr(index), int(n), int(seg_off), int(bucket_len), int(seg), int(world),
+                                    C.c_void_p(int(recv_local)), C.c_void_p(int(flags_local)), _ptr(epoch),
+                                    _ptr(counters), _stream()), 'iwvi_dp_reduce')

@@ -37,7 +37,7 @@ class GradBucket:
     parameters and the ELBO slot last (tag 'final'), so that a segment can be all-reduced on its own as soon as the backward
     pass has completed it (allreduce(tag)) -- or the whole bucket in one call (allreduce())."""
 
-    def __init__(self, flat, always_reduce=(), process_group=None, groups=()):
+    def __init__(self, flat, always_reduce=(), process_group=None, groups=(), p2p=False):
         from .params import LowerTriangular
         self.flat, self.pg = flat, process_group
         flat.refresh_mask()
@@ -65,6 +65,47 @@ class GradBucket:
             off += idx.numel()
         self.index = torch.cat(parts).contiguous()
         self.buf = torch.zeros(self.index.numel(), dtype=torch.float64, device=flat.device)
+        self.seg_ids = {tag: i for i, tag in enumerate(self.segments)}
+        self.p2p = None
+        self.p2p_error = None
+        if p2p and flat.device.type == 'cuda' and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size(process_group) > 1 and dist.get_backend(process_group) == 'nccl':
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """One-shot all-reduce over NVLink peer memory (csrc/dp_exchange.cu): a symmetric receive buffer
+        [2][world][bucket] + flag words per (segment, rank), mapped into every peer by torch's symmetric memory
+        (allocation + handle exchange only; the data path is iwvi_dp_push / iwvi_dp_reduce).  Falls back to NCCL, and
+        says so in `p2p_error`, if the mapping cannot be established."""
+        import ctypes as C
+        world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+        n, nseg = self.index.numel(), len(self.segments) + 1            # (+1: the whole bucket as one segment)
+        ok = torch.ones(1, device=self.flat.device)
+        try:
+            if world > 16:
+                raise RuntimeError('more than IWVI_DP_MAX_RANKS ranks')
+            import torch.distributed._symmetric_memory as symm_mem
+            recv_doubles = 2 * world * n
+            t = symm_mem.empty(recv_doubles + nseg * world, dtype=torch.float64, device=self.flat.device)
+            hdl = symm_mem.rendezvous(t, self.pg if self.pg is not None else dist.group.WORLD)
+            t.zero_()
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+        except Exception as e:  # noqa: BLE001
+            self.p2p_error = '%s: %s' % (type(e).__name__, str(e).splitlines()[0] if str(e) else '')
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)       # all ranks or none (and: everybody has zeroed)
+        torch.cuda.synchronize()
+        if ok.item() == 0:
+            if self.p2p_error is None:
+                self.p2p_error = 'a peer could not map the symmetric buffer'
+            return
+        self.p2p = {
+            'world': world, 'rank': rank, 'n': n, 'buf': t, 'hdl': hdl,
+            'recv_ptrs': (C.c_uint64 * world)(*ptrs),
+            'flag_ptrs': (C.c_uint64 * world)(*[p + 8 * recv_doubles for p in ptrs]),
+            'recv_local': ptrs[rank], 'flags_local': ptrs[rank] + 8 * recv_doubles,
+            'epoch': torch.zeros(nseg, dtype=torch.int64, device=self.flat.device),
+            'counters': torch.zeros(2 * nseg, dtype=torch.int32, device=self.flat.device)}
 
     def allreduce(self, tag=None):
         """pack -> all_reduce(SUM) -> unpack of one segment (or of the whole bucket), in stream order on the current
@@ -73,6 +114,15 @@ class GradBucket:
         if a == b:
             return
         g, idx, buf = self.flat.g, self.index[a:b], self.buf[a:b]
+        if self.p2p is not None:
+            # pack + transfer + rank-ordered sum + unpack in two launches over the peers' memory
+            P = self.p2p
+            seg = len(self.segments) if tag is None else self.seg_ids[tag]
+            capi.dp_push(g, idx, b - a, a, P['n'], seg, P['rank'], P['world'], P['recv_ptrs'], P['flag_ptrs'],
+                         P['epoch'], P['counters'])
+            capi.dp_reduce(g, idx, b - a, a, P['n'], seg, P['world'], P['recv_local'], P['flags_local'],
+                           P['epoch'], P['counters'])
+            return
         torch.index_select(g, 0, idx, out=buf)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
         g.index_copy_(0, idx, buf)
@@ -150,7 +200,8 @@ class Trainer:
                     groups.append((('gp_q', 0), [layer.q_mu, layer.q_sqrt]))
                 else:
                     groups.append((('gp', r['gi']), hyp + [layer.q_mu, layer.q_sqrt]))
-        self.gbucket = GradBucket(self.flat, self.always_reduce, self.pg, groups)
+        import os
+        self.gbucket = GradBucket(self.flat, self.always_reduce, self.pg, groups, p2p=self.world_size > 1 and not os.environ.get('IWVI_DP_NCCL'))
         # Adam masks: trainable entries of each segment (the packed index of a segment also holds always_reduce entries
         # and, for 'final', the ELBO slot: the trainable mask filters those out)
         f = self.flat

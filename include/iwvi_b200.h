@@ -320,6 +320,26 @@ int iwvi_normal_fill_counter(double* out, int64_t n_points, int32_t C, int64_t f
 int iwvi_batch_gather(const double* X, const double* Y, const int64_t* idx, int32_t B, int32_t Dx, int32_t Dy,
                       double* Xb, double* Yb, double* XYb, void* stream);
 
+/* ---- exchange step of data-parallel training (the reference is single-device: its optimiser consumes
+ * tf.gradients of the whole minibatch, build_models.py:293-295) as a one-shot all-reduce over NVLink peer memory ----
+ * Every rank owns a receive buffer recv [2][world][bucket_len] doubles and a flag array [n_segments][world] of 64-bit
+ * words, both ZERO-INITIALISED and mapped into every peer (e.g. torch.distributed._symmetric_memory); recv_ptrs /
+ * flag_ptrs are HOST arrays [world] of this rank's device addresses of every rank's buffers (own one included).
+ * epoch [n_segments] (64-bit, zero-initialised) and counters [2 * n_segments] (32-bit, zero-initialised) are plain
+ * device memory of the calling rank.  A segment = n entries g[index[0 .. n-1]] (index: int64 device indices into the
+ * gradient bucket g), stored at seg_off inside the packed bucket of bucket_len entries.
+ *   iwvi_dp_push    stores this rank's segment into every peer's slot and publishes the segment's next epoch;
+ *   iwvi_dp_reduce  (same stream, after the push) waits for all ranks' epochs, sums the slots in rank order (bit-identical
+ *                   on every rank) into g[index[.]] and advances the epoch.
+ * All ranks must issue the same sequence of (push, reduce) pairs per segment.  Both launches replay inside a CUDA graph. */
+#define IWVI_DP_MAX_RANKS 16
+int iwvi_dp_push(const double* g, const int64_t* index, int64_t n, int64_t seg_off, int64_t bucket_len, int32_t seg,
+                 int32_t rank, int32_t world, const uint64_t* recv_ptrs, const uint64_t* flag_ptrs, const uint64_t* epoch,
+                 uint32_t* counters, void* stream);
+int iwvi_dp_reduce(double* g, const int64_t* index, int64_t n, int64_t seg_off, int64_t bucket_len, int32_t seg,
+                   int32_t world, const double* recv_local, const uint64_t* flags_local, uint64_t* epoch,
+                   uint32_t* counters, void* stream);
+
 /* ---- optimiser step either side of the path (experiments/build_models.py:284-295) ----
  * gpflow.transforms.positive (Log1pe): theta = softplus(x) + 1e-6 for the first n entries. */
 int iwvi_positive_fwd(const double* x, double* theta, int64_t n, void* stream);

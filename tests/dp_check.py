@@ -64,6 +64,16 @@ def main():
         assert tr._graphs is not None and (tr._graphs[1] is None) == (mode == 'overlap_graph')
         finals[mode] = (FlatParams.of(m2).x.clone(), float(loss.item()))
         tr.engine.check_info()
+        # replicas must agree bit for bit (the peer-memory exchange sums the ranks' slots in rank order on every rank; NCCL's
+        # all-reduce is bitwise reproducible across ranks as well)
+        xs = [torch.empty_like(finals[mode][0]) for _ in range(world)]
+        dist.all_gather(xs, finals[mode][0])
+        same = all(torch.equal(xs[0], xi) for xi in xs)
+        if rank == 0:
+            print('Trainer dp%d [%s]: exchange = %s, replicas bit-identical = %s'
+                  % (world, mode, 'peer memory (iwvi_dp_push / iwvi_dp_reduce)' if tr.gbucket.p2p is not None
+                     else 'NCCL (%s)' % tr.gbucket.p2p_error, same), flush=True)
+        ok = ok and same
     if rank == 0:
         m1 = build_model(X, Y, 'L1_G4_G3', M=M, num_IW_samples=K, minibatch_size=Bg, mode='IWAE', seed=3)
         tr1 = Trainer(m1, Bg, lr=1e-2, seed=4, distributed=False)
