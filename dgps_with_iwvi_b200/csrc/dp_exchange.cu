@@ -86,8 +86,13 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(double* __restrict__ g, 
 __global__ void __launch_bounds__(32) dp_wait_kernel(int seg, int world, const unsigned long long* flags,
                                                      const unsigned long long* epoch) {
   const unsigned long long e = epoch[seg] + 1ull;
-  if ((int)threadIdx.x < world)
-    while (ld_acquire_sys(flags + (size_t)seg * world + threadIdx.x) < e) {}
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + (size_t)seg * world + threadIdx.x) < e) {
+      // a peer that never arrives (crashed rank) must not leave this GPU spinning for ever: fail loudly after ~60 s
+      if (clock64() - t0 > 120000000000ll) __trap();
+    }
+  }
 }
 
 inline int dp_grid(int64_t n) {

@@ -27,7 +27,8 @@ inline int pick_reduce_split(int items, int npairs, int nchunks, int nsm) {
   int bestS = 1;
   double best = 1e300;
   const int ns = nsm < 256 ? (nsm > 0 ? nsm : 1) : 256;
-  for (int S = 1; S <= 16 && S <= nchunks; S++) {
+  const int s_cap = nchunks >= 2048 ? 32 : 16;      // (c4-sized problems: 32 measured 3 % faster than 16; c3: 14)
+  for (int S = 1; S <= s_cap && S <= nchunks; S++) {
     const int cps = (nchunks + S - 1) / S;
     double freeat[256];
     for (int k = 0; k < ns; k++) freeat[k] = 0.0;
