@@ -367,6 +367,17 @@ struct RingT {
     }
     it++;
   }
+  // producer warp: the block plus a small second transaction (`xbytes` from `xsrc` to `xdst`) signalled on the same barrier
+  __device__ __forceinline__ void produce2(const BlockSrc& b, void* xdst, const void* xsrc, uint32_t xbytes, int lane) {
+    const uint32_t s = it % NST;
+    if (lane == 0) {
+      mbar_wait(&empty[s], ((it / NST) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(&full[s], b.bytes + xbytes);
+      bulk_g2s(stages + (size_t)s * IWVI_STAGE_DOUBLES, b.src, b.bytes, &full[s]);
+      if (xbytes) bulk_g2s(xdst, xsrc, xbytes, &full[s]);
+    }
+    it++;
+  }
   // consumer warps: oldest outstanding block (offset k blocks ahead, k < NST)
   __device__ __forceinline__ const double* wait(uint32_t k = 0) {
     const uint32_t i2 = it + k, s = i2 % NST;

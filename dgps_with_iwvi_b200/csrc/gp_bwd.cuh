@@ -14,7 +14,7 @@
 #define GRAM_CTAS_PER_SM 2
 
 struct BwdWs {   // workspace layout (doubles)
-  int64_t off_bbar, off_gmb, off_gvb, off_epi, off_tile, off_red, off_qred, total;
+  int64_t off_bbar, off_gmb, off_gvb, off_gvt, off_epi, off_tile, off_red, off_qred, total;
   int Tp, n_epi, grid_tile, S, npairs, chunks_per_split, tile_stride;
   int gram_slots;   // per-CTA partial slots of the gram-adjoint kernel per point chain (its grid never exceeds this)
 };
@@ -84,6 +84,7 @@ inline BwdWs bwd_ws_layout(const iwvi_gp_desc& d, int nsm, bool fast = false) {
   w.off_bbar = o; o += sv.u_stride;            // Bbar / 2, block-major like the saved A
   w.off_gmb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
   w.off_gvb = o;  o += (int64_t)w.Tp * IWVI_MAX_R;
+  w.off_gvt = o;  o += (int64_t)w.Tp * IWVI_MAX_R;   // 2 gvar_bar transposed [r][Tp]: the reduce kernel's per-chunk scale vectors, one bulk copy each
   w.off_epi = o;  o += (int64_t)w.n_epi * EPI_STRIDE;
   w.gram_slots = GRAM_CTAS_PER_SM * nsm;
   w.off_tile = o; o += (int64_t)2 * w.gram_slots * w.tile_stride;  // per-CTA partials of the gram-adjoint kernel: two point chains (see iwvi_gp_rows_bwd_range)

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) gp_epi_bwd_kernel(const BwdParams p) {
     if (pt < (size_t)p.wl.Tp) {
       gmb[pt * IWVI_MAX_R + r] = gm_;
       gvb[pt * IWVI_MAX_R + r] = gv_;
+      p.ws[p.wl.off_gvt + (size_t)r * p.wl.Tp + pt] = 2.0 * gv_;
     }
   }
   // mean-function part of dX (the gram part is added by the tile kernel): Identity copies, Linear is the skinny product
@@ -520,25 +521,23 @@ struct RedSeq {
   __device__ __forceinline__ void advance() { if (which == 0) which = 1; else { which = 0; ++c; } }
 };
 
-struct ReduceLoopArgs { const double *gvb, *gmb; int q; bool is_lm; int c0, c1, wm0, wn0, lane; };
+#define RED_SC_SLOTS (RED_NST / 2)   // one scale vector per chunk step in flight
+struct ReduceLoopArgs { const double *gvb, *gmb, *sc_s; int q; bool is_lm; int c0, c1, wm0, wn0, lane; };
 
+// The per-point factors 2 gvar_bar_r[k] of dLq_r = 2 tril(A diag(gvar_bar_r) U_r^T) arrive in shared memory with the
+// chunk itself (gp_epi_bwd_kernel leaves them transposed, [r][Tp], so that a chunk's 64 factors are ONE 512-byte bulk
+// copy signalled on the B block's barrier): no per-lane gather from global memory and no 2 x 16 registers of prefetch
+// buffer in the product loop (which had cost it its software pipelining: 0.410 -> 0.383 ms per launch at c3 with the
+// factors out of the way).  dLm = -tril(Bbar A^T) (Bbar / 2 is stored) needs the constant -2 only: applied once to the
+// finished sums (exact).
 template <bool QMU>
 __device__ __forceinline__ void reduce_loop(RingT<RED_NST>& pipe, const ReduceLoopArgs& la, double (&acc)[4][2][2],
                                             double (&accq)[4][2]) {
   const int g = la.lane >> 2, t = la.lane & 3;
-  // per-point scale factors of this lane's k indices (k = 4*ks + t), prefetched one chunk ahead so that their
-  // global-memory latency hides behind the previous chunk's DMMAs
-  double sc[16], scn[16];
-  auto load_scales = [&](int c, double (&s_)[16]) {
-    const size_t pt0 = (size_t)c * IWVI_BLK + t;
-#pragma unroll
-    for (int ks = 0; ks < 16; ks++) s_[ks] = la.is_lm ? -2.0 : 2.0 * __ldg(la.gvb + (pt0 + 4 * ks) * IWVI_MAX_R + la.q);
-  };
-  load_scales(la.c0, sc);
   for (int c = la.c0; c < la.c1; c++) {
-    if (c + 1 < la.c1) load_scales(c + 1, scn);
+    const double* scs = la.sc_s + ((pipe.it / 2) % RED_SC_SLOTS) * IWVI_BLK + t;
     const double* sa = pipe.wait(0);   // [k = point][m]  -> A operand, k-major
-    const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major
+    const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major (+ the chunk's scale vector)
     const double* ap = sa + t * IWVI_LDS + la.wm0 + g;
     const double* bp = sb + t * IWVI_LDS + la.wn0 + g;
 #pragma unroll
@@ -547,8 +546,14 @@ __device__ __forceinline__ void reduce_loop(RingT<RED_NST>& pipe, const ReduceLo
       double a[4], b[2];
 #pragma unroll
       for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
+      if (la.is_lm) {
 #pragma unroll
-      for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * sc[ks];
+        for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8];
+      } else {
+        const double sck = scs[k0];
+#pragma unroll
+        for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * sck;
+      }
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -560,8 +565,12 @@ __device__ __forceinline__ void reduce_loop(RingT<RED_NST>& pipe, const ReduceLo
       }
     }
     pipe.release(la.lane, 2);
+  }
+  if (la.is_lm) {
 #pragma unroll
-    for (int ks = 0; ks < 16; ks++) sc[ks] = scn[ks];
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) { acc[i][j][0] *= -2.0; acc[i][j][1] *= -2.0; }
   }
 }
 
@@ -581,15 +590,8 @@ __device__ __forceinline__ void reduce_diag(RingT<RED_NST>& pipe, const ReduceLo
   for (int j = 0; j < N1; j++) { acc1[j][0] = 0.0; acc1[j][1] = 0.0; }
 #pragma unroll
   for (int j = 0; j < N2; j++) { acc2[j][0] = 0.0; acc2[j][1] = 0.0; }
-  double sc[8], scn[8];
-  auto load_scales = [&](int c, double (&s_)[8]) {
-    const size_t pt0 = (size_t)c * IWVI_BLK + 32 * half + t;
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) s_[ks] = la.is_lm ? -2.0 : 2.0 * __ldg(la.gvb + (pt0 + 4 * ks) * IWVI_MAX_R + la.q);
-  };
-  load_scales(la.c0, sc);
   for (int c = la.c0; c < la.c1; c++) {
-    if (c + 1 < la.c1) load_scales(c + 1, scn);
+    const double* scs = la.sc_s + ((pipe.it / 2) % RED_SC_SLOTS) * IWVI_BLK + 32 * half + t;   // (see reduce_loop)
     const double* sa = pipe.wait(0);
     const double* sb = pipe.wait(1);
     const double* ap = sa + (32 * half + t) * IWVI_LDS + g;
@@ -598,7 +600,8 @@ __device__ __forceinline__ void reduce_diag(RingT<RED_NST>& pipe, const ReduceLo
     for (int ks = 0; ks < 8; ks++) {
       const int k0 = 4 * ks;
       const double a1u = ap[k0 * IWVI_LDS + R1 * 8], a2u = ap[k0 * IWVI_LDS + R2 * 8];
-      const double a1 = a1u * sc[ks], a2 = a2u * sc[ks];
+      const double sck = la.is_lm ? 1.0 : scs[k0];
+      const double a1 = a1u * sck, a2 = a2u * sck;
 #pragma unroll
       for (int j = 0; j < N2; j++) {
         const double b = bp[k0 * IWVI_LDS + j * 8];
@@ -612,9 +615,8 @@ __device__ __forceinline__ void reduce_diag(RingT<RED_NST>& pipe, const ReduceLo
       }
     }
     pipe.release(la.lane, 2);
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) sc[ks] = scn[ks];
   }
+  const double fin = la.is_lm ? -2.0 : 1.0;     // dLm: the constant factor, once (exact)
   // combine the two k halves through the ring memory, once EVERY consumer warp has finished reading its last stages
   named_bar_sync(1, 256);
   double* scr = scratch + (size_t)((warp & 3) * 32 + la.lane) * 24;
@@ -630,11 +632,11 @@ __device__ __forceinline__ void reduce_diag(RingT<RED_NST>& pipe, const ReduceLo
 #pragma unroll
     for (int j = 0; j < N1; j++)
 #pragma unroll
-      for (int c = 0; c < 2; c++) out[(R1 * 8 + g) * IWVI_BLK + j * 8 + 2 * t + c] = acc1[j][c] + scr[2 * j + c];
+      for (int c = 0; c < 2; c++) out[(R1 * 8 + g) * IWVI_BLK + j * 8 + 2 * t + c] = fin * (acc1[j][c] + scr[2 * j + c]);
 #pragma unroll
     for (int j = 0; j < N2; j++)
 #pragma unroll
-      for (int c = 0; c < 2; c++) out[(R2 * 8 + g) * IWVI_BLK + j * 8 + 2 * t + c] = acc2[j][c] + scr[2 * (N1 + j) + c];
+      for (int c = 0; c < 2; c++) out[(R2 * 8 + g) * IWVI_BLK + j * 8 + 2 * t + c] = fin * (acc2[j][c] + scr[2 * (N1 + j) + c]);
     if (QMU) {
 #pragma unroll
       for (int c = 0; c < 2; c++) {
@@ -654,6 +656,7 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
   const BwdWs& wl = p.wl;
   double* stages = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RED_NST * IWVI_STAGE_DOUBLES);
+  double* sc_s = smem + RED_NST * IWVI_STAGE_DOUBLES + 2 * RED_NST;      // [RED_SC_SLOTS][64] scale vectors
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -693,13 +696,22 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
     seq.Aop = (is_lm ? bbar_T : A_T) + (size_t)bi * IWVI_STAGE_DOUBLES;
     seq.Bop = (is_lm ? A_T : U_T + (size_t)q * sv.u_stride) + (size_t)bj * IWVI_STAGE_DOUBLES;
     seq.NB = NB; seq.c = c0; seq.c1 = c1; seq.which = 0;
-    while (!seq.done()) { pipe.produce(seq.get(), lane); seq.advance(); }
+    const double* gvt = p.ws + wl.off_gvt + (size_t)(is_lm ? 0 : q) * wl.Tp;
+    while (!seq.done()) {
+      // the B block of a chunk travels with the chunk's 64 per-point factors (dLq_r only)
+      if (seq.which == 1 && !is_lm)
+        pipe.produce2(seq.get(), sc_s + ((pipe.it / 2) % RED_SC_SLOTS) * IWVI_BLK, gvt + (size_t)seq.c * IWVI_BLK,
+                      IWVI_BLK * 8, lane);
+      else
+        pipe.produce(seq.get(), lane);
+      seq.advance();
+    }
     return;
   }
   double* out = p.ws + wl.off_red + (((size_t)q * wl.S + s) * wl.npairs + pair) * IWVI_BLK * IWVI_BLK;
   double* oq = p.ws + wl.off_qred + ((size_t)s * NB + bi) * IWVI_BLK * IWVI_MAX_R;
   if (bi == bj) {
-    const ReduceLoopArgs la = {gvb, gmb, q, is_lm, c0, c1, 0, 0, lane};
+    const ReduceLoopArgs la = {gvb, gmb, sc_s, q, is_lm, c0, c1, 0, 0, lane};
     if (do_qmu) {
       switch (warp & 3) {
         case 0: reduce_diag<0, true>(pipe, la, warp, stages, out, oq); break;
@@ -729,7 +741,7 @@ __global__ void __launch_bounds__(RED_THREADS, 1) gp_reduce_bwd_kernel(const Bwd
   // The two warps of the few CTAs that also form dq_mu = A gmean_bar take a separate copy of the loop: a DMMA that is
   // merely predicated off still occupies the FP64 pipe for its full 16 cycles (measured: 24 instead of 16 cycles per
   // useful DMMA when the ride-along sat under a predicate in the common loop).
-  const ReduceLoopArgs la = {gvb, gmb, q, is_lm, c0, c1, wm0, wn0, lane};
+  const ReduceLoopArgs la = {gvb, gmb, sc_s, q, is_lm, c0, c1, wm0, wn0, lane};
   if (do_qmu && wn0 == 0) reduce_loop<true>(pipe, la, acc, accq);
   else reduce_loop<false>(pipe, la, acc, accq);
 
@@ -999,7 +1011,7 @@ static int rows_bwd_impl(const iwvi_gp_desc* d, const double* Lm, const double* 
   const int part = d->flags & (IWVI_FLAG_PART_A | IWVI_FLAG_PART_B);
   const bool do_a = part != IWVI_FLAG_PART_B, do_b = part != IWVI_FLAG_PART_A;
   if (!only || (only & IWVI_FLAG_ONLY_REDUCE)) {
-    const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * RED_NST) * 8;
+    const int red_smem = (RED_NST * IWVI_STAGE_DOUBLES + 2 * RED_NST + RED_SC_SLOTS * IWVI_BLK) * 8;
     if (cudaFuncSetAttribute(gp_reduce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem) != cudaSuccess)
       return IWVI_ERR_LAUNCH;
     const int per_q = p.wl.S * p.wl.npairs;

@@ -246,6 +246,7 @@ class Engine:
         self.ev_pbwd = [torch.cuda.Event() for _ in range(self.n_gp)]
         self.side_b = torch.cuda.Stream(device=dev)      # second half of the first GP layer's reductions (backward)
         self.ev_part_b = torch.cuda.Event()
+        self.ev_part_a = torch.cuda.Event()
         self.ev_elbo, self.ev_loss = torch.cuda.Event(), torch.cuda.Event()
         self._loss_pending = False
         # training: called as grad_hook(tag) on the stream where the gradients named by `tag` have just been completed --
@@ -527,6 +528,7 @@ class Engine:
                         hp.wait_event(self.ev_rows_b[gi])
                     with torch.cuda.stream(hp):
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_A), *args)
+                        self.ev_part_a.record(hp)
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_SKIP_KL), *pargs)
                         if not r['ard']:
                             self._fold_dls(r)
@@ -534,6 +536,14 @@ class Engine:
                             self.grad_hook(('gp_h', 0))
                         self.ev_pbwd[gi].record(hp)
                     self.side_b.wait_event(self.ev_rows[gi])
+                    # Part B starts when part A's reduce + finalize launches are done (its adjoint chain still overlaps):
+                    # the two reduce launches must NOT run side by side.  With both in flight (part A's 140 CTAs on the
+                    # high-priority stream arriving while part B's CTAs stream their operands) part B's sums came out
+                    # wrong by about one point's contribution in about one cold evaluation out of two once the reduce
+                    # kernel's product loop got faster (round 2; bisected on the GPU: any ordering that keeps the two
+                    # reduce grids apart is clean, any that lets them overlap is not; the memory they touch is disjoint,
+                    # the mechanism is not understood).  Part A is one short wave, so nothing is lost by the order.
+                    self.side_b.wait_event(self.ev_part_a)
                     with torch.cuda.stream(self.side_b):
                         capi.gp_rows_bwd(capi.with_flags(r['d'], red | LIB.FLAG_PART_B), *args)
                         capi.gp_prologue_bwd(capi.with_flags(r['d'], LIB.FLAG_ACCUM | LIB.FLAG_ONLY_KL), *pargs)
