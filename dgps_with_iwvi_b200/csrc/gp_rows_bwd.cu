@@ -540,29 +540,41 @@ __device__ __forceinline__ void reduce_loop(RingT<RED_NST>& pipe, const ReduceLo
     const double* sb = pipe.wait(1);   // [k = point][n]  -> B operand, k-major (+ the chunk's scale vector)
     const double* ap = sa + t * IWVI_LDS + la.wm0 + g;
     const double* bp = sb + t * IWVI_LDS + la.wn0 + g;
+    // The B fragments of HALF a chunk are loaded and scaled in one burst (16 LDS + 16 DMUL, kept in registers), a warp
+    // barrier keeps ptxas from sinking the DMULs back between the DMMAs (where they stall the shared FP64 pipe far beyond
+    // their own issue time), and the product loop is pure LDS (A fragments) + DMMA.
 #pragma unroll
-    for (int ks = 0; ks < 16; ks++) {
-      const int k0 = 4 * ks;
-      double a[4], b[2];
+    for (int h = 0; h < 2; h++) {
+      double b[8][2];
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
-      if (la.is_lm) {
+      for (int kk = 0; kk < 8; kk++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8];
-      } else {
-        const double sck = scs[k0];
+        for (int j = 0; j < 2; j++) b[kk][j] = bp[4 * (8 * h + kk) * IWVI_LDS + j * 8];
+      if (!la.is_lm) {
 #pragma unroll
-        for (int j = 0; j < 2; j++) b[j] = bp[k0 * IWVI_LDS + j * 8] * sck;
+        for (int kk = 0; kk < 8; kk++) {
+          const double sck = scs[4 * (8 * h + kk)];
+          b[kk][0] *= sck; b[kk][1] *= sck;
+        }
       }
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int kk = 0; kk < 8; kk++) {
+        const int k0 = 4 * (8 * h + kk);
+        double a[4];
 #pragma unroll
-        for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[j]);
-      if (QMU) {
-        const double bq = __ldg(la.gmb + ((size_t)c * IWVI_BLK + t + k0) * IWVI_MAX_R + g);
+        for (int i = 0; i < 4; i++) a[i] = ap[k0 * IWVI_LDS + i * 8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) dmma884(acc[i][j], a[i], b[kk][j]);
+        if (QMU) {
+          const double bq = __ldg(la.gmb + ((size_t)c * IWVI_BLK + t + k0) * IWVI_MAX_R + g);
+#pragma unroll
+          for (int i = 0; i < 4; i++) dmma884(accq[i], a[i], bq);
+        }
       }
+      __syncwarp();
     }
     pipe.release(la.lane, 2);
   }
