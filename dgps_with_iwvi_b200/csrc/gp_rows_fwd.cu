@@ -581,7 +581,7 @@ extern "C" int iwvi_gp_rows_fwd_range(const iwvi_gp_desc* d, const double* Lm, c
   cudaStream_t st = (cudaStream_t)stream;
   rc = TP == 64 ? launch_fwd<64>(p, smem_bytes, grid, st) : launch_fwd<32>(p, smem_bytes, grid, st);
   if (rc != IWVI_OK) return rc;
-  if ((d->flags & IWVI_FLAG_SAVE) && !getenv("IWVI_SKIP_EPIF")) {
+  if (d->flags & IWVI_FLAG_SAVE) {
     const int64_t npts = point_end - point_begin;
     const int egrid = (int)((npts + EPIF_PTS - 1) / EPIF_PTS);
     gp_epi_fwd_kernel<<<egrid, 256, 0, st>>>(p, (int)point_begin, (int)point_end);
