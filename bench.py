@@ -532,6 +532,9 @@ def main():
         'roofline': {'bound': 'tensor', 'kernel': dom['kernel'], 'achieved': dom['tflops'], 'peak': peak_tf,
                      'unit': 'TFLOP/s', 'frac': dom['tflops'] / peak_tf,
                      'traffic': ncu_traffic(args.config, dom['kernel']),
+                     'traffic_scope': 'dram bytes of ONE launch in the committed ncu capture (profiles/ncu_%s_summary.json): the '
+                                      'per-point kernels run there as the chain of full waves (296 of 400 tiles at c3), '
+                                      'the timed launch above covers all tiles' % args.config,
                      'peak_source': 'FP64 DMMA issue-rate probe measured in this run (fp64_peak; round-1 pool figure '
                                     '%.2f); MEASURED_PEAKS.json carries only bf16 and HBM' % FP64_DMMA_PEAK_TFLOPS},
         'kernels': kern,
