@@ -85,7 +85,12 @@ extern "C" {
 /* The reduce + finalize launches in two halves, so that iwvi_gp_prologue_bwd (needs dLm, dZ, dls, dvariance only) can
  * overlap with the second one on another stream:  PART_A: dLm, dZ, dls, dvariance, dW, dmfA, dmfb;  PART_B: dq_mu, dq_sqrt.
  * Neither flag: everything.  With the split, run iwvi_gp_prologue_bwd with IWVI_FLAG_SKIP_KL after part A and with
- * IWVI_FLAG_ONLY_KL (the whitened-KL adjoint, which adds into dq_mu / dq_sqrt) after part B. */
+ * IWVI_FLAG_ONLY_KL (the whitened-KL adjoint, which adds into dq_mu / dq_sqrt) after part B.
+ * ORDER the two halves: launch part B's REDUCE only after part A's REDUCE + FINAL launches have completed (an event
+ * between the two streams; iwvi_gp_prologue_bwd of part A may still overlap part B).  With the two REDUCE launches in
+ * flight together part B's sums were observed to come out wrong by about one point's contribution on cold buffers
+ * (DESIGN.md section 8); the memory they touch is disjoint, the cause is not understood, the order costs nothing
+ * measurable (part A is one short wave). */
 #define IWVI_FLAG_PART_A   256
 #define IWVI_FLAG_PART_B   512
 #define IWVI_FLAG_SKIP_KL  1024
