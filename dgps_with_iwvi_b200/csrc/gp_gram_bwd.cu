@@ -14,8 +14,9 @@
 // kernel that keeps ONE CTA of eight warps per SM because its panel fills the shared memory, so nothing hid their
 // latencies.  Here the same arithmetic runs with two CTAs (sixteen warps) per SM, no block-wide barrier inside the
 // work loop and no shared-memory round trip for G:
-//   * a CTA walks over strips of 32 points; per strip and 64-row block of inducing points, warp w owns rows 8w..8w+7:
-//     r2 as one 8 x 32 DMMA tile row, K and dK/dr2 in registers, G in the accumulator layout;
+//   * a CTA walks over strips of GRAM_PTS = 16 points (32 would need ~160 registers per thread and spill at the 128
+//     that two CTAs per SM allow); per strip and 64-row block of inducing points, warp w owns rows 8w..8w+7: r2 as one
+//     8 x 16 DMMA tile row, K and dK/dr2 in registers, G in the accumulator layout;
 //   * G x~ uses the accumulator registers directly as the DMMA A operand (the k index of an m8n8k4 product is free to
 //     permute: k-step (b, c) pairs G[m][8b + 2t + c] with x~[8b + 2t + c][.]);
 //   * G^T z~ needs G as a B operand: two shuffles per fragment move it there, no shared memory;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
       const double znr = zn[mg];
       const double ze = XCOL ? zrow[NDX] : 0.0;
 
-      // ---- r2 tile: 8 rows x 32 points
+      // ---- r2 tile: 8 rows x PTS points
       double acc[NBT][2];
 #pragma unroll
       for (int b = 0; b < NBT; b++) { acc[b][0] = 0.0; acc[b][1] = 0.0; }
