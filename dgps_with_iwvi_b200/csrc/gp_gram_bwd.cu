@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
           if (XCOL) sxy = fma(ze, xe[b][c], sxy);
           kv[b * 2 + c] = znr + xnr[b][c] - 2.0 * sxy;
         }
-      kern_n<KIND, 2 * NBT, true>(kv, dkv, variance);
+      // RBF: dK/dr2 = -K/2, so G = 2 (Bbar/2) dK/dr2 = -(Bbar/2) K and sum Bbar K = -2 sum G: neither dK/dr2 nor the
+      // variance adjoint needs instructions of its own (the latter falls out of the column sums, once per strip)
+      kern_n<KIND, 2 * NBT, KIND != IWVI_KERN_RBF>(kv, dkv, variance);
       double rs = 0.0;
       const bool mvalid = mg < M;
 #pragma unroll
@@ -232,9 +234,14 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           const bool valid = mvalid && (n0 + 8 * b + 2 * t + c < T);
-          const double bbv = 2.0 * bb[b][c];
-          const double G = valid ? bbv * dkv[b * 2 + c] : 0.0;
-          if (valid) dvar_acc = fma(bbv, kv[b * 2 + c], dvar_acc);
+          double G;
+          if (KIND == IWVI_KERN_RBF) {
+            G = valid ? -(bb[b][c] * kv[b * 2 + c]) : 0.0;
+          } else {
+            const double bbv = 2.0 * bb[b][c];
+            G = valid ? bbv * dkv[b * 2 + c] : 0.0;
+            if (valid) dvar_acc = fma(bbv, kv[b * 2 + c], dvar_acc);
+          }
           acc[b][c] = G;
           cs[b][c] += G;
           rs += G;
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, GRAM_CTAS_PER_SM) gp_gram_bwd_ke
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         double v = cs[b][c];
+        if (KIND == IWVI_KERN_RBF) dvar_acc = fma(-2.0, v, dvar_acc);     // sum Bbar K over this thread's entries of the strip
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
